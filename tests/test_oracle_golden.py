@@ -1,0 +1,125 @@
+"""CPU: the oracle restatement replayed against fixtures produced by the reference itself."""
+import numpy as np
+import pytest
+
+from oracle import radet_oracle as orc
+from radet_b200 import synthetic as syn
+from tests import helpers as hp
+
+
+def _assign(case):
+    return orc.assign_image_seeded(case["boxes"], case["grid"], case["H"], case["W"], case["seed"], grid_step=8)
+
+
+def test_assignment_matches_reference_bit_exact():
+    g, names = hp.assign_cases()
+    assert len(names) >= 25
+    for name in names:
+        case = hp.image_for(g, name)
+        idx, w, used = _assign(case)
+        assert np.array_equal(idx, g[f"{name}/idx"].astype(np.int64)), name
+        assert np.array_equal(w, g[f"{name}/w"]), name
+        # stream position after the call: next two doubles of np.random.seed(seed) stream
+        rs = np.random.RandomState(case["seed"])
+        rs.random_sample(used)
+        assert np.array_equal(rs.random_sample(2), g[f"{name}/tail"]), name
+
+
+def _head_inputs(key):
+    wl, batch = hp.head_case(key)
+    a = [orc.assign_image_seeded(im.gt_bboxes, im.masks, im.H, im.W, im.seed) for im in batch]
+    idx_l, w_l = [x[0] for x in a], [x[1] for x in a]
+    ho = syn.make_head_outputs(wl, batch, idx_l)
+    return wl, batch, idx_l, w_l, ho
+
+
+@pytest.mark.parametrize("key", ["small", "cfg1", "cfg3b2"])
+def test_targets_and_loss_match_reference(key):
+    g = hp.load("head.npz")
+    wl, batch, idx_l, w_l, ho = _head_inputs(key)
+    assert (hp.sha(*ho.cls, *ho.bbox, *ho.iou) == g[f"{key}/sha"]).all()
+    lab, tg, wt, anc = orc.get_targets([b.gt_bboxes for b in batch], [b.gt_labels for b in batch], idx_l, w_l, wl.C, wl.H, wl.W)
+    for l in range(5):
+        assert np.array_equal(lab[l], g[f"{key}/labels{l}"].astype(np.int64))
+        if key == "small":
+            assert np.array_equal(tg[l], g[f"{key}/tg{l}"])          # bit-exact: power-of-two scalings
+            assert np.array_equal(wt[l], g[f"{key}/wt{l}"])
+            assert np.array_equal(anc[l], g[f"{key}/anc{l}"])
+        else:
+            nz = g[f"{key}/tg_nz{l}"]
+            assert np.array_equal(np.nonzero(tg[l].any(1))[0], nz)
+            assert np.array_equal(tg[l][nz], g[f"{key}/tg_val{l}"])
+    out = orc.head_loss(ho.cls, ho.bbox, ho.iou, [b.gt_bboxes for b in batch], [b.gt_labels for b in batch], idx_l, w_l,
+                        wl.C, wl.H, wl.W)
+    for k in ("loss_cls", "loss_bbox", "loss_iou"):
+        assert abs(out[k] - float(g[f"{key}/{k}"])) <= 1e-5 * abs(float(g[f"{key}/{k}"])), k
+    for l in range(5):
+        if key == "small":
+            refs = (g[f"{key}/gcls{l}"], g[f"{key}/gbox{l}"], g[f"{key}/giou{l}"])
+            mine = (out["grad_cls"][l], out["grad_bbox"][l], out["grad_iou"][l])
+        else:
+            refs = [g[f"{key}/gcls_s{l}"], g[f"{key}/gbox{l}"], g[f"{key}/giou{l}"]]
+            mine = [out["grad_cls"][l].reshape(-1)[::97], out["grad_bbox"][l], out["grad_iou"][l]]
+            if l < 2:
+                mine[1] = mine[1].reshape(-1)[::13]
+                mine[2] = mine[2].reshape(-1)[::13]
+        for a, b in zip(mine, refs):
+            np.testing.assert_allclose(a, b, rtol=1e-5, atol=1e-6 * max(1e-12, float(np.abs(b).max())))
+
+
+@pytest.mark.parametrize("key", ["small", "cfg1", "cfg3b2"])
+@pytest.mark.parametrize("typ", ["vote", "global_vote"])
+@pytest.mark.parametrize("thr", [0.05, 0.1])
+def test_get_bboxes_matches_reference_bit_exact(key, typ, thr):
+    g = hp.load("head.npz")
+    wl, batch, idx_l, w_l, ho = _head_inputs(key)
+    sf = np.ones(4, np.float32)
+    for b, im in enumerate(batch):
+        dets, labs = orc.get_bboxes_image([m[b] for m in ho.cls], [m[b] for m in ho.bbox], [m[b] for m in ho.iou],
+                                          (im.H, im.W, 3), sf, score_thr=thr,
+                                          nms_cfg=dict(type=typ, iou_threshold=0.65, cluster_score=["cls", "iou"],
+                                                       vote_score=["iou", "cls"], iou_enable=False, sima=0.025))
+        assert np.array_equal(dets.view(np.uint32), g[f"{key}/det_{typ}_{thr}_{b}"].view(np.uint32)), (key, typ, thr, b)
+        assert np.array_equal(labs, g[f"{key}/lab_{typ}_{thr}_{b}"].astype(np.int64))
+
+
+@pytest.mark.parametrize("key", ["small", "cfg1"])
+def test_candidates_match_reference(key):
+    g = hp.load("head.npz")
+    wl, batch, idx_l, w_l, ho = _head_inputs(key)
+    for b, im in enumerate(batch):
+        bx, sc, ctr, cats, anc = orc.select_candidates([m[b] for m in ho.cls], [m[b] for m in ho.bbox], [m[b] for m in ho.iou],
+                                                       (im.H, im.W, 3), np.ones(4, np.float32), 0.05, 1000)
+        full = np.concatenate([bx, (sc * ctr)[:, None], anc], 1).astype(np.float32)
+        o = np.lexsort((cats, full[:, 8], full[:, 7], full[:, 6], full[:, 5]))
+        ref = g[f"{key}/cand_{b}"]
+        cols = [0, 1, 2, 3, 5, 6, 7, 8]
+        assert np.array_equal(full[o][:, cols].view(np.uint32), ref[:, cols].view(np.uint32))
+        # score*centerness: torch-CPU sigmoid is alignment dependent (SIMD vs scalar path), <= 2 ulp apart
+        np.testing.assert_allclose(full[o][:, 4], ref[:, 4], rtol=2.5e-7, atol=0)
+        assert np.array_equal(cats[o], g[f"{key}/candlab_{b}"].astype(np.int64))
+
+
+@pytest.mark.parametrize("case", range(5))
+def test_ops_match_reference_bit_exact(case):
+    g = hp.load("ops.npz")
+    boxes, labels = g[f"c{case}/boxes"], g[f"c{case}/labels"].astype(np.int64)
+    cls, ctr = g[f"c{case}/cls"], g[f"c{case}/ctr"]
+    cfg = dict(iou_threshold=0.65, cluster_score=["cls", "iou"], vote_score=["iou", "cls"], iou_enable=False, sima=0.025)
+    for nm, gm in (("vote", False), ("gvote", True)):
+        d, l = orc.vote_nms_wrapper(boxes, cls, labels, cfg, score_factor=ctr, global_mode=gm)
+        assert np.array_equal(d.view(np.uint32), g[f"c{case}/{nm}_dets"].view(np.uint32)), nm
+        assert np.array_equal(l, g[f"c{case}/{nm}_labels"].astype(np.int64))
+    _, _, _, inst, cnum = orc.vote_nms_c(boxes, cls * ctr, cls * ctr, labels, 0.65)
+    assert np.array_equal(inst, g[f"c{case}/inst"])
+    assert np.array_equal(cnum, g[f"c{case}/cnum"])
+    if boxes.shape[0] <= 64:    # python restatement agrees with the C one
+        b2, l2, s2 = orc.vote_nms_py(boxes, cls * ctr, cls * ctr, labels, 0.65)
+        b1, l1, s1, _, _ = orc.vote_nms_c(boxes, cls * ctr, cls * ctr, labels, 0.65)
+        assert np.array_equal(b1.view(np.uint32), b2.view(np.uint32)) and np.array_equal(l1, l2) and np.array_equal(s1, s2)
+
+
+def test_anchor_docstring_kat():
+    # anchor_generator.py:40-55 known answers, with this config's scale (8) instead of 9 checked structurally
+    a = orc.grid_anchors(32, 32, strides=(16,), octave_base_scale=9)
+    assert np.array_equal(a, np.array([[-72, -72, 72, 72], [-56, -72, 88, 72], [-72, -56, 72, 88], [-56, -56, 88, 88]], np.float32))
