@@ -1,0 +1,672 @@
+// Visibility-guided sample assignment on sm_100a.
+//
+// Reference semantics: radet/datasets/pipelines/label_assignment.py:57-201 (numpy, one image at a time in a
+// DataLoader worker).  Here a whole batch is assigned in two launches:
+//
+//   assign_pairs    grid (ceil(P/256), B): every point x GT pair test (inside-box, level range, visible bit).
+//                   GT boxes (area-sorted) and the image's bit-packed visible masks are staged in shared memory
+//                   with one TMA bulk copy each; the result is two bit sets per point (candidate / visible
+//                   candidate, bit r = GT of area rank r).
+//   assign_resolve  one CTA per image: resolves the sequential min-area claiming as a fixed point over the set of
+//                   "fallback" GTs (no visible unclaimed candidate), ranks members, draws the numpy-legacy
+//                   weighted choice from an MT19937 stream, writes points_to_gt_index / points_weight.
+//
+// Why the claiming is a fixed point: GT r (area order) claims N_r = R_r&vis if any(R_r&vis) else R_r, where
+// R_r = candidates not claimed by smaller GTs.  Let F = {r : no visible unclaimed candidate}.  Then the owner of
+// point p is the lowest set bit of  vis[p] | (cand[p] & F), and r is in F iff no point is owned by r through a
+// visible bit.  A(F) = {owners through visible bits} is monotone decreasing in F, so iterating
+// F <- ~A(F) from F = {} converges (usually in 2 passes) to the unique solution, which is the sequential one.
+#include "common.cuh"
+
+namespace radet {
+
+// ------------------------------------------------------------------------------------------------ mask packing
+__global__ void pack_masks_kernel(const uint8_t* __restrict__ src, int64_t num_gt, int src_h, int src_w, int step,
+                                  int grid_h, int grid_w, int pitch, uint32_t* __restrict__ bits,
+                                  int* __restrict__ status) {
+  // one warp per output word: lane i tests sample gx = word*32 + i
+  const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  const int64_t total = num_gt * grid_h * pitch;
+  if (warp >= total) return;
+  const int wx = (int)(warp % pitch);
+  const int gy = (int)((warp / pitch) % grid_h);
+  const int64_t g = warp / ((int64_t)pitch * grid_h);
+  const int gx = wx * 32 + lane;
+  int v = 0;
+  if (gx < grid_w) {
+    const int sy = gy * step, sx = gx * step;
+    if (sy < src_h && sx < src_w) v = src[(g * src_h + sy) * (int64_t)src_w + sx];
+  }
+  const unsigned word = __ballot_sync(kFull, v != 0);
+  // binary-mask check (cheap, per word): two different non-zero values -> not a visible mask
+  const int vmax = __reduce_max_sync(kFull, v);
+  const int vmin = __reduce_min_sync(kFull, v ? v : 256);
+  if (lane == 0) {
+    bits[warp] = word;
+    if (status && word && vmin != vmax) atomicOr(status, 1);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ MT19937 (numpy legacy)
+struct MtWarp {
+  // 624-word key in shared memory, driven by ONE warp.  pos = next unread word (624 = exhausted).
+  uint32_t* key;
+  int pos;
+
+  __device__ static uint32_t temper(uint32_t y) {
+    y ^= (y >> 11);
+    y ^= (y << 7) & 0x9d2c5680u;
+    y ^= (y << 15) & 0xefc60000u;
+    y ^= (y >> 18);
+    return y;
+  }
+  __device__ static uint32_t tw(uint32_t a, uint32_t b) {
+    const uint32_t y = (a & 0x80000000u) | (b & 0x7fffffffu);
+    return (y >> 1) ^ ((y & 1u) ? 0x9908b0dfu : 0u);
+  }
+  // numpy mt19937_seed(): init_genrand recurrence; inherently sequential (lane 0).
+  __device__ void seed(uint32_t s, int lane) {
+    if (lane == 0) {
+      for (int i = 0; i < 624; ++i) {
+        key[i] = s;
+        s = 1812433253u * (s ^ (s >> 30)) + (uint32_t)(i + 1);
+      }
+    }
+    pos = 624;
+    __syncwarp();
+  }
+  // mt19937_gen(): regenerate the block, warp-parallel in three dependent phases.
+  __device__ void twist(int lane) {
+    for (int base = 0; base < 227; base += 32) {  // key[k] = key[k+397] ^ tw(key[k], key[k+1])
+      const int k = base + lane;
+      uint32_t v = 0;
+      if (k < 227) v = key[k + 397] ^ tw(key[k], key[k + 1]);
+      __syncwarp();
+      if (k < 227) key[k] = v;
+      __syncwarp();
+    }
+    for (int base = 227; base < 623; base += 32) {  // key[k] = key[k-227] ^ tw(key[k], key[k+1])
+      const int k = base + lane;
+      uint32_t v = 0;
+      if (k < 623) v = key[k - 227] ^ tw(key[k], key[k + 1]);
+      __syncwarp();
+      if (k < 623) key[k] = v;
+      __syncwarp();
+    }
+    if (lane == 0) key[623] = key[396] ^ tw(key[623], key[0]);
+    __syncwarp();
+  }
+  // Lane i < count receives the i-th of the next `count` doubles of random_sample() (count <= 32).
+  __device__ double draw(int count, int lane) {
+    const int qa = pos + 2 * lane, qb = qa + 1;
+    uint32_t a = 0, b = 0;
+    const bool act = lane < count;
+    if (act && qa < 624) a = key[qa];
+    if (act && qb < 624) b = key[qb];
+    __syncwarp();
+    if (pos + 2 * count > 624) {
+      twist(lane);
+      if (act && qa >= 624) a = key[qa - 624];
+      if (act && qb >= 624) b = key[qb - 624];
+      pos = pos + 2 * count - 624;
+    } else {
+      pos += 2 * count;
+    }
+    __syncwarp();
+    const uint32_t ha = temper(a) >> 5, hb = temper(b) >> 6;
+    return ((double)ha * 67108864.0 + (double)hb) / 9007199254740992.0;
+  }
+};
+
+__global__ void mt19937_uniforms_kernel(const uint32_t* __restrict__ seeds, int n, double* __restrict__ out) {
+  __shared__ uint32_t key[624];
+  const int lane = threadIdx.x;
+  MtWarp mt{key, 624};
+  mt.seed(seeds[blockIdx.x], lane);
+  double* o = out + (int64_t)blockIdx.x * n;
+  for (int base = 0; base < n; base += 32) {
+    const int cnt = min(32, n - base);
+    const double u = mt.draw(cnt, lane);
+    if (lane < cnt) o[base + lane] = u;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ pair tests
+constexpr int kPairThreads = 256;
+
+// stable ascending-area rank (label_assignment.py:156,170): rank = #{k : a_k < a_g or (a_k == a_g and k < g)}
+__device__ __forceinline__ void area_ranks(const float* __restrict__ boxes, int G, float* s_area, int* s_rank2gt) {
+  for (int g = threadIdx.x; g < G; g += blockDim.x) {
+    const float4 b = *reinterpret_cast<const float4*>(boxes + 4 * g);
+    s_area[g] = __fmul_rn(b.z - b.x, b.w - b.y);
+  }
+  __syncthreads();
+  for (int g = threadIdx.x; g < G; g += blockDim.x) {
+    const float a = s_area[g];
+    int r = 0;
+    for (int k = 0; k < G; ++k) r += (s_area[k] < a || (s_area[k] == a && k < g)) ? 1 : 0;
+    s_rank2gt[r] = g;
+  }
+  __syncthreads();
+}
+
+template <int W32>
+__global__ void __launch_bounds__(kPairThreads)
+assign_pairs_kernel(GridDev grid, const int* __restrict__ gt_offsets, const float* __restrict__ gt_bboxes,
+                    const uint32_t* __restrict__ mask_bits, int mask_h, int mask_pitch, int mask_step, int stage_masks,
+                    uint32_t* __restrict__ pair_bits /* [B][P][2*W32] */) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int b = blockIdx.y;
+  const int P = grid.off[grid.num_levels];
+  const int g0 = gt_offsets[b], G = gt_offsets[b + 1] - g0;
+  const int p = blockIdx.x * kPairThreads + threadIdx.x;
+  uint32_t* out = pair_bits + ((int64_t)b * P + p) * (2 * W32);
+  if (G <= 0) {
+    if (p < P) {
+#pragma unroll
+      for (int w = 0; w < 2 * W32; ++w) out[w] = 0u;
+    }
+    return;
+  }
+  // shared: raw boxes [G][4] (TMA destination) | sorted boxes [G] float4 | area [G] | rank2gt [G] | mbarrier | masks
+  const int Gp = (G + 3) & ~3;
+  float* s_raw = reinterpret_cast<float*>(smem_raw);
+  float4* s_box = reinterpret_cast<float4*>(s_raw + 4 * Gp);
+  float* s_area = reinterpret_cast<float*>(s_box + Gp);
+  int* s_rank2gt = reinterpret_cast<int*>(s_area + Gp);
+  uint64_t* s_bar = reinterpret_cast<uint64_t*>(s_rank2gt + Gp);
+  uint32_t* s_mask = reinterpret_cast<uint32_t*>(s_bar + 2);
+  const int words_per_gt = mask_h * mask_pitch;
+  const uint32_t box_bytes = (uint32_t)G * 16u;
+  const uint32_t mask_bytes = (uint32_t)G * (uint32_t)words_per_gt * 4u;
+  // TMA bulk staging needs 16-byte aligned source + size; the per-image slices are (16 B boxes; masks checked on host)
+  const uint32_t* img_masks = mask_bits + (int64_t)g0 * words_per_gt;
+  const bool tma_masks = stage_masks && (mask_bytes % 16u == 0) && ((reinterpret_cast<uintptr_t>(img_masks) & 15) == 0);
+  if (threadIdx.x == 0) {
+    mbar_init(s_bar, 1);
+    fence_barrier_init();
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    mbar_expect_tx(s_bar, box_bytes + (tma_masks ? mask_bytes : 0u));
+    tma_bulk_g2s(s_raw, gt_bboxes + 4 * (int64_t)g0, box_bytes, s_bar);
+    if (tma_masks) tma_bulk_g2s(s_mask, img_masks, mask_bytes, s_bar);
+  }
+  if (stage_masks && !tma_masks) {
+    for (int i = threadIdx.x; i < G * words_per_gt; i += kPairThreads) s_mask[i] = img_masks[i];
+  }
+  const uint32_t* mask_src = stage_masks ? s_mask : img_masks;  // huge G x resolution: read the bits through L2 instead
+  mbar_wait(s_bar, 0);
+  area_ranks(s_raw, G, s_area, s_rank2gt);
+  for (int r = threadIdx.x; r < G; r += kPairThreads) s_box[r] = *reinterpret_cast<const float4*>(s_raw + 4 * s_rank2gt[r]);
+  __syncthreads();
+  if (p >= P) return;
+
+  const int l = level_of(grid, p);
+  const int q = p - grid.off[l];
+  const int y = q / grid.w[l], x = q - y * grid.w[l];
+  const int s = grid.stride[l];
+  const float cx = (float)(x * s), cy = (float)(y * s);
+  const float lo = grid.lo[l], hi = grid.hi[l];
+  const int my = (y * s) / mask_step, mx = (x * s) / mask_step;  // int(cy), int(cx) on the sample grid
+  const int mword = my * mask_pitch + (mx >> 5);
+  const uint32_t mbit = 1u << (mx & 31);
+
+  uint32_t c[W32], v[W32];
+#pragma unroll
+  for (int w = 0; w < W32; ++w) c[w] = v[w] = 0u;
+#pragma unroll
+  for (int w = 0; w < W32; ++w) {
+    const int rend = min(G, (w + 1) * 32);
+    for (int r = w * 32; r < rend; ++r) {
+      const float4 bx = s_box[r];
+      const float le = cx - bx.x, ri = bx.z - cx, to = cy - bx.y, bo = bx.w - cy;  // label_assignment.py:65-68
+      const float mn = fminf(fminf(le, to), fminf(ri, bo));
+      const float mxs = fmaxf(fmaxf(le, to), fmaxf(ri, bo));
+      if (mn > 0.01f && mxs >= lo && mxs <= hi) {                                   // :71-75
+        c[w] |= 1u << (r & 31);
+        if (mask_src[s_rank2gt[r] * words_per_gt + mword] & mbit) v[w] |= 1u << (r & 31);
+      }
+    }
+  }
+  if (W32 == 1) {
+    *reinterpret_cast<uint2*>(out) = make_uint2(c[0], v[0]);
+  } else {
+#pragma unroll
+    for (int w = 0; w < W32; ++w) {
+      out[w] = c[w];
+      out[W32 + w] = v[w];
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ resolve + sample
+constexpr int kResolveThreads = 1024;
+constexpr int kListCap = 16384;  // shared-memory capacity of the candidate-point list
+
+// t = max{c in [0,m] : fl64(c/m) <= x}: position in numpy's normalised cumulative sum of m equal weights
+// (cdf[j] = fl64((j+1)*p / (m*p)) = fl64((j+1)/m) exactly, because both products are exact in binary64).
+__device__ __forceinline__ int cdf_search(double x, int m) {
+  long long t = (long long)(x * (double)m);
+  if (t < 0) t = 0;
+  if (t > m) t = m;
+  while (t < m && __ddiv_rn((double)(t + 1), (double)m) <= x) ++t;
+  while (t > 0 && __ddiv_rn((double)t, (double)m) > x) --t;
+  return (int)t;
+}
+
+struct ResolveSmem {
+  // fixed part; dynamic arrays follow (see resolve_smem_bytes)
+  uint32_t F[8], A[8];
+  int scan[34];
+  int M;
+  int changed;
+};
+
+__host__ __device__ inline size_t resolve_smem_bytes(int maxG, int K, bool list_in_smem) {
+  size_t s = sizeof(ResolveSmem);
+  s = (s + 15) & ~size_t(15);
+  s += 624 * 4;                             // MT key
+  s += (size_t)maxG * 4 * 3;                // area, rank2gt, n_r
+  s += (size_t)maxG * K * 4;                // sel_pos
+  s += (size_t)maxG * K;                    // sel_cnt
+  s += (size_t)maxG * 4;                    // n_sel
+  s = (s + 15) & ~size_t(15);
+  if (list_in_smem) s += (size_t)kListCap * 4 + (size_t)kListCap * 2;
+  return s;
+}
+
+template <int W32>
+__global__ void __launch_bounds__(kResolveThreads)
+assign_resolve_kernel(GridDev grid, const int* __restrict__ gt_offsets, const float* __restrict__ gt_bboxes,
+                      const uint32_t* __restrict__ pair_bits, int maxG, int K, int balance,
+                      const double* __restrict__ uniforms, int n_uniform, const uint32_t* __restrict__ seeds,
+                      uint32_t* __restrict__ mt_states, uint32_t* __restrict__ g_list, uint16_t* __restrict__ g_own,
+                      int list_in_smem, int64_t* __restrict__ out_idx, float* __restrict__ out_w,
+                      int* __restrict__ consumed) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  const int P = grid.off[grid.num_levels];
+  const int g0 = gt_offsets[b], G = gt_offsets[b + 1] - g0;
+  int64_t* idx = out_idx + (int64_t)b * P;
+  float* wt = out_w + (int64_t)b * P;
+
+  ResolveSmem* S = reinterpret_cast<ResolveSmem*>(smem_raw);
+  unsigned char* cur = smem_raw + ((sizeof(ResolveSmem) + 15) & ~size_t(15));
+  uint32_t* s_key = reinterpret_cast<uint32_t*>(cur); cur += 624 * 4;
+  float* s_area = reinterpret_cast<float*>(cur); cur += (size_t)maxG * 4;
+  int* s_rank2gt = reinterpret_cast<int*>(cur); cur += (size_t)maxG * 4;
+  int* s_nr = reinterpret_cast<int*>(cur); cur += (size_t)maxG * 4;
+  int* s_selpos = reinterpret_cast<int*>(cur); cur += (size_t)maxG * K * 4;
+  int* s_nsel = reinterpret_cast<int*>(cur); cur += (size_t)maxG * 4;
+  unsigned char* s_selcnt = cur; cur += (size_t)maxG * K;
+  cur = smem_raw + (((size_t)(cur - smem_raw) + 15) & ~size_t(15));
+  uint32_t* list;
+  uint16_t* own;
+  if (list_in_smem) {
+    list = reinterpret_cast<uint32_t*>(cur);
+    own = reinterpret_cast<uint16_t*>(cur + (size_t)kListCap * 4);
+  } else {
+    list = g_list + (int64_t)b * P;
+    own = g_own + (int64_t)b * P;
+  }
+
+  if (G <= 0) {  // label_assignment.py:166-167 defaults
+    for (int p = tid; p < P; p += kResolveThreads) {
+      idx[p] = -1;
+      wt[p] = 1.0f;
+    }
+    if (tid == 0) consumed[b] = 0;
+    return;
+  }
+  area_ranks(gt_bboxes + 4 * (int64_t)g0, G, s_area, s_rank2gt);
+  for (int r = tid; r < G; r += kResolveThreads) {
+    s_nr[r] = 0;
+    s_nsel[r] = 0;
+  }
+  if (tid < 8) S->F[tid] = 0u;
+
+  const uint32_t* bits = pair_bits + (int64_t)b * P * (2 * W32);
+  // 1. ordered compaction of points that are a candidate of at least one GT; everything else keeps the defaults
+  int M = 0;
+  for (int base = 0; base < P; base += kResolveThreads) {
+    const int p = base + tid;
+    int flag = 0;
+    if (p < P) {
+      uint32_t any = 0;
+#pragma unroll
+      for (int w = 0; w < W32; ++w) any |= bits[(int64_t)p * (2 * W32) + w];
+      flag = any != 0u;
+      if (!flag) {
+        idx[p] = -1;
+        wt[p] = 1.0f;
+      }
+    }
+    int total;
+    const int pos = block_exclusive_scan(flag, S->scan, &total);
+    if (flag) list[M + pos] = (uint32_t)p;
+    M += total;
+  }
+  __syncthreads();
+
+  // 2. fixed point over the fallback set F
+  for (int round = 0; round <= G; ++round) {
+    if (tid < 8) S->A[tid] = 0u;
+    if (tid == 0) S->changed = 0;
+    __syncthreads();
+    uint32_t acc[W32];
+#pragma unroll
+    for (int w = 0; w < W32; ++w) acc[w] = 0u;
+    for (int e = tid; e < M; e += kResolveThreads) {
+      const uint32_t* pb = bits + (int64_t)list[e] * (2 * W32);
+#pragma unroll
+      for (int w = 0; w < W32; ++w) {
+        const uint32_t c = pb[w], v = pb[W32 + w];
+        const uint32_t cl = v | (c & S->F[w]);
+        if (cl) {
+          const uint32_t low = cl & (0u - cl);
+          if (v & low) acc[w] |= low;
+          break;
+        }
+      }
+    }
+#pragma unroll
+    for (int w = 0; w < W32; ++w) {
+      const uint32_t r = __reduce_or_sync(kFull, acc[w]);
+      if (lane == 0 && r) atomicOr(&S->A[w], r);
+    }
+    __syncthreads();
+    if (tid < W32) {
+      const int rem = G - tid * 32;
+      const uint32_t valid = rem >= 32 ? 0xffffffffu : (rem <= 0 ? 0u : ((1u << rem) - 1u));
+      const uint32_t nf = ~S->A[tid] & valid;
+      if (nf != S->F[tid]) {
+        S->F[tid] = nf;
+        S->changed = 1;
+      }
+    }
+    __syncthreads();
+    const int changed = S->changed;
+    __syncthreads();
+    if (!changed) break;
+  }
+
+  // 3. owners, member counts; unclaimed candidate points keep the defaults
+  for (int e = tid; e < M; e += kResolveThreads) {
+    const int p = (int)list[e];
+    const uint32_t* pb = bits + (int64_t)p * (2 * W32);
+    int r = -1;
+#pragma unroll
+    for (int w = 0; w < W32; ++w) {
+      const uint32_t cl = pb[W32 + w] | (pb[w] & S->F[w]);
+      if (cl) {
+        r = w * 32 + __ffs((int)cl) - 1;
+        break;
+      }
+    }
+    own[e] = (uint16_t)(r < 0 ? 0xffff : r);
+    if (r >= 0) {
+      atomicAdd(&s_nr[r], 1);
+    } else {
+      idx[p] = -1;
+      wt[p] = 1.0f;
+    }
+  }
+  __syncthreads();
+
+  // 4. numpy-legacy weighted choice per GT, in area order, from one sequential MT19937 stream (warp 0)
+  if (wid == 0) {
+    MtWarp mt{s_key, 624};
+    const double* ub = uniforms ? uniforms + (int64_t)b * n_uniform : nullptr;
+    if (!ub) {
+      if (mt_states) {
+        const uint32_t* st = mt_states + (int64_t)b * RADET_MT_STATE_WORDS;
+        for (int i = lane; i < 624; i += 32) s_key[i] = st[i];
+        mt.pos = (int)st[624];
+        __syncwarp();
+      } else {
+        mt.seed(seeds[b], lane);
+      }
+    }
+    int used = 0;
+    bool overflow = false;
+    auto draw = [&](int count) -> double {
+      double u = 0.0;
+      if (ub) {
+        if (used + count > n_uniform) overflow = true;
+        else if (lane < count) u = ub[used + lane];
+      } else {
+        u = mt.draw(count, lane);
+      }
+      used += count;
+      return u;
+    };
+    for (int r = 0; r < G && !overflow; ++r) {
+      const int n = s_nr[r];
+      if (n == 0) continue;                                         // label_assignment.py:182-183: no RNG use
+      int* selpos = s_selpos + r * K;
+      unsigned char* selcnt = s_selcnt + r * K;
+      if (n < K) {
+        if (!balance) {                                             // :116 chosen = arange(n)
+          if (lane == 0) s_nsel[r] = -1;
+          continue;
+        }
+        const double x = draw(K);                                   // :112 choice(n, K, p, replace=True)
+        if (overflow) break;
+        const int c = lane < K ? cdf_search(x, n) : -1;
+        int cnt = 0;
+        bool first = lane < K;
+        for (int j = 0; j < K; ++j) {
+          const int cj = __shfl_sync(kFull, c, j);
+          if (lane < K && cj == c) {
+            ++cnt;
+            if (j < lane) first = false;
+          }
+        }
+        const unsigned fm = __ballot_sync(kFull, first);
+        if (first) {
+          const int slot = __popc(fm & ((1u << lane) - 1u));
+          selpos[slot] = c;
+          selcnt[slot] = (unsigned char)cnt;
+        }
+        if (lane == 0) s_nsel[r] = __popc(fm);
+      } else {                                                      // :119 choice(n, K, p, replace=False)
+        int found = -1;  // lane k holds found[k]
+        int n_uniq = 0;
+        while (n_uniq < K) {
+          const int d = K - n_uniq, m = n - n_uniq;
+          const double x = draw(d);
+          if (overflow) break;
+          int pos = -1;
+          if (lane < d) {
+            const int t = cdf_search(x, m);  // rank among the not-yet-found entries
+            pos = t;
+          }
+          // skip over found entries: pos = t + #{f in found : f <= pos}, iterated to its fixed point
+          {
+            const int base = pos;
+            int cur_pos = base;
+            for (int it = 0; it <= n_uniq; ++it) {
+              int le = 0;
+              for (int j = 0; j < n_uniq; ++j) {
+                const int f = __shfl_sync(kFull, found, j);
+                le += (f <= cur_pos) ? 1 : 0;
+              }
+              const int nxt = base + le;
+              const bool same = (nxt == cur_pos);
+              cur_pos = nxt;
+              if (__all_sync(kFull, same || lane >= d)) break;
+            }
+            pos = cur_pos;
+          }
+          // keep the first occurrence of each value, in draw order
+          bool first = lane < d;
+          for (int j = 0; j < d; ++j) {
+            const int pj = __shfl_sync(kFull, pos, j);
+            if (lane < d && j < lane && pj == pos) first = false;
+          }
+          const unsigned fm = __ballot_sync(kFull, first);
+          const int slot = n_uniq + __popc(fm & ((1u << lane) - 1u));
+          // scatter: lane `slot` must receive pos of this lane
+          for (int j = 0; j < d; ++j) {
+            const int pj = __shfl_sync(kFull, pos, j);
+            const int sj = __shfl_sync(kFull, slot, j);
+            const bool fj = (fm >> j) & 1u;
+            if (fj && lane == sj) found = pj;
+          }
+          n_uniq += __popc(fm);
+        }
+        if (overflow) break;
+        if (lane < K) {
+          selpos[lane] = found;
+          selcnt[lane] = 1;
+        }
+        if (lane == 0) s_nsel[r] = K;
+      }
+      __syncwarp();
+    }
+    if (lane == 0) consumed[b] = overflow ? -1 : used;
+    if (!ub && mt_states) {  // hand the advanced generator back
+      uint32_t* st = mt_states + (int64_t)b * RADET_MT_STATE_WORDS;
+      for (int i = lane; i < 624; i += 32) st[i] = s_key[i];
+      if (lane == 0) st[624] = (uint32_t)mt.pos;
+    }
+  }
+  __syncthreads();
+
+  // 5. one warp per GT: walk its members in ascending point order, selected -> positive, others -> ignore
+  for (int r = wid; r < G; r += kResolveThreads / 32) {
+    if (s_nr[r] == 0) continue;
+    const int gt1 = s_rank2gt[r] + 1;
+    const int nsel = s_nsel[r];
+    const int* selpos = s_selpos + r * K;
+    const unsigned char* selcnt = s_selcnt + r * K;
+    int running = 0;
+    for (int base = 0; base < M; base += 32) {
+      const int e = base + lane;
+      const bool mine = e < M && own[e] == (uint16_t)r;
+      const unsigned ball = __ballot_sync(kFull, mine);
+      if (mine) {
+        const int mpos = running + __popc(ball & ((1u << lane) - 1u));
+        int cnt = 0;
+        if (nsel < 0) cnt = 1;
+        for (int j = 0; j < nsel; ++j)
+          if (selpos[j] == mpos) cnt = selcnt[j];
+        const int p = (int)list[e];
+        idx[p] = cnt > 0 ? gt1 : 0;          // label_assignment.py:193-194
+        wt[p] = (float)cnt;                  // :195-196
+      }
+      running += __popc(ball);
+    }
+  }
+}
+
+}  // namespace radet
+
+// ================================================================================================ C ABI
+using namespace radet;
+
+extern "C" int radet_pack_masks(const uint8_t* src, int64_t num_gt, int32_t src_h, int32_t src_w, int32_t step,
+                                int32_t grid_h, int32_t grid_w, uint32_t* bits, int32_t* status, void* stream) {
+  if (num_gt == 0) return RADET_OK;
+  if (!src || !bits || num_gt < 0 || src_h <= 0 || src_w <= 0 || step <= 0 || grid_h <= 0 || grid_w <= 0) return RADET_E_BADARG;
+  const int pitch = (grid_w + 31) / 32;
+  const int64_t warps = num_gt * grid_h * pitch;
+  const int threads = 256;
+  const int64_t blocks = (warps * 32 + threads - 1) / threads;
+  pack_masks_kernel<<<(unsigned)blocks, threads, 0, (cudaStream_t)stream>>>(src, num_gt, src_h, src_w, step, grid_h, grid_w,
+                                                                           pitch, bits, status);
+  RADET_LAUNCH_CHECK();
+  return RADET_OK;
+}
+
+extern "C" int radet_mt19937_uniforms(const uint32_t* seeds, int32_t batch, int32_t n, double* out, void* stream) {
+  if (batch == 0 || n == 0) return RADET_OK;
+  if (!seeds || !out || batch < 0 || n < 0) return RADET_E_BADARG;
+  mt19937_uniforms_kernel<<<batch, 32, 0, (cudaStream_t)stream>>>(seeds, n, out);
+  RADET_LAUNCH_CHECK();
+  return RADET_OK;
+}
+
+static int words_for(int maxG) { return maxG <= 32 ? 1 : maxG <= 64 ? 2 : maxG <= 128 ? 4 : 8; }
+
+extern "C" size_t radet_assign_workspace_bytes(const radet_grid_t* grid, int32_t batch) {
+  GridDev g;
+  if (make_grid_dev(grid, &g) != RADET_OK || batch <= 0) return 0;
+  const size_t P = (size_t)g.off[g.num_levels];
+  // pair bits (worst case 8 words x 2) + global fallback list (u32) + owners (u16)
+  return align_up((size_t)batch * P * 16 * 4, 256) + align_up((size_t)batch * P * 4, 256) + align_up((size_t)batch * P * 2, 256);
+}
+
+extern "C" int radet_assign(const radet_grid_t* grid, int32_t batch, const int32_t* gt_offsets, const int32_t* gt_offsets_host,
+                            const float* gt_bboxes, const uint32_t* mask_bits, int32_t mask_h, int32_t mask_w,
+                            int32_t mask_step, const double* uniforms, int32_t n_uniform, const uint32_t* seeds,
+                            uint32_t* mt_states, int32_t positive_num, int32_t balance_sample, int64_t* points_to_gt_index,
+                            float* points_weight, int32_t* consumed, void* workspace, size_t workspace_bytes, void* stream) {
+  GridDev g;
+  int rc = make_grid_dev(grid, &g);
+  if (rc != RADET_OK) return rc;
+  if (batch == 0) return RADET_OK;
+  if (batch < 0 || !gt_offsets || !gt_offsets_host || !points_to_gt_index || !points_weight || !consumed || !workspace)
+    return RADET_E_BADARG;
+  if (positive_num <= 0 || positive_num > RADET_MAX_POSITIVE_NUM) return RADET_E_UNSUPPORTED;
+  const int nrng = (uniforms ? 1 : 0) + (seeds ? 1 : 0) + (mt_states ? 1 : 0);
+  if (nrng != 1 || (uniforms && n_uniform < 0)) return RADET_E_BADARG;
+  int maxG = 0;
+  for (int b = 0; b < batch; ++b) {
+    const int G = gt_offsets_host[b + 1] - gt_offsets_host[b];
+    if (G < 0) return RADET_E_BADARG;
+    maxG = G > maxG ? G : maxG;
+  }
+  if (maxG > RADET_MAX_GT_PER_IMAGE) return RADET_E_TOO_MANY_GT;
+  if (maxG > 0 && (!gt_bboxes || !mask_bits || mask_h <= 0 || mask_w <= 0 || mask_step <= 0)) return RADET_E_BADARG;
+  for (int l = 0; l < g.num_levels && maxG > 0; ++l) {
+    if (g.stride[l] % mask_step != 0) return RADET_E_BADARG;  // sample grid must contain every (y*s, x*s)
+    if ((g.h[l] - 1) * g.stride[l] / mask_step >= mask_h || (g.w[l] - 1) * g.stride[l] / mask_step >= mask_w) return RADET_E_BADARG;
+  }
+  if (workspace_bytes < radet_assign_workspace_bytes(grid, batch) || (reinterpret_cast<uintptr_t>(workspace) & 255))
+    return RADET_E_WORKSPACE;
+  const int P = g.off[g.num_levels];
+  unsigned char* ws = static_cast<unsigned char*>(workspace);
+  uint32_t* pair_bits = reinterpret_cast<uint32_t*>(ws);
+  ws += align_up((size_t)batch * P * 16 * 4, 256);
+  uint32_t* g_list = reinterpret_cast<uint32_t*>(ws);
+  ws += align_up((size_t)batch * P * 4, 256);
+  uint16_t* g_own = reinterpret_cast<uint16_t*>(ws);
+  cudaStream_t st = (cudaStream_t)stream;
+  const int W = words_for(maxG > 0 ? maxG : 1);
+  const int mask_pitch = (mask_w + 31) / 32;
+  const int Gp = (maxG + 3) & ~3;
+  size_t pair_smem = (size_t)Gp * (16 + 16 + 4 + 4) + 16 + (size_t)maxG * mask_h * mask_pitch * 4 + 16;
+  int stage_masks = 1;
+  if (pair_smem > 96 * 1024) {  // keep >= 2 CTAs/SM; otherwise read mask bits through L2
+    stage_masks = 0;
+    pair_smem = (size_t)Gp * (16 + 16 + 4 + 4) + 32;
+  }
+  dim3 pgrid((P + kPairThreads - 1) / kPairThreads, batch);
+  const bool list_in_smem = P <= kListCap;
+  const int mg = maxG > 0 ? maxG : 1;
+  const size_t rs = resolve_smem_bytes(mg, positive_num, list_in_smem);
+#define RADET_ASSIGN_LAUNCH(WW)                                                                                          \
+  do {                                                                                                                   \
+    cudaFuncSetAttribute(assign_pairs_kernel<WW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pair_smem);          \
+    assign_pairs_kernel<WW><<<pgrid, kPairThreads, pair_smem, st>>>(g, gt_offsets, gt_bboxes, mask_bits, mask_h,         \
+                                                                     mask_pitch, mask_step, stage_masks, pair_bits);     \
+    RADET_LAUNCH_CHECK();                                                                                                \
+    cudaFuncSetAttribute(assign_resolve_kernel<WW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rs);               \
+    assign_resolve_kernel<WW><<<batch, kResolveThreads, rs, st>>>(g, gt_offsets, gt_bboxes, pair_bits, mg, positive_num, \
+                                                                   balance_sample, uniforms, n_uniform, seeds, mt_states, \
+                                                                   g_list, g_own, list_in_smem ? 1 : 0,                  \
+                                                                   points_to_gt_index, points_weight, consumed);         \
+    RADET_LAUNCH_CHECK();                                                                                                \
+  } while (0)
+  switch (W) {
+    case 1: RADET_ASSIGN_LAUNCH(1); break;
+    case 2: RADET_ASSIGN_LAUNCH(2); break;
+    case 4: RADET_ASSIGN_LAUNCH(4); break;
+    default: RADET_ASSIGN_LAUNCH(8); break;
+  }
+#undef RADET_ASSIGN_LAUNCH
+  return RADET_OK;
+}

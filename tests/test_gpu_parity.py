@@ -1,0 +1,426 @@
+"""GPU parity tests proper: the CUDA path (through the C ABI) against the oracle and the committed golden vectors.
+
+Bars: bit-exact for indices, labels, weights, targets, NMS keep sets and voted boxes; loss values within 1e-5
+relative, gradients within rtol 1e-4 + atol 1e-6*max|grad| of the fp32 oracle (and 2e-5 / 1e-7 of the fp64 oracle
+on the small case).
+"""
+import numpy as np
+import pytest
+import torch
+
+from oracle import radet_oracle as orc
+from radet_b200 import functional as F
+from radet_b200 import plugin as P
+from radet_b200 import synthetic as syn
+from tests import helpers as hp
+
+pytestmark = pytest.mark.gpu
+GEOM = F.Geometry()
+DEV = "cuda"
+
+
+def cuda_sigmoid(x):
+    return torch.sigmoid(torch.from_numpy(x).to(DEV)).cpu().numpy()
+
+
+@pytest.fixture(autouse=True)
+def _oracle_sigmoid():
+    # the reference runs .sigmoid() on CUDA tensors (radet_head.py:106-109); the oracle mirrors that here
+    orc.set_sigmoid(cuda_sigmoid)
+    yield
+    orc.set_sigmoid(None)
+
+
+# ------------------------------------------------------------------------------------------------ RNG
+def test_mt19937_matches_numpy():
+    seeds = [0, 1, 777, 12345, 2 ** 31 - 1, 4000000000]
+    n = 1500
+    out = F.mt19937_uniforms(torch.tensor(seeds, dtype=torch.int64, device=DEV), n).cpu().numpy()
+    for i, s in enumerate(seeds):
+        assert np.array_equal(out[i], np.random.RandomState(s).random_sample(n)), s
+
+
+# ------------------------------------------------------------------------------------------------ assignment
+def _assign_gpu(cases, mode="seeds"):
+    """cases: list of dicts from helpers.image_for sharing (H, W)."""
+    H, W = cases[0]["H"], cases[0]["W"]
+    shapes = GEOM.level_shapes(H, W)
+    counts = [c["boxes"].shape[0] for c in cases]
+    gh, gw = cases[0]["grid"].shape[1:] if cases[0]["grid"].ndim == 3 else (H // 8, W // 8)
+    boxes = torch.from_numpy(np.concatenate([c["boxes"].reshape(-1, 4) for c in cases]).astype(np.float32)).to(DEV)
+    grids = torch.from_numpy(np.concatenate([c["grid"].reshape(-1, gh, gw) for c in cases])).to(DEV)
+    bits = F.pack_masks(grids, 1, gh, gw) if grids.shape[0] else torch.zeros((0, gh, (gw + 31) // 32), dtype=torch.int32, device=DEV)
+    kw = {}
+    if mode == "seeds":
+        kw["seeds"] = torch.tensor([c["seed"] for c in cases], dtype=torch.int64, device=DEV)
+    elif mode == "uniforms":
+        kw["uniforms"] = torch.from_numpy(np.stack([np.random.RandomState(c["seed"]).random_sample(4096) for c in cases])).to(DEV)
+    idx, w, used = F.assign(GEOM, shapes, counts, boxes, bits, (gh, gw), **kw)
+    return idx.cpu().numpy(), w.cpu().numpy(), used.cpu().numpy()
+
+
+@pytest.mark.parametrize("mode", ["seeds", "uniforms"])
+def test_assignment_golden_bit_exact(mode):
+    g, names = hp.assign_cases()
+    by_shape = {}
+    for name in names:
+        c = hp.image_for(g, name)
+        c["name"] = name
+        by_shape.setdefault((c["H"], c["W"]), []).append(c)
+    for cases in by_shape.values():
+        idx, w, used = _assign_gpu(cases, mode)
+        for i, c in enumerate(cases):
+            name = c["name"]
+            assert np.array_equal(idx[i], g[f"{name}/idx"].astype(np.int64)), name
+            assert np.array_equal(w[i], g[f"{name}/w"]), name
+            rs = np.random.RandomState(c["seed"])
+            rs.random_sample(int(used[i]))
+            assert np.array_equal(rs.random_sample(2), g[f"{name}/tail"]), name   # stream position parity
+
+
+def test_assignment_vs_oracle_many_images():
+    # cfg3 clutter + cfg5 high-res, images beyond the golden set
+    for key, first, B in (("cfg3", 8, 24), ("cfg5", 3, 6), ("cfg2", 8, 16)):
+        wl = syn.WORKLOADS[key]
+        batch = syn.make_batch(wl, B, first)
+        cases = [dict(boxes=im.gt_bboxes, grid=syn.sample_grid(im.masks), H=im.H, W=im.W, seed=im.seed) for im in batch]
+        idx, w, used = _assign_gpu(cases)
+        for i, im in enumerate(batch):
+            oi, ow, ou = orc.assign_image_seeded(im.gt_bboxes, im.masks, im.H, im.W, im.seed)
+            assert np.array_equal(idx[i], oi), (key, i)
+            assert np.array_equal(w[i], ow), (key, i)
+            assert used[i] == ou
+
+
+def test_assignment_many_gt_and_ragged():
+    # up to 200 GT per image (multi-word bit sets), plus an empty image in the same batch
+    wl = syn.Workload("many", 480, 640, 30, 3, 1, 1, 7)
+    rs = np.random.RandomState(5)
+    imgs = [syn.make_image(rs, 480, 640, 30, G, occluded_frac=0.15) for G in (200, 0, 70)]
+    cases = [dict(boxes=im.gt_bboxes, grid=syn.sample_grid(im.masks), H=480, W=640, seed=100 + i) for i, im in enumerate(imgs)]
+    idx, w, used = _assign_gpu(cases)
+    for i, im in enumerate(imgs):
+        oi, ow, ou = orc.assign_image_seeded(im.gt_bboxes, im.masks, 480, 640, 100 + i)
+        assert np.array_equal(idx[i], oi) and np.array_equal(w[i], ow) and used[i] == ou, i
+
+
+def test_uniform_stream_overflow_is_reported():
+    wl = syn.WORKLOADS["cfg1"]
+    im = syn.make_batch(wl, 1)[0]
+    shapes = GEOM.level_shapes(im.H, im.W)
+    grid = syn.sample_grid(im.masks)
+    bits = F.pack_masks(torch.from_numpy(grid).to(DEV), 1, grid.shape[1], grid.shape[2])
+    u = torch.rand((1, 5), dtype=torch.float64, device=DEV)
+    _, _, used = F.assign(GEOM, shapes, [im.gt_bboxes.shape[0]], torch.from_numpy(im.gt_bboxes).to(DEV), bits, grid.shape[1:], uniforms=u)
+    assert int(used[0]) == -1
+
+
+def test_label_assignment_plugin_numpy_global_rng():
+    """Drop-in contract: results dict in/out and numpy GLOBAL RNG state identical to the reference afterwards."""
+    la = P.LabelAssignment(anchor_generator_cfg=dict(type="AnchorGenerator", ratios=[1.0], octave_base_scale=8, scales_per_octave=1,
+                                                     strides=[8, 16, 32, 64, 128]),
+                           neg_threshold=0.2, positive_num=10, adapt_positive_num=False, balance_sample=True)
+    g, names = hp.assign_cases()
+    for name in ["cfg1_0", "cfg3_1", "cfg5_0", "edge_occluded_and_tiny", "edge_no_gt"]:
+        if name.startswith("edge_"):
+            c = hp.image_for(g, name)
+            masks = np.zeros((c["boxes"].shape[0], c["H"], c["W"]), np.uint8)
+            masks[:, ::8, ::8] = c["grid"]
+            boxes, labels, H, W, seed = c["boxes"], c["labels"], c["H"], c["W"], c["seed"]
+        else:
+            key, i = name.rsplit("_", 1)
+            im = syn.make_batch(syn.WORKLOADS[key], 1, int(i))[0]
+            masks, boxes, labels, H, W, seed = im.masks, im.gt_bboxes, im.gt_labels, im.H, im.W, im.seed
+        np.random.seed(seed)
+        res = la(dict(img_shape=(H, W, 3), gt_bboxes=boxes, gt_labels=labels, distance_maps=masks))
+        tail = np.random.random_sample(2)
+        assert res["points_to_gt_index"].dtype == np.int64 and res["points_weight"].dtype == np.float32
+        assert np.array_equal(res["points_to_gt_index"], g[f"{name}/idx"].astype(np.int64)), name
+        assert np.array_equal(res["points_weight"], g[f"{name}/w"]), name
+        assert np.array_equal(tail, g[f"{name}/tail"]), name
+
+
+# ------------------------------------------------------------------------------------------------ targets + loss
+def _head_inputs(key, B=None):
+    wl, batch = hp.head_case(key)
+    a = [orc.assign_image_seeded(im.gt_bboxes, im.masks, im.H, im.W, im.seed) for im in batch]
+    idx_l, w_l = [x[0] for x in a], [x[1] for x in a]
+    ho = syn.make_head_outputs(wl, batch, idx_l)
+    return wl, batch, idx_l, w_l, ho
+
+
+def _to_dev(ho):
+    T = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(DEV)
+    return [T(m) for m in ho.cls], [T(m) for m in ho.bbox], [T(m) for m in ho.iou]
+
+
+def _gt_dev(batch):
+    counts = [im.gt_bboxes.shape[0] for im in batch]
+    boxes = torch.from_numpy(np.concatenate([im.gt_bboxes for im in batch])).to(DEV)
+    labels = torch.from_numpy(np.concatenate([im.gt_labels for im in batch])).to(DEV)
+    return counts, boxes, labels
+
+
+@pytest.mark.parametrize("key", ["small", "cfg1", "cfg3b2"])
+def test_get_targets_bit_exact(key):
+    wl, batch, idx_l, w_l, ho = _head_inputs(key)
+    shapes = GEOM.level_shapes(wl.H, wl.W)
+    counts, boxes, labels = _gt_dev(batch)
+    idx = torch.from_numpy(np.stack(idx_l)).to(DEV)
+    w = torch.from_numpy(np.stack(w_l)).to(DEV)
+    lab, tg, wt, anc = F.get_targets(GEOM, shapes, wl.C, counts, boxes, labels, idx, w)
+    olab, otg, owt, oanc = orc.get_targets([b.gt_bboxes for b in batch], [b.gt_labels for b in batch], idx_l, w_l, wl.C, wl.H, wl.W)
+    assert np.array_equal(lab.cpu().numpy(), np.concatenate(olab))
+    assert np.array_equal(tg.cpu().numpy(), np.concatenate(otg))
+    assert np.array_equal(wt.cpu().numpy(), np.concatenate(owt))
+    assert np.array_equal(anc.cpu().numpy(), np.concatenate(oanc))
+    g = hp.load("head.npz")
+    sizes = [len(batch) * h * w_ for h, w_ in shapes]
+    for l, part in enumerate(lab.split(sizes)):
+        assert np.array_equal(part.cpu().numpy(), g[f"{key}/labels{l}"].astype(np.int64))
+
+
+def _check_grads(mine, ref, rtol, atol_rel):
+    for a, b in zip(mine, ref):
+        a = a.cpu().numpy() if isinstance(a, torch.Tensor) else a
+        np.testing.assert_allclose(a, b, rtol=rtol, atol=atol_rel * max(1e-30, float(np.abs(b).max())))
+
+
+@pytest.mark.parametrize("key", ["small", "cfg1", "cfg3b2"])
+def test_loss_forward_backward_vs_oracle_and_golden(key):
+    wl, batch, idx_l, w_l, ho = _head_inputs(key)
+    cls, bbox, iou = _to_dev(ho)
+    counts, boxes, labels = _gt_dev(batch)
+    idx = torch.from_numpy(np.stack(idx_l)).to(DEV)
+    w = torch.from_numpy(np.stack(w_l)).to(DEV)
+    losses, grads = F.loss_fwd_bwd(GEOM, wl.C, cls, bbox, iou, counts, boxes, labels, idx, w, F.LossConfig())
+    losses = losses.cpu().numpy()
+    gt_b, gt_l = [b.gt_bboxes for b in batch], [b.gt_labels for b in batch]
+    o32 = orc.head_loss(ho.cls, ho.bbox, ho.iou, gt_b, gt_l, idx_l, w_l, wl.C, wl.H, wl.W)
+    g = hp.load("head.npz")
+    for i, k in enumerate(("loss_cls", "loss_bbox", "loss_iou")):
+        assert abs(losses[i] - o32[k]) <= 1e-5 * abs(o32[k]), (k, losses[i], o32[k])
+        assert abs(losses[i] - float(g[f"{key}/{k}"])) <= 1e-5 * abs(float(g[f"{key}/{k}"])), k     # the reference itself
+    assert losses[3] == o32["num_pos"]
+    _check_grads(grads[0], o32["grad_cls"], 1e-4, 1e-6)
+    _check_grads(grads[1], o32["grad_bbox"], 1e-4, 1e-6)
+    _check_grads(grads[2], o32["grad_iou"], 1e-4, 1e-6)
+    if key == "small":
+        o64 = orc.head_loss(ho.cls, ho.bbox, ho.iou, gt_b, gt_l, idx_l, w_l, wl.C, wl.H, wl.W, dtype="float64")
+        for i, k in enumerate(("loss_cls", "loss_bbox", "loss_iou")):
+            assert abs(losses[i] - o64[k]) <= 2e-6 * abs(o64[k]), k
+        _check_grads(grads[0], o64["grad_cls"], 2e-5, 1e-7)
+        _check_grads(grads[1], o64["grad_bbox"], 2e-5, 1e-6)
+        _check_grads(grads[2], o64["grad_iou"], 2e-5, 1e-6)
+        for l in range(5):   # golden gradients of the reference (fp32 autograd)
+            _check_grads([grads[0][l], grads[1][l], grads[2][l]], [g[f"small/gcls{l}"], g[f"small/gbox{l}"], g[f"small/giou{l}"]], 1e-4, 1e-6)
+
+
+def test_loss_autograd_through_head_api():
+    """RADetHead.loss: dict of autograd-connected scalars; backward gives the fused gradients, scaled by upstream."""
+    wl, batch, idx_l, w_l, ho = _head_inputs("small")
+    head = P.build_head(dict(type="RADetHead", num_classes=wl.C, in_channels=8, feat_channels=8, stacked_convs=1,
+                             norm_cfg=dict(type="GN", num_groups=4, requires_grad=True))).to(DEV)
+    cls, bbox, iou = _to_dev(ho)
+    for t in cls + bbox + iou:
+        t.requires_grad_()
+    T = lambda a: torch.from_numpy(a).to(DEV)
+    metas = syn.img_metas(batch)
+    out = head.loss(cls, bbox, iou, [T(b.gt_bboxes) for b in batch], [T(b.gt_labels) for b in batch], [T(i) for i in idx_l],
+                    [T(w) for w in w_l], metas)
+    assert set(out) == {"loss_cls", "loss_bbox", "loss_iou"}
+    (out["loss_cls"] + 0.5 * out["loss_bbox"] + 2.0 * out["loss_iou"]).backward()
+    o32 = orc.head_loss(ho.cls, ho.bbox, ho.iou, [b.gt_bboxes for b in batch], [b.gt_labels for b in batch], idx_l, w_l, wl.C, wl.H, wl.W)
+    _check_grads([t.grad for t in cls], o32["grad_cls"], 1e-4, 1e-6)
+    g = hp.load("head.npz")
+    # bbox grads scale by 0.5, iou grads by 2 relative to the golden (which used the plain sum)
+    _check_grads([t.grad * 2.0 for t in bbox], [g[f"small/gbox{l}"] for l in range(5)], 1e-4, 1e-6)
+    _check_grads([t.grad * 0.5 for t in iou], [g[f"small/giou{l}"] for l in range(5)], 1e-4, 1e-6)
+
+
+def test_loss_no_positive_branch():
+    """num_pos == 0 (radet_head.py:279-281): loss_bbox / loss_iou are plain sums over the (ignored) positives."""
+    wl, batch, idx_l, w_l, ho = _head_inputs("small")
+    idx_l = [np.where(i > 0, 0, i) for i in idx_l]          # positives -> ignored (still members of pos_inds)
+    w_l = [np.where(i >= 0, 0.0, w).astype(np.float32) for i, w in zip(idx_l, w_l)]
+    cls, bbox, iou = _to_dev(ho)
+    counts, boxes, labels = _gt_dev(batch)
+    losses, grads = F.loss_fwd_bwd(GEOM, wl.C, cls, bbox, iou, counts, boxes, labels, torch.from_numpy(np.stack(idx_l)).to(DEV),
+                                   torch.from_numpy(np.stack(w_l)).to(DEV), F.LossConfig())
+    o = orc.head_loss(ho.cls, ho.bbox, ho.iou, [b.gt_bboxes for b in batch], [b.gt_labels for b in batch], idx_l, w_l, wl.C, wl.H, wl.W)
+    losses = losses.cpu().numpy()
+    assert o["num_pos"] == 0 and losses[3] == 0
+    for i, k in enumerate(("loss_cls", "loss_bbox", "loss_iou")):
+        assert abs(losses[i] - o[k]) <= 1e-5 * abs(o[k]) + 1e-6, k
+    _check_grads(grads[1], o["grad_bbox"], 1e-5, 1e-7)
+    _check_grads(grads[2], o["grad_iou"], 1e-5, 1e-7)
+    _check_grads(grads[0], o["grad_cls"], 1e-4, 1e-6)
+
+
+def test_loss_odd_plane_sizes_scalar_path():
+    """h*w not a multiple of 4 on some levels (100x100 image -> 13x13, 7x7, 4x4, 2x2, 1x1)."""
+    wl = syn.Workload("odd", 100, 100, 7, 3, 2, 5, 11)
+    batch = syn.make_batch(wl)
+    a = [orc.assign_image_seeded(im.gt_bboxes, im.masks, im.H, im.W, im.seed) for im in batch]
+    idx_l, w_l = [x[0] for x in a], [x[1] for x in a]
+    ho = syn.make_head_outputs(wl, batch, idx_l)
+    cls, bbox, iou = _to_dev(ho)
+    counts, boxes, labels = _gt_dev(batch)
+    losses, grads = F.loss_fwd_bwd(GEOM, wl.C, cls, bbox, iou, counts, boxes, labels, torch.from_numpy(np.stack(idx_l)).to(DEV),
+                                   torch.from_numpy(np.stack(w_l)).to(DEV), F.LossConfig())
+    o = orc.head_loss(ho.cls, ho.bbox, ho.iou, [b.gt_bboxes for b in batch], [b.gt_labels for b in batch], idx_l, w_l, wl.C, wl.H, wl.W)
+    losses = losses.cpu().numpy()
+    for i, k in enumerate(("loss_cls", "loss_bbox", "loss_iou")):
+        assert abs(losses[i] - o[k]) <= 1e-5 * abs(o[k]), k
+    _check_grads(grads[0], o["grad_cls"], 1e-4, 1e-6)
+    _check_grads(grads[1], o["grad_bbox"], 1e-4, 1e-6)
+    _check_grads(grads[2], o["grad_iou"], 1e-4, 1e-6)
+    # and the assignment on the same odd geometry
+    cases = [dict(boxes=im.gt_bboxes, grid=syn.sample_grid(im.masks), H=im.H, W=im.W, seed=im.seed) for im in batch]
+    idx, w, used = _assign_gpu(cases)
+    for i in range(len(batch)):
+        assert np.array_equal(idx[i], idx_l[i]) and np.array_equal(w[i], w_l[i])
+
+
+# ------------------------------------------------------------------------------------------------ inference
+NMS_CFG = dict(iou_threshold=0.65, cluster_score=["cls", "iou"], vote_score=["iou", "cls"], iou_enable=False, sima=0.025)
+
+
+def test_sigmoid_flavour_is_torch_cuda():
+    """The kernel's 1/(1+expf(-x)) must be bit-identical to torch's CUDA sigmoid (what the reference runs)."""
+    x = torch.randn(1, 1, 64, 64, device=DEV) * 4
+    # route through get_bboxes with one class, thr 0: scores come back as score*ctr with ctr = sigmoid(0) = 0.5 -> exact
+    geom = F.Geometry(strides=(8,), regress_ranges=((-1, 1e8),))
+    cfg = F.DetectConfig(score_thr=0.0, nms_pre=-1, max_per_img=4096, nms_type="nms", iou_threshold=2.0)
+    bbox = torch.zeros(1, 4, 64, 64, device=DEV)
+    bbox[0, 0] = torch.arange(64 * 64, device=DEV).reshape(64, 64) * 0.001   # distinct boxes
+    dets, labels, num = F.get_bboxes(geom, 1, [x], [bbox], [torch.zeros(1, 1, 64, 64, device=DEV)],
+                                     torch.tensor([[512, 512]], dtype=torch.int32, device=DEV),
+                                     torch.ones(1, 4, device=DEV), cfg)
+    assert int(num[0]) == 4096
+    got = np.sort(dets[0, :, 4].cpu().numpy())
+    want = np.sort((torch.sigmoid(x).reshape(-1) * 0.5).cpu().numpy())
+    assert np.array_equal(got, want)
+
+
+@pytest.mark.parametrize("key", ["small", "cfg1", "cfg3b2"])
+@pytest.mark.parametrize("typ", ["vote", "global_vote", "nms"])
+@pytest.mark.parametrize("thr", [0.05, 0.1])
+def test_get_bboxes_bit_exact_vs_oracle(key, typ, thr):
+    wl, batch, idx_l, w_l, ho = _head_inputs(key)
+    cls, bbox, iou = _to_dev(ho)
+    cfg = F.DetectConfig(score_thr=thr, nms_type=typ, **{k: v for k, v in NMS_CFG.items() if k != "sima"})
+    shp = torch.tensor([[im.H, im.W] for im in batch], dtype=torch.int32, device=DEV)
+    sf = torch.full((len(batch), 4), 1.25, device=DEV)
+    dets, labels, num = F.get_bboxes(GEOM, wl.C, cls, bbox, iou, shp, sf, cfg, rescale=True)
+    dets, labels, num = dets.cpu().numpy(), labels.cpu().numpy(), num.cpu().numpy()
+    for b, im in enumerate(batch):
+        od, ol = orc.get_bboxes_image([m[b] for m in ho.cls], [m[b] for m in ho.bbox], [m[b] for m in ho.iou], (im.H, im.W, 3),
+                                      np.full(4, 1.25, np.float32), score_thr=thr, nms_cfg=dict(type=typ, **NMS_CFG))
+        assert num[b] == od.shape[0], (key, typ, thr, b)
+        assert np.array_equal(dets[b, :num[b]].view(np.uint32), od.view(np.uint32)), (key, typ, thr, b)
+        assert np.array_equal(labels[b, :num[b]], ol)
+
+
+@pytest.mark.parametrize("key", ["small", "cfg1"])
+def test_get_bboxes_vs_reference_golden(key):
+    """Against the reference run on CPU (torch-CPU sigmoid flavour): same detections up to the <=1 ulp score flavour."""
+    g = hp.load("head.npz")
+    wl, batch, idx_l, w_l, ho = _head_inputs(key)
+    cls, bbox, iou = _to_dev(ho)
+    head = P.build_head(dict(type="RADetHead", num_classes=wl.C, in_channels=8, feat_channels=8, stacked_convs=1,
+                             norm_cfg=dict(type="GN", num_groups=4, requires_grad=True),
+                             test_cfg=dict(nms_pre=1000, min_bbox_size=0, score_thr=0.05, nms=dict(type="vote", **NMS_CFG), max_per_img=100)))
+    res = head.get_bboxes(cls, bbox, iou, syn.img_metas(batch), rescale=True)
+    for b, (d, l) in enumerate(res):
+        assert not d.is_cuda and d.shape[1] == 5                      # vote branch hands back CPU tensors like the reference
+        ref_d, ref_l = g[f"{key}/det_vote_0.05_{b}"], g[f"{key}/lab_vote_0.05_{b}"].astype(np.int64)
+        assert d.shape == ref_d.shape
+        assert np.array_equal(l.numpy(), ref_l)
+        np.testing.assert_allclose(d.numpy(), ref_d, rtol=2e-6, atol=1e-4)
+
+
+def test_get_bboxes_empty_and_ragged():
+    wl, batch, idx_l, w_l, ho = _head_inputs("small")
+    cls, bbox, iou = _to_dev(ho)
+    cls = [c.clone() for c in cls]
+    for c in cls:
+        c[1] = -20.0                                                  # image 1: nothing above threshold
+    head = P.build_head(dict(type="RADetHead", num_classes=wl.C, in_channels=8, feat_channels=8, stacked_convs=1,
+                             norm_cfg=dict(type="GN", num_groups=4, requires_grad=True),
+                             test_cfg=dict(nms_pre=1000, score_thr=0.05, nms=dict(type="vote", **NMS_CFG), max_per_img=100)))
+    res = head.get_bboxes(cls, bbox, iou, syn.img_metas(batch), rescale=False)
+    assert res[0][0].shape[0] > 0
+    assert tuple(res[1][0].shape) == (0, 5) and tuple(res[1][1].shape) == (0, 1) and res[1][1].dtype == torch.int32
+
+
+# ------------------------------------------------------------------------------------------------ radet.ops
+@pytest.mark.parametrize("case", range(5))
+@pytest.mark.parametrize("on_gpu", [True, False])
+def test_ops_golden_bit_exact(case, on_gpu):
+    g = hp.load("ops.npz")
+    dev = DEV if on_gpu else "cpu"
+    boxes = torch.from_numpy(g[f"c{case}/boxes"]).to(dev)
+    labels = torch.from_numpy(g[f"c{case}/labels"].astype(np.int64)).to(dev)
+    cls = torch.from_numpy(g[f"c{case}/cls"]).to(dev)
+    ctr = torch.from_numpy(g[f"c{case}/ctr"]).to(dev)
+    cfg = P.ConfigDict(type="vote", **NMS_CFG)
+    for nm, fn in (("vote", P.ops.vote_nms), ("gvote", P.ops.global_vote_nms)):
+        d, l = fn(boxes, cls, labels, cfg, score_factor=ctr, max_num=0)
+        assert d.is_cuda == on_gpu
+        assert np.array_equal(d.cpu().numpy().view(np.uint32), g[f"c{case}/{nm}_dets"].view(np.uint32)), nm
+        assert np.array_equal(l.cpu().numpy(), g[f"c{case}/{nm}_labels"].astype(np.int64))
+    d, l = P.ops.vote_nms(boxes, cls, labels, cfg, score_factor=ctr, max_num=7)
+    assert np.array_equal(d.cpu().numpy().view(np.uint32), g[f"c{case}/vote_dets"][:7].view(np.uint32))
+    inst, cnum = P.ops.cluster_nms(g[f"c{case}/boxes"], g[f"c{case}/cls"] * g[f"c{case}/ctr"], g[f"c{case}/labels"].astype(np.int64), 0.65)
+    assert np.array_equal(inst.numpy(), g[f"c{case}/inst"]) and np.array_equal(cnum.numpy(), g[f"c{case}/cnum"])
+
+
+def test_vote_nms_large_list_global_memory_path_and_batch():
+    """n > shared-memory capacity (5120) takes the global-memory variant; lists of different length in one launch."""
+    rs = np.random.RandomState(99)
+    lists = []
+    for n, nobj, ncls in ((7000, 300, 4), (0, 1, 1), (513, 40, 30), (1, 1, 1)):
+        ctr = rs.uniform(50, 590, (nobj, 2))
+        wh = rs.uniform(20, 200, (nobj, 2))
+        pick = rs.randint(0, nobj, n)
+        c = ctr[pick] + rs.normal(0, 3, (n, 2))
+        s = wh[pick] * np.exp(rs.normal(0, 0.06, (n, 2)))
+        boxes = np.concatenate([c - s / 2, c + s / 2], 1).astype(np.float32).reshape(-1, 4)
+        labels = rs.randint(0, ncls, n).astype(np.int64)
+        sc = rs.permutation(n).astype(np.float32) / max(n, 1) * 0.9 + 0.05     # tie-free
+        vs = rs.uniform(0.1, 1, n).astype(np.float32)
+        lists.append((boxes, sc, vs, labels))
+    cat = lambda i, dt: torch.from_numpy(np.concatenate([l[i] for l in lists]).astype(dt)).to(DEV)
+    counts = [l[0].shape[0] for l in lists]
+    dets, olab, oidx, num, inst, cnum, off = F.vote_nms_lists(counts, cat(0, np.float32), cat(1, np.float32), cat(2, np.float32),
+                                                              cat(3, np.int64), 0.65, want_clusters=True)
+    dets, olab, num, inst, cnum = dets.cpu().numpy(), olab.cpu().numpy(), num.cpu().numpy(), inst.cpu().numpy(), cnum.cpu().numpy()
+    for i, (boxes, sc, vs, labels) in enumerate(lists):
+        ob, ol, os_, oi, oc = orc.vote_nms_c(boxes, sc, vs, labels, 0.65)
+        k = ob.shape[0]
+        assert num[i] == k, i
+        r0 = off[i]
+        assert np.array_equal(dets[r0:r0 + k, :4].view(np.uint32), ob.view(np.uint32)), i
+        assert np.array_equal(dets[r0:r0 + k, 4], os_) and np.array_equal(olab[r0:r0 + k], ol)
+        assert np.array_equal(inst[r0:r0 + counts[i]], oi) and np.array_equal(cnum[r0:r0 + counts[i]], oc)
+
+
+def test_nms_properties_full_size():
+    """Size-independent properties at cfg4 scale (B=64): idempotence of the keep set and score ordering."""
+    wl = syn.WORKLOADS["cfg4"]
+    B = 8
+    batch = syn.make_batch(wl, B)
+    a = [orc.assign_image_seeded(im.gt_bboxes, im.masks, im.H, im.W, im.seed) for im in batch]
+    ho = syn.make_head_outputs(wl, batch, [x[0] for x in a])
+    cls, bbox, iou = _to_dev(ho)
+    cfg = F.DetectConfig(score_thr=wl.score_thr, nms_type="nms", iou_threshold=0.65)
+    shp = torch.tensor([[im.H, im.W] for im in batch], dtype=torch.int32, device=DEV)
+    sf = torch.ones((B, 4), device=DEV)
+    dets, labels, num = F.get_bboxes(GEOM, wl.C, cls, bbox, iou, shp, sf, cfg)
+    for b in range(B):
+        k = int(num[b])
+        d, l = dets[b, :k], labels[b, :k]
+        assert bool((d[:-1, 4] >= d[1:, 4]).all())                                  # sorted by score
+        d2, keep = P.ops.batched_nms(d[:, :4], d[:, 4], l, dict(type="nms", iou_threshold=0.65))
+        assert d2.shape[0] == k and np.array_equal(keep.cpu().numpy(), np.arange(k))  # NMS of a kept set keeps everything
