@@ -1,0 +1,581 @@
+#!/usr/bin/env python
+"""bench.py — images/s of RADet's dense-head hot path (assign + loss fwd/bwd + decode/vote-NMS) on B200.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload cfg2] [--no-graph]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P bench.py --gpus N ...
+
+One "step" = one pass of the hot path over one synthetic batch (BASELINE.json configs[1]: YCB-V-shaped 640x480,
+B=8 images per GPU, 21 classes, 3..21 GT per image, random visible masks):
+    pack masks -> assign (pairs + resolve) -> loss normalisers -> fused loss fwd+bwd -> backward rescale ->
+    candidate select -> per-image top-k/sort/decode/vote-NMS.
+`value` = images/s with inputs resident in HBM (CUDA-graph replay of the step; R rotating input sets larger than L2),
+`e2e` = the same through the plugin API with pinned HOST buffers (H2D of every input + D2H of losses/detections inside
+the timed region), `roofline` = the fused loss kernel's algorithmic bytes / its CUDA-event duration / measured HBM peak,
+`cpu_baseline` = the CPU restatement of the reference path on this box's host cores (bounded sample).
+Ranks shard images (weak scaling); the path has no data-path collective.
+"""
+import argparse
+import ctypes
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+from radet_b200 import synthetic as syn  # noqa: E402
+
+L2_BYTES = 126 * 1024 * 1024
+NMS_CFG = dict(iou_threshold=0.65, cluster_score=["cls", "iou"], vote_score=["iou", "cls"], iou_enable=False)
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=2000)
+    ap.add_argument("--warmup", type=int, default=50)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="cfg2", choices=sorted(syn.WORKLOADS))
+    ap.add_argument("--batch", type=int, default=0, help="images per GPU (default: the workload's)")
+    ap.add_argument("--no-graph", action="store_true", help="eager launches instead of CUDA-graph replay")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--profile", action="store_true", help="few eager steps, nothing else (for ncu)")
+    ap.add_argument("--sets", type=int, default=0, help="rotating input sets (default: enough to exceed 2x L2)")
+    ap.add_argument("--cpu-baseline-json", action="store_true", help=argparse.SUPPRESS)
+    return ap.parse_args()
+
+
+# ------------------------------------------------------------------------------------------------ CPU path (oracle)
+def _cpu_assign(args):
+    from oracle import radet_oracle as orc
+
+    boxes, masks, H, W, seed = args
+    return orc.assign_image_seeded(boxes, masks, H, W, seed)[:2]
+
+
+def _cpu_detect(args):
+    from oracle import radet_oracle as orc
+
+    cls, bbox, iou, H, W, thr = args
+    return orc.get_bboxes_image(cls, bbox, iou, (H, W, 3), np.ones(4, np.float32), score_thr=thr,
+                                nms_cfg=dict(type="vote", **NMS_CFG))
+
+
+def cpu_step(wl, batch, ho, pool, idx_w=None):
+    """The reference path on host cores: per-image assignment and decode+vote-NMS fanned out over `pool`
+    (mirrors workers_per_gpu), loss forward+backward with torch intra-op threads.  Returns seconds per stage."""
+    from oracle import radet_oracle as orc
+
+    t0 = time.perf_counter()
+    aw = pool.map(_cpu_assign, [(im.gt_bboxes, im.masks, im.H, im.W, im.seed) for im in batch])
+    t1 = time.perf_counter()
+    orc.head_loss(ho.cls, ho.bbox, ho.iou, [im.gt_bboxes for im in batch], [im.gt_labels for im in batch],
+                  [a[0] for a in aw], [a[1] for a in aw], wl.C, wl.H, wl.W)
+    t2 = time.perf_counter()
+    pool.map(_cpu_detect, [([m[b] for m in ho.cls], [m[b] for m in ho.bbox], [m[b] for m in ho.iou], im.H, im.W, wl.score_thr)
+                           for b, im in enumerate(batch)])
+    t3 = time.perf_counter()
+    return dict(assign=t1 - t0, loss=t2 - t1, detect=t3 - t2, total=t3 - t0)
+
+
+def make_inputs(wl, B, first_image, assign_fn):
+    """Synthetic batch + head outputs (SURVEY 8d protocol: the logits are boosted at the assigned positives, so an
+    assignment is needed to shape them).  assign_fn: the oracle in the CPU legs, the CUDA path in the GPU leg."""
+    batch = syn.make_batch(wl, B, first_image)
+    idx_l = assign_fn(batch)
+    ho = syn.make_head_outputs(wl, batch, idx_l, seed_base=wl.cfg_id * 100 + 7 * first_image)
+    return batch, ho
+
+
+def oracle_assign_fn(batch):
+    from oracle import radet_oracle as orc
+
+    return [orc.assign_image_seeded(im.gt_bboxes, im.masks, im.H, im.W, im.seed)[0] for im in batch]
+
+
+def cpu_baseline_leg(wl, B, reps=3, warm=1):
+    """Times the CPU port on a bounded sample; runs in its own process (see --cpu-baseline-json) so that the fork pool
+    never coexists with a CUDA context and the GPU process never imports oracle/."""
+    import multiprocessing as mp
+
+    import torch
+
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    from oracle import radet_oracle as orc
+
+    orc.build_c_oracle()
+    batch, ho = make_inputs(wl, B, 0, oracle_assign_fn)
+    with mp.get_context("fork").Pool(min(cores, B)) as pool:
+        for _ in range(warm):
+            cpu_step(wl, batch, ho, pool)
+        t0 = time.perf_counter()
+        st = [cpu_step(wl, batch, ho, pool) for _ in range(reps)]
+        dt = time.perf_counter() - t0
+    return {"value": B * reps / dt, "unit": "images/s", "cores": cores, "kind": "port",
+            "sample": f"{reps} steps x {B} images of {wl.name}; numpy/C oracle port of the reference path (the Python reference "
+                      f"cannot travel to this box), per-image stages over a {min(cores, B)}-process pool, loss fwd+bwd on {cores} "
+                      "torch threads; stage ms/step: " +
+                      ", ".join(f"{k}={1e3 * np.mean([x[k] for x in st]):.1f}" for k in ("assign", "loss", "detect"))}, dt / reps
+
+
+def run_reference(args, wl, B):
+    """--impl reference: the reference's CPU implementation of the path (oracle port; NMS loops in compiled C) on all
+    host cores, same workload/metric/unit."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    steps = max(1, min(args.steps, 10))
+    warm = max(1, min(args.warmup, 2))
+    cb, sec = cpu_baseline_leg(wl, B, reps=steps, warm=warm)
+    v = cb["value"]
+    print(json.dumps({
+        "metric": "images/s (assign + loss fwd/bwd + decode/vote-NMS)", "value": v, "unit": "images/s", "impl": "reference",
+        "n_gpus": args.gpus, "steps": steps, "warmup": warm, "ms_per_step": 1e3 * sec,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": wl.name, "images_per_step": B}, "cpu_baseline": cb,
+        "e2e": {"value": v, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }))
+
+
+# ------------------------------------------------------------------------------------------------ clocks
+class ClockSampler:
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.rows, self.proc = [], None
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                                          "-i", str(index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.th = threading.Thread(target=self._read, daemon=True)
+            self.th.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append((time.perf_counter(), line.strip()))
+
+    def stop(self, t0, t1):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        rows = [r for t, r in self.rows if t0 <= t <= t1] or [r for _, r in self.rows[-3:]]
+        sm, mx, reasons = [], [], set()
+        for r in rows:
+            f = [x.strip() for x in r.split(",")]
+            try:
+                sm.append(float(f[0]))
+                mx.append(float(f[1]))
+            except Exception:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[2:6]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------------ ours
+def main():
+    args = parse()
+    wl = syn.WORKLOADS[args.workload]
+    B = args.batch or wl.B
+    if args.impl == "reference":
+        return run_reference(args, wl, B)
+    if args.cpu_baseline_json:
+        print(json.dumps(cpu_baseline_leg(wl, B)[0]))
+        return
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+
+    # ---- CPU baseline (rank 0, N=1 only) in its own process, concurrently with the GPU set-up below
+    cpu_proc = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline and not args.profile:
+        cpu_proc = subprocess.Popen([sys.executable, os.path.abspath(__file__), "--cpu-baseline-json", "--workload", args.workload,
+                                     "--batch", str(B)], stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True)
+        cpu_proc_out = cpu_proc.communicate()   # finish before any GPU timing: the host cores must be quiet then
+    cpu_base = None
+    if cpu_proc is not None:
+        try:
+            cpu_base = json.loads(cpu_proc_out[0].strip().splitlines()[-1])
+        except Exception:
+            cpu_base = {"error": (cpu_proc_out[1] or "")[-300:]}
+
+    import torch
+    import torch.distributed as dist
+
+    from radet_b200 import _lib
+    from radet_b200 import functional as F
+    from radet_b200 import plugin as P
+
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    geom = F.Geometry()
+    shapes = geom.level_shapes(wl.H, wl.W)
+    Ppts = geom.num_points(shapes)
+    gh, gw = -(-wl.H // 8), -(-wl.W // 8)
+    lcfg = F.LossConfig()
+    dcfg = F.DetectConfig(score_thr=wl.score_thr, nms_pre=wl.nms_pre, max_per_img=wl.max_per_img, nms_type="vote", **NMS_CFG)
+
+    # ---- R rotating input sets (device-resident), total footprint > 2 x L2
+    per_set = B * Ppts * (wl.C + 5) * 4 * 2 + B * Ppts * 12
+    R = args.sets or max(2, int(np.ceil(2.2 * L2_BYTES / per_set)))
+    if args.profile:
+        R = 2
+    sets = []
+    host_sets = []
+
+    def gpu_assign_fn(batch):   # the product path shapes its own synthetic logits (no oracle in this process)
+        counts = [im.gt_bboxes.shape[0] for im in batch]
+        g = torch.from_numpy(np.concatenate([syn.sample_grid(im.masks) for im in batch])).to(dev)
+        idx, _, _ = F.assign(geom, shapes, counts, torch.from_numpy(np.concatenate([im.gt_bboxes for im in batch])).to(dev),
+                             F.pack_masks(g, 1, gh, gw), (gh, gw),
+                             seeds=torch.tensor([im.seed for im in batch], dtype=torch.int32, device=dev))
+        return list(idx.cpu().numpy())
+
+    for r in range(R):
+        batch, ho = make_inputs(wl, B, (rank * R + r) * B, gpu_assign_fn)
+        counts = [im.gt_bboxes.shape[0] for im in batch]
+        off_h, off_d = F.offsets_of(counts, dev)
+        T = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)
+        s = dict(counts=counts, off=(off_h, off_d), boxes=T(np.concatenate([im.gt_bboxes for im in batch])),
+                 labels=T(np.concatenate([im.gt_labels for im in batch])),
+                 grids=T(np.concatenate([syn.sample_grid(im.masks) for im in batch])),
+                 seeds=torch.tensor([im.seed for im in batch], dtype=torch.int32, device=dev),
+                 cls=[T(m) for m in ho.cls], bbox=[T(m) for m in ho.bbox], iou=[T(m) for m in ho.iou],
+                 shp=torch.tensor([[im.H, im.W] for im in batch], dtype=torch.int32, device=dev),
+                 sf=torch.ones((B, 4), dtype=torch.float32, device=dev), pairs=sum(counts) * Ppts)
+        sets.append(s)
+        if r < 4:
+            host_sets.append((batch, ho))
+    up_ones = torch.ones(3, dtype=torch.float32, device=dev)
+
+    def step(s, keep=None):
+        bits = F.pack_masks(s["grids"], 1, gh, gw)
+        idx, w, used = F.assign(geom, shapes, s["counts"], s["boxes"], bits, (gh, gw), seeds=s["seeds"], gt_offsets=s["off"])
+        losses, grads = F.loss_fwd_bwd(geom, wl.C, s["cls"], s["bbox"], s["iou"], s["counts"], s["boxes"], s["labels"], idx, w, lcfg,
+                                       gt_offsets=s["off"])
+        F.scale_grads(geom, wl.C, grads, up_ones)            # what autograd's backward of the three losses launches
+        dets, dl, num = F.get_bboxes(geom, wl.C, s["cls"], s["bbox"], s["iou"], s["shp"], s["sf"], dcfg, rescale=True)
+        if keep is not None:
+            keep.append((idx, w, losses, grads, dets, dl, num))
+        return losses, num
+
+    torch.cuda.synchronize()
+    if args.profile:
+        for i in range(args.warmup + args.steps):
+            step(sets[i % R])
+        torch.cuda.synchronize()
+        return
+
+    # ---- launches per step, eager warm-up
+    l0 = _lib.launch_count()
+    step(sets[0])
+    launches_per_step = _lib.launch_count() - l0
+    for i in range(max(3, min(args.warmup, 20))):
+        step(sets[i % R])
+    torch.cuda.synchronize()
+
+    # ---- CUDA graphs: one per input set (the C ABI only enqueues, so the whole step is capturable)
+    use_graph = not args.no_graph
+    graphs, outs = [], []
+    if use_graph:
+        pool = torch.cuda.graph_pool_handle()
+        for s in sets:
+            g = torch.cuda.CUDAGraph()
+            keep = []
+            with torch.cuda.graph(g, pool=pool):
+                step(s, keep)
+            graphs.append(g)
+            outs.append(keep)
+        run = lambda i: graphs[i % R].replay()
+    else:
+        run = lambda i: step(sets[i % R])
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    for i in range(args.warmup):
+        run(i)
+    # keep the GPU under load long enough for the clock sampler to see it (not timed)
+    t_load = time.perf_counter()
+    i = 0
+    while time.perf_counter() - t_load < 0.6:
+        run(i)
+        i += 1
+        if i % 256 == 0:
+            torch.cuda.synchronize()
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t_clk0 = time.perf_counter()
+    e0.record()
+    for i in range(args.steps):
+        run(i)
+    e1.record()
+    barrier()
+    t_clk1 = time.perf_counter()
+    ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    ms_total = float(ms.item())
+    ms_per_step = ms_total / args.steps
+    value = world * B * args.steps / (ms_total * 1e-3)
+
+    # ---- stage / kernel timings with CUDA events (each stage looped alone over the rotating sets)
+    def time_stage(fn, iters=400):
+        """us per call of one stage, CUDA events around graph replays (one captured graph per rotating input set, so
+        neither Python/ctypes overhead nor a warm L2 flatters or penalises the kernels)."""
+        for i in range(3):
+            fn(sets[i % R])
+        torch.cuda.synchronize()
+        gs, keepalive = [], []
+        if use_graph:
+            for s in sets:
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g, pool=pool):
+                    keepalive.append(fn(s))
+                gs.append(g)
+            call = lambda i: gs[i % R].replay()
+        else:
+            call = lambda i: fn(sets[i % R])
+        for i in range(R):
+            call(i)
+        torch.cuda.synchronize()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for i in range(iters):
+            call(i)
+        b.record()
+        torch.cuda.synchronize()
+        return a.elapsed_time(b) * 1e3 / iters   # us
+
+    pre = []
+    for s in sets:
+        bits = F.pack_masks(s["grids"], 1, gh, gw)
+        idx, w, _ = F.assign(geom, shapes, s["counts"], s["boxes"], bits, (gh, gw), seeds=s["seeds"], gt_offsets=s["off"])
+        s["bits"], s["idx"], s["w"] = bits, idx, w
+        s["grads"] = F.loss_fwd_bwd(geom, wl.C, s["cls"], s["bbox"], s["iou"], s["counts"], s["boxes"], s["labels"], idx, w, lcfg,
+                                    gt_offsets=s["off"])[1]
+    lib = _lib.load()
+
+    def dense_only(s):   # phase 2 = the fused dense kernel alone (normalisers already in the workspace)
+        grid = geom.grid(shapes)
+        maps = _lib.make_maps([t.data_ptr() for t in s["cls"]], [t.data_ptr() for t in s["bbox"]], [t.data_ptr() for t in s["iou"]])
+        g = s["grads"]
+        gm = _lib.make_maps([t.data_ptr() for t in g[0]], [t.data_ptr() for t in g[1]], [t.data_ptr() for t in g[2]])
+        ws = F._workspace(("loss", B, Ppts, wl.C), 0, dev)
+        c = lcfg.c_struct(B)
+        rc = lib.radet_loss_fwd_bwd(ctypes.byref(grid), B, wl.C, ctypes.byref(maps), F._ptr(s["off"][1]), F._ptr(s["boxes"]),
+                                    F._ptr(s["labels"]), F._ptr(s["idx"]), F._ptr(s["w"]), ctypes.byref(c), None, ctypes.byref(gm),
+                                    F._ptr(s["losses_buf"]), 2, F._ptr(ws), ws.numel(), F._stream())
+        assert rc == 0, rc
+
+    for s in sets:
+        s["losses_buf"] = torch.empty(4, dtype=torch.float32, device=dev)
+    stage_us = {
+        "pack_masks": time_stage(lambda s: F.pack_masks(s["grids"], 1, gh, gw)),
+        "assign(pairs+resolve)": time_stage(lambda s: F.assign(geom, shapes, s["counts"], s["boxes"], s["bits"], (gh, gw), seeds=s["seeds"],
+                                                               gt_offsets=s["off"])),
+        "loss(pos+dense)": time_stage(lambda s: F.loss_fwd_bwd(geom, wl.C, s["cls"], s["bbox"], s["iou"], s["counts"], s["boxes"],
+                                                              s["labels"], s["idx"], s["w"], lcfg, gt_offsets=s["off"])),
+        "loss_dense_kernel": time_stage(dense_only),
+        "get_bboxes(select+nms)": time_stage(lambda s: F.get_bboxes(geom, wl.C, s["cls"], s["bbox"], s["iou"], s["shp"], s["sf"], dcfg,
+                                                                    rescale=True)),
+    }
+    peaks = {}
+    pk = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(pk):
+        peaks = json.load(open(pk))
+    peak_gbs = float(peaks.get("hbm_gbs", 6650.0))
+    peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650 GB/s"
+    loss_bytes = B * Ppts * (8 * wl.C + 52)
+    ach = loss_bytes / (stage_us["loss_dense_kernel"] * 1e-6) / 1e9
+    roofline = {"bound": "hbm", "kernel": "loss_dense_kernel", "achieved": ach, "peak": peak_gbs, "unit": "GB/s", "frac": ach / peak_gbs,
+                "traffic": None, "peak_source": peak_src, "algorithmic_bytes_per_launch": loss_bytes,
+                "us_per_launch": stage_us["loss_dense_kernel"],
+                "note": f"(8C+52) B/point x {B * Ppts} points; at this batch the launch moves {loss_bytes / 1e6:.1f} MB "
+                        "(latency-bound regime, SURVEY 8d); see roofline_large for the bandwidth-bound regime"}
+
+    # ---- the same kernel in the bandwidth-bound regime (cfg5-shaped: 1280x960, C=30, B=16 -> ~120 MB per launch)
+    roofline_large = None
+    if rank == 0:
+        try:
+            roofline_large = large_roofline(F, _lib, dev, peak_gbs)
+        except Exception as e:  # never lose the headline line to the auxiliary measurement
+            roofline_large = {"error": repr(e)}
+
+    # ---- e2e: plugin API, pinned host buffers, H2D + D2H inside the timed region
+    e2e = None
+    if not args.no_e2e:
+        e2e = run_e2e(args, wl, B, host_sets, dev, P, F, world)
+
+    clocks = sampler.stop(t_clk0, t_clk1) if sampler else None
+    if world > 1:
+        dist.barrier()
+    if rank == 0:
+        pairs = float(np.mean([s["pairs"] for s in sets]))
+        out = {
+            "metric": "images/s (assign + loss fwd/bwd + decode/vote-NMS)", "value": value, "unit": "images/s", "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": wl.name, "images_per_gpu": B, "points_per_image": Ppts, "classes": wl.C,
+                       "launch": "cuda_graph" if use_graph else "eager",
+                       "l2": f"{R} rotating input sets, {R * per_set / 1e6:.0f} MB total > L2 ({L2_BYTES / 1e6:.0f} MB)",
+                       "parallelism": f"images sharded over {world} rank(s), no data-path collective"},
+            "point_gt_pairs_per_s": world * pairs / (stage_us["assign(pairs+resolve)"] * 1e-6),
+            "point_gt_pairs_per_s_train_path": world * pairs / ((stage_us["assign(pairs+resolve)"] + stage_us["loss(pos+dense)"]) * 1e-6),
+            "stage_us": stage_us, "gpu_launches": launches_per_step * args.steps, "launches_per_step": launches_per_step,
+            "roofline": roofline, "roofline_large": roofline_large, "cpu_baseline": cpu_base, "e2e": e2e, "clocks": clocks,
+        }
+        print(json.dumps(out))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def large_roofline(F, _lib, dev, peak_gbs):
+    """loss_dense_kernel and the assignment at cfg5 scale (per-GPU share), synthetic random tensors of that shape."""
+    import torch
+
+    wl = syn.WORKLOADS["cfg5"]
+    B, C = wl.B, wl.C
+    geom = F.Geometry()
+    shapes = geom.level_shapes(wl.H, wl.W)
+    Ppts = geom.num_points(shapes)
+    g = torch.Generator(device=dev).manual_seed(0)
+    R = 3   # 3 x ~120 MB > L2
+    sets = []
+    rs = np.random.RandomState(0)
+    for r in range(R):
+        counts = [int(c) for c in rs.randint(wl.g_lo, wl.g_hi + 1, B)]
+        imgs = [syn.make_image(np.random.RandomState(50 + r * B + i), wl.H, wl.W, C, counts[i]) for i in range(2)]
+        # boxes/masks: two real synthetic images tiled over the batch (mask generation at 1280x960 is slow on the host)
+        counts = [imgs[i % 2].gt_bboxes.shape[0] for i in range(B)]
+        off = F.offsets_of(counts, dev)
+        boxes = torch.from_numpy(np.concatenate([imgs[i % 2].gt_bboxes for i in range(B)])).to(dev)
+        labels = torch.from_numpy(np.concatenate([imgs[i % 2].gt_labels for i in range(B)])).to(dev)
+        grids = torch.from_numpy(np.concatenate([syn.sample_grid(imgs[i % 2].masks) for i in range(B)])).to(dev)
+        gh, gw = grids.shape[1:]
+        bits = F.pack_masks(grids, 1, gh, gw)
+        seeds = torch.arange(B, dtype=torch.int32, device=dev) + 1000 * r
+        idx, w, _ = F.assign(geom, shapes, counts, boxes, bits, (gh, gw), seeds=seeds, gt_offsets=off)
+        cls = [torch.randn((B, C, h, w_), device=dev, generator=g) - 4.6 for h, w_ in shapes]
+        bbox = [torch.relu(torch.randn((B, 4, h, w_), device=dev, generator=g) + 1) for h, w_ in shapes]
+        iou = [torch.randn((B, 1, h, w_), device=dev, generator=g) for h, w_ in shapes]
+        sets.append(dict(counts=counts, off=off, boxes=boxes, labels=labels, bits=bits, seeds=seeds, idx=idx, w=w, cls=cls, bbox=bbox,
+                         iou=iou, gh=gh, gw=gw, pairs=sum(counts) * Ppts))
+    lcfg = F.LossConfig()
+
+    def timeit(fn, iters=60):
+        for i in range(3):
+            fn(sets[i % R])
+        torch.cuda.synchronize()
+        gs, keepalive = [], []
+        for s in sets:   # graph replays: no Python/ctypes time between the launches
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                keepalive.append(fn(s))
+            gs.append(g)
+        for i in range(R):
+            gs[i].replay()
+        torch.cuda.synchronize()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for i in range(iters):
+            gs[i % R].replay()
+        b.record()
+        torch.cuda.synchronize()
+        return a.elapsed_time(b) * 1e3 / iters
+
+    t_loss = timeit(lambda s: F.loss_fwd_bwd(geom, C, s["cls"], s["bbox"], s["iou"], s["counts"], s["boxes"], s["labels"], s["idx"], s["w"],
+                                             lcfg, gt_offsets=s["off"]))
+    t_assign = timeit(lambda s: F.assign(geom, shapes, s["counts"], s["boxes"], s["bits"], (s["gh"], s["gw"]), seeds=s["seeds"],
+                                         gt_offsets=s["off"]))
+    loss_bytes = B * Ppts * (8 * C + 52)
+    gavg = float(np.mean([sum(s["counts"]) for s in sets])) / B
+    assign_bytes = B * (12 * Ppts + gavg * (16 + sets[0]["gh"] * ((sets[0]["gw"] + 31) // 32) * 4))   # idx i64 + w f32 out; boxes + bit masks in
+    return {"workload": wl.name + " (per-GPU share)", "loss_fwd_bwd": {"us": t_loss, "algorithmic_bytes": loss_bytes,
+                                                                        "achieved_GBps": loss_bytes / t_loss / 1e3,
+                                                                        "frac": loss_bytes / t_loss / 1e3 / peak_gbs},
+            "assign": {"us": t_assign, "algorithmic_bytes": assign_bytes, "achieved_GBps": assign_bytes / t_assign / 1e3,
+                       "frac": assign_bytes / t_assign / 1e3 / peak_gbs,
+                       "point_gt_pairs_per_s": float(np.mean([s["pairs"] for s in sets])) / (t_assign * 1e-6)}}
+
+
+def run_e2e(args, wl, B, host_sets, dev, P, F, world):
+    """The call a user of the reference makes: LabelAssignment (batched entry point) -> RADetHead.loss (+backward) ->
+    RADetHead.get_bboxes, fed from pinned HOST buffers every step; losses and detections are read back to the host."""
+    import torch
+    import torch.distributed as dist
+
+    la = P.LabelAssignment(anchor_generator_cfg=dict(type="AnchorGenerator", ratios=[1.0], octave_base_scale=8, scales_per_octave=1,
+                                                     strides=[8, 16, 32, 64, 128]),
+                           neg_threshold=0.2, positive_num=10, adapt_positive_num=False, balance_sample=True)
+    head = P.build_head(dict(type="RADetHead", num_classes=wl.C, in_channels=8, feat_channels=8, stacked_convs=1,
+                             norm_cfg=dict(type="GN", num_groups=4, requires_grad=True),
+                             test_cfg=dict(nms_pre=wl.nms_pre, score_thr=wl.score_thr, nms=dict(type="vote", **NMS_CFG),
+                                           max_per_img=wl.max_per_img))).to(dev)
+    pin = lambda a: torch.from_numpy(np.ascontiguousarray(a)).pin_memory()
+    hs = []
+    for batch, ho in host_sets:
+        hs.append(dict(batch=batch, boxes=[pin(im.gt_bboxes) for im in batch], labels=[pin(im.gt_labels) for im in batch],
+                       grids=[pin(syn.sample_grid(im.masks)) for im in batch],
+                       seeds=pin(np.asarray([im.seed for im in batch], np.int32)),
+                       cls=[pin(m) for m in ho.cls], bbox=[pin(m) for m in ho.bbox], iou=[pin(m) for m in ho.iou],
+                       metas=syn.img_metas(batch)))
+    h2d = sum(t.numel() * t.element_size() for t in hs[0]["boxes"] + hs[0]["labels"] + hs[0]["grids"] + hs[0]["cls"] + hs[0]["bbox"] +
+              hs[0]["iou"]) + hs[0]["seeds"].numel() * 4
+    d2h_box = [0]
+
+    def e2e_step(h):
+        up = lambda t: t.to(dev, non_blocking=True)
+        idx, w, used = la.assign_batch([(wl.H, wl.W)] * B, h["boxes"], h["grids"], seeds=up(h["seeds"]))
+        cls = [up(t).requires_grad_() for t in h["cls"]]
+        bbox = [up(t).requires_grad_() for t in h["bbox"]]
+        iou = [up(t).requires_grad_() for t in h["iou"]]
+        gtb = [up(t) for t in h["boxes"]]
+        gtl = [up(t) for t in h["labels"]]
+        losses = head.loss(cls, bbox, iou, gtb, gtl, idx, w, h["metas"])
+        total = losses["loss_cls"] + losses["loss_bbox"] + losses["loss_iou"]
+        total.backward()
+        res = head.get_bboxes([t.detach() for t in cls], [t.detach() for t in bbox], [t.detach() for t in iou], h["metas"], rescale=True)
+        lv = torch.stack([losses["loss_cls"].detach(), losses["loss_bbox"].detach(), losses["loss_iou"].detach()]).cpu()
+        d2h_box[0] = 12 + B * wl.max_per_img * (5 * 4 + 8) + 4 * B
+        return lv, res
+
+    n = max(10, min(args.steps, 300))
+    for i in range(5):
+        e2e_step(hs[i % len(hs)])
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for i in range(n):
+        e2e_step(hs[i % len(hs)])
+    torch.cuda.synchronize()
+    dt = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(dt, op=dist.ReduceOp.MAX)
+    dt = float(dt.item())
+    return {"value": world * B * n / dt, "unit": "images/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h_box[0]),
+            "steps": n, "ms_per_step": 1e3 * dt / n, "timing": "host wall clock between device synchronisations (max over ranks)",
+            "api": "plugin.LabelAssignment.assign_batch -> RADetHead.loss + backward -> RADetHead.get_bboxes (pinned host inputs)"}
+
+
+if __name__ == "__main__":
+    main()

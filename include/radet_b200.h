@@ -208,8 +208,8 @@ int radet_vote_nms(int32_t batch, const int32_t* offsets_host, const float* boxe
  *   score mode: how cluster / vote scores are formed from cls score S and centerness c
  *               (vote_wrapper.py:14-30): 0 = S*c (list/tuple), 1 = S ('cls'), 2 = c ('iou')
  * Outputs: dets f32 [B, max_per_img, 5], labels int64 [B, max_per_img], num_dets int32 [B].
- * workspace: radet_get_bboxes_workspace_bytes(); its first 256*ceil(B/8) bytes (the candidate counters) must be
- *        zero before the FIRST call; the kernels re-arm them. */
+ * workspace: radet_get_bboxes_workspace_bytes(); it must be zero-filled once before the FIRST call with a given
+ *        (grid, batch, classes, nms_pre) — the kernels re-arm their counters afterwards. */
 typedef struct {
   float score_thr;
   int32_t nms_pre;        /* <=0: no per-level limit */

@@ -68,6 +68,7 @@ struct MtWarp {
   // numpy mt19937_seed(): init_genrand recurrence; inherently sequential (lane 0).
   __device__ void seed(uint32_t s, int lane) {
     if (lane == 0) {
+#pragma unroll 8
       for (int i = 0; i < 624; ++i) {
         key[i] = s;
         s = 1812433253u * (s ^ (s >> 30)) + (uint32_t)(i + 1);
@@ -98,7 +99,9 @@ struct MtWarp {
     __syncwarp();
   }
   // Lane i < count receives the i-th of the next `count` doubles of random_sample() (count <= 32).
-  __device__ double draw(int count, int lane) {
+  __device__ double draw(int count, int lane) { return (double)draw53(count, lane) / 9007199254740992.0; }
+  // 53-bit integer X of the next doubles: random_sample() = X / 2^53 with X = (a >> 5) << 26 | (b >> 6)
+  __device__ unsigned long long draw53(int count, int lane) {
     const int qa = pos + 2 * lane, qb = qa + 1;
     uint32_t a = 0, b = 0;
     const bool act = lane < count;
@@ -115,7 +118,7 @@ struct MtWarp {
     }
     __syncwarp();
     const uint32_t ha = temper(a) >> 5, hb = temper(b) >> 6;
-    return ((double)ha * 67108864.0 + (double)hb) / 9007199254740992.0;
+    return ((unsigned long long)ha << 26) | (unsigned long long)hb;
   }
 };
 
@@ -155,9 +158,24 @@ template <int W32>
 __global__ void __launch_bounds__(kPairThreads)
 assign_pairs_kernel(GridDev grid, const int* __restrict__ gt_offsets, const float* __restrict__ gt_bboxes,
                     const uint32_t* __restrict__ mask_bits, int mask_h, int mask_pitch, int mask_step, int stage_masks,
-                    uint32_t* __restrict__ pair_bits /* [B][P][2*W32] */) {
+                    uint32_t* __restrict__ pair_bits /* [B][P][2*W32] */, const uint32_t* __restrict__ seeds,
+                    uint32_t* __restrict__ seeded_states /* [B][625] */, int pair_blocks) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int b = blockIdx.y;
+  if ((int)blockIdx.x == pair_blocks) {
+    // Extra CTA per image (seeded mode only): np.random.seed(seeds[b]) is a sequential 624-step recurrence; running
+    // it here, in the shadow of the pair tests on the other SMs, takes it off assign_resolve's critical path.
+    __shared__ uint32_t s_mtkey[624];
+    if (threadIdx.x < 32) {
+      MtWarp mt{s_mtkey, 624};
+      mt.seed(seeds[b], threadIdx.x);
+      mt.twist(threadIdx.x);   // first block of the stream
+      uint32_t* st = seeded_states + (int64_t)b * RADET_MT_STATE_WORDS;
+      for (int i = threadIdx.x; i < 624; i += 32) st[i] = s_mtkey[i];
+      if (threadIdx.x == 0) st[624] = 0u;
+    }
+    return;
+  }
   const int P = grid.off[grid.num_levels];
   const int g0 = gt_offsets[b], G = gt_offsets[b + 1] - g0;
   const int p = blockIdx.x * kPairThreads + threadIdx.x;
@@ -247,13 +265,32 @@ constexpr int kListCap = 16384;  // shared-memory capacity of the candidate-poin
 
 // t = max{c in [0,m] : fl64(c/m) <= x}: position in numpy's normalised cumulative sum of m equal weights
 // (cdf[j] = fl64((j+1)*p / (m*p)) = fl64((j+1)/m) exactly, because both products are exact in binary64).
+// fl64(c/m) <= x is decided from the sign of the exactly-rounded residual x*m - c (one DFMA); only inside the
+// half-ulp band above x is the IEEE division itself evaluated, so the result is identical to numpy's.
+__device__ __forceinline__ bool cdf_le(double c, double m, double x) {
+  const double s = fma(x, m, -c);
+  if (s >= 0.0) return true;                  // c/m <= x  =>  RN(c/m) <= x (x is representable)
+  if (s < -2.3e-16 * (m * x)) return false;   // c/m > x (1 + 2^-52): rounds above x
+  return __ddiv_rn(c, m) <= x;
+}
+// Same position from the 53-bit integer X (x = X / 2^53): floor(x*m) exactly by a 64x64 high multiply; the only other
+// possible answer is floor+1, and only when (t0+1)/m lies within half an ulp above x, i.e. when the residual
+// R = 2^53 - frac(X*m / 2^53)*2^53 is <= m (probability ~m*2^-53): then the exact fp64 test decides.
+__device__ __forceinline__ int cdf_search(double x, int m);
+__device__ __forceinline__ int cdf_search53(unsigned long long X, int m) {
+  const unsigned long long hi = __umul64hi(X << 11, (unsigned long long)m);   // floor(X*m / 2^53)
+  const unsigned long long lo = (X << 11) * (unsigned long long)m;            // frac * 2^64
+  const unsigned long long R = (0ull - lo) >> 11;                             // (1 - frac) * 2^53 (2^53 when frac == 0)
+  if (lo != 0ull && R <= (unsigned long long)m) return cdf_search((double)X / 9007199254740992.0, m);
+  return (int)hi;
+}
 __device__ __forceinline__ int cdf_search(double x, int m) {
-  long long t = (long long)(x * (double)m);
-  if (t < 0) t = 0;
-  if (t > m) t = m;
-  while (t < m && __ddiv_rn((double)(t + 1), (double)m) <= x) ++t;
-  while (t > 0 && __ddiv_rn((double)t, (double)m) > x) --t;
-  return (int)t;
+  const double dm = (double)m;
+  int t = (int)(x * dm);
+  t = max(0, min(t, m));
+  while (t < m && cdf_le((double)(t + 1), dm, x)) ++t;
+  while (t > 0 && !cdf_le((double)t, dm, x)) --t;
+  return t;
 }
 
 struct ResolveSmem {
@@ -262,7 +299,41 @@ struct ResolveSmem {
   int scan[34];
   int M;
   int changed;
+  int found[RADET_MAX_POSITIVE_NUM];
+  volatile int done;   // GTs (area ranks) whose selection is final: warps 1..31 write those outputs meanwhile
 };
+
+// warps 1..31 of the resolve CTA synchronise among themselves on named barrier 1 (warp 0 runs the RNG bring-up)
+constexpr int kWorkers = kResolveThreads - 32;
+__device__ __forceinline__ void worker_barrier() { asm volatile("bar.sync 1, %0;" ::"n"(kWorkers) : "memory"); }
+
+// exclusive prefix sum of one int per worker thread (threads 32..1023); scratch holds 33 ints
+__device__ __forceinline__ int worker_exclusive_scan(int v, int* scratch, int* total) {
+  const int lane = threadIdx.x & 31, ww = (threadIdx.x >> 5) - 1;  // worker warp 0..30
+  int inc = v;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    int t = __shfl_up_sync(kFull, inc, o);
+    if (lane >= o) inc += t;
+  }
+  worker_barrier();  // scratch reuse across calls
+  if (lane == 31) scratch[ww] = inc;
+  worker_barrier();
+  if (ww == 0) {
+    int s = lane < 31 ? scratch[lane] : 0;
+    int si = s;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      int t = __shfl_up_sync(kFull, si, o);
+      if (lane >= o) si += t;
+    }
+    scratch[lane] = si - s;
+    if (lane == 31) scratch[32] = si;
+  }
+  worker_barrier();
+  *total = scratch[32];
+  return scratch[ww] + inc - v;
+}
 
 __host__ __device__ inline size_t resolve_smem_bytes(int maxG, int K, bool list_in_smem) {
   size_t s = sizeof(ResolveSmem);
@@ -284,7 +355,8 @@ assign_resolve_kernel(GridDev grid, const int* __restrict__ gt_offsets, const fl
                       const double* __restrict__ uniforms, int n_uniform, const uint32_t* __restrict__ seeds,
                       uint32_t* __restrict__ mt_states, uint32_t* __restrict__ g_list, uint16_t* __restrict__ g_own,
                       int list_in_smem, int64_t* __restrict__ out_idx, float* __restrict__ out_w,
-                      int* __restrict__ consumed) {
+                      int* __restrict__ consumed, int state_writeback, long long* __restrict__ dbg) {
+#define RESOLVE_DBG(k) do { if (dbg && lane == 0) dbg[(int64_t)blockIdx.x * 16 + (k)] = clock64(); } while (0)
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
   const int P = grid.off[grid.num_levels];
@@ -326,123 +398,175 @@ assign_resolve_kernel(GridDev grid, const int* __restrict__ gt_offsets, const fl
     s_nsel[r] = 0;
   }
   if (tid < 8) S->F[tid] = 0u;
+  __syncthreads();
 
   const uint32_t* bits = pair_bits + (int64_t)b * P * (2 * W32);
-  // 1. ordered compaction of points that are a candidate of at least one GT; everything else keeps the defaults
+  const double* ub = uniforms ? uniforms + (int64_t)b * n_uniform : nullptr;
+  MtWarp mt{s_key, 624};
   int M = 0;
-  for (int base = 0; base < P; base += kResolveThreads) {
-    const int p = base + tid;
-    int flag = 0;
-    if (p < P) {
-      uint32_t any = 0;
-#pragma unroll
-      for (int w = 0; w < W32; ++w) any |= bits[(int64_t)p * (2 * W32) + w];
-      flag = any != 0u;
-      if (!flag) {
-        idx[p] = -1;
-        wt[p] = 1.0f;
-      }
-    }
-    int total;
-    const int pos = block_exclusive_scan(flag, S->scan, &total);
-    if (flag) list[M + pos] = (uint32_t)p;
-    M += total;
-  }
-  __syncthreads();
-
-  // 2. fixed point over the fallback set F
-  for (int round = 0; round <= G; ++round) {
-    if (tid < 8) S->A[tid] = 0u;
-    if (tid == 0) S->changed = 0;
-    __syncthreads();
-    uint32_t acc[W32];
-#pragma unroll
-    for (int w = 0; w < W32; ++w) acc[w] = 0u;
-    for (int e = tid; e < M; e += kResolveThreads) {
-      const uint32_t* pb = bits + (int64_t)list[e] * (2 * W32);
-#pragma unroll
-      for (int w = 0; w < W32; ++w) {
-        const uint32_t c = pb[w], v = pb[W32 + w];
-        const uint32_t cl = v | (c & S->F[w]);
-        if (cl) {
-          const uint32_t low = cl & (0u - cl);
-          if (v & low) acc[w] |= low;
-          break;
-        }
-      }
-    }
-#pragma unroll
-    for (int w = 0; w < W32; ++w) {
-      const uint32_t r = __reduce_or_sync(kFull, acc[w]);
-      if (lane == 0 && r) atomicOr(&S->A[w], r);
-    }
-    __syncthreads();
-    if (tid < W32) {
-      const int rem = G - tid * 32;
-      const uint32_t valid = rem >= 32 ? 0xffffffffu : (rem <= 0 ? 0u : ((1u << rem) - 1u));
-      const uint32_t nf = ~S->A[tid] & valid;
-      if (nf != S->F[tid]) {
-        S->F[tid] = nf;
-        S->changed = 1;
-      }
-    }
-    __syncthreads();
-    const int changed = S->changed;
-    __syncthreads();
-    if (!changed) break;
-  }
-
-  // 3. owners, member counts; unclaimed candidate points keep the defaults
-  for (int e = tid; e < M; e += kResolveThreads) {
-    const int p = (int)list[e];
-    const uint32_t* pb = bits + (int64_t)p * (2 * W32);
-    int r = -1;
-#pragma unroll
-    for (int w = 0; w < W32; ++w) {
-      const uint32_t cl = pb[W32 + w] | (pb[w] & S->F[w]);
-      if (cl) {
-        r = w * 32 + __ffs((int)cl) - 1;
-        break;
-      }
-    }
-    own[e] = (uint16_t)(r < 0 ? 0xffff : r);
-    if (r >= 0) {
-      atomicAdd(&s_nr[r], 1);
-    } else {
-      idx[p] = -1;
-      wt[p] = 1.0f;
-    }
-  }
-  __syncthreads();
-
-  // 4. numpy-legacy weighted choice per GT, in area order, from one sequential MT19937 stream (warp 0)
+  if (wid == 0) RESOLVE_DBG(0);
   if (wid == 0) {
-    MtWarp mt{s_key, 624};
-    const double* ub = uniforms ? uniforms + (int64_t)b * n_uniform : nullptr;
+    // ---- warp 0 (specialised): bring up the MT19937 state while the other 31 warps resolve the claiming.
+    // np.random.seed() is an inherently sequential 624-step recurrence (~6 us); it is fully hidden here.
     if (!ub) {
       if (mt_states) {
         const uint32_t* st = mt_states + (int64_t)b * RADET_MT_STATE_WORDS;
-        for (int i = lane; i < 624; i += 32) s_key[i] = st[i];
+        uint32_t tmp[20];
+#pragma unroll
+        for (int k = 0; k < 20; ++k) tmp[k] = (lane + 32 * k < 624) ? st[lane + 32 * k] : 0u;   // all loads in flight
         mt.pos = (int)st[624];
+#pragma unroll
+        for (int k = 0; k < 20; ++k)
+          if (lane + 32 * k < 624) s_key[lane + 32 * k] = tmp[k];
         __syncwarp();
       } else {
         mt.seed(seeds[b], lane);
       }
+      if (mt.pos >= 624) {  // first block of the stream
+        mt.twist(lane);
+        mt.pos = 0;
+      }
     }
+    RESOLVE_DBG(1);
+  } else {
+    // ---- warps 1..31 (992 worker threads, named barrier 1)
+    const int wt_ = tid - 32;
+    // 1. ordered compaction of points that are a candidate of at least one GT; everything else keeps the defaults.
+    //    Each worker owns `per` consecutive points (one block scan per tile of kWorkers*per points).
+    const int per = min(32, (P + kWorkers - 1) / kWorkers);
+    for (int base = 0; base < P; base += kWorkers * per) {
+      const int p0 = base + wt_ * per;
+      unsigned fl = 0u;
+      for (int k = 0; k < per; ++k) {
+        const int p = p0 + k;
+        if (p < P) {
+          uint32_t any = 0;
+#pragma unroll
+          for (int w = 0; w < W32; ++w) any |= bits[(int64_t)p * (2 * W32) + w];
+          if (any) fl |= 1u << k;
+        }
+      }
+      for (int k = 0; k < per; ++k) {
+        const int p = p0 + k;
+        if (p < P && !((fl >> k) & 1u)) {
+          idx[p] = -1;
+          wt[p] = 1.0f;
+        }
+      }
+      int total;
+      int pos = M + worker_exclusive_scan(__popc(fl), S->scan, &total);
+      while (fl) {
+        const int k = __ffs((int)fl) - 1;
+        fl &= fl - 1u;
+        list[pos++] = (uint32_t)(p0 + k);
+      }
+      M += total;
+    }
+    worker_barrier();
+
+    // 2. fixed point over the fallback set F
+    for (int round = 0; round <= G; ++round) {
+      if (wt_ < 8) S->A[wt_] = 0u;
+      if (wt_ == 0) S->changed = 0;
+      worker_barrier();
+      uint32_t acc[W32];
+#pragma unroll
+      for (int w = 0; w < W32; ++w) acc[w] = 0u;
+      for (int e = wt_; e < M; e += kWorkers) {
+        const uint32_t* pb = bits + (int64_t)list[e] * (2 * W32);
+#pragma unroll
+        for (int w = 0; w < W32; ++w) {
+          const uint32_t c = pb[w], v = pb[W32 + w];
+          const uint32_t cl = v | (c & S->F[w]);
+          if (cl) {
+            const uint32_t low = cl & (0u - cl);
+            if (v & low) acc[w] |= low;
+            break;
+          }
+        }
+      }
+#pragma unroll
+      for (int w = 0; w < W32; ++w) {
+        const uint32_t r = __reduce_or_sync(kFull, acc[w]);
+        if (lane == 0 && r) atomicOr(&S->A[w], r);
+      }
+      worker_barrier();
+      if (wt_ < W32) {
+        const int rem = G - wt_ * 32;
+        const uint32_t valid = rem >= 32 ? 0xffffffffu : (rem <= 0 ? 0u : ((1u << rem) - 1u));
+        const uint32_t nf = ~S->A[wt_] & valid;
+        if (nf != S->F[wt_]) {
+          S->F[wt_] = nf;
+          S->changed = 1;
+        }
+      }
+      worker_barrier();
+      const int changed = S->changed;
+      worker_barrier();
+      if (!changed) break;
+    }
+
+    // 3. owners, member counts; unclaimed candidate points keep the defaults
+    for (int e = wt_; e < M; e += kWorkers) {
+      const int p = (int)list[e];
+      const uint32_t* pb = bits + (int64_t)p * (2 * W32);
+      int r = -1;
+#pragma unroll
+      for (int w = 0; w < W32; ++w) {
+        const uint32_t cl = pb[W32 + w] | (pb[w] & S->F[w]);
+        if (cl) {
+          r = w * 32 + __ffs((int)cl) - 1;
+          break;
+        }
+      }
+      own[e] = (uint16_t)(r < 0 ? 0xffff : r);
+      if (r >= 0) {
+        atomicAdd(&s_nr[r], 1);
+      } else {
+        idx[p] = -1;
+        wt[p] = 1.0f;
+      }
+    }
+    if (wt_ == 0) {
+      S->M = M;
+      S->done = 0;
+    }
+    if (wid == 1) RESOLVE_DBG(2);
+  }
+  __syncthreads();
+  M = S->M;
+  if (wid == 0) RESOLVE_DBG(3);
+
+  // 4. numpy-legacy weighted choice per GT, in area order, from one sequential MT19937 stream (warp 0).
+  //    Lanes = draws of one choice() round; found[] lives in shared memory.
+  if (wid == 0) {
+    int* s_found = S->found;
     int used = 0;
     bool overflow = false;
-    auto draw = [&](int count) -> double {
-      double u = 0.0;
+    // next `count` uniforms as 53-bit integers (bit 63 set: not of the form X/2^53 -> use the fp64 search on ux)
+    double ux = 0.0;
+    auto draw = [&](int count) -> unsigned long long {
+      unsigned long long X = 0ull;
       if (ub) {
         if (used + count > n_uniform) overflow = true;
-        else if (lane < count) u = ub[used + lane];
+        else if (lane < count) {
+          ux = ub[used + lane];
+          const double sc = ux * 9007199254740992.0;
+          X = (unsigned long long)sc;
+          if ((double)X != sc || !(ux >= 0.0 && ux < 1.0)) X = 1ull << 63;
+        }
       } else {
-        u = mt.draw(count, lane);
+        X = mt.draw53(count, lane);
       }
       used += count;
-      return u;
+      return X;
     };
+    auto search = [&](unsigned long long X, int m) -> int { return (X >> 63) ? cdf_search(ux, m) : cdf_search53(X, m); };
     for (int r = 0; r < G && !overflow; ++r) {
+      if (lane == 0 && r > 0) {
+        __threadfence_block();
+        S->done = r;                                                // selections of ranks < r are final
+      }
       const int n = s_nr[r];
       if (n == 0) continue;                                         // label_assignment.py:182-183: no RNG use
       int* selpos = s_selpos + r * K;
@@ -452,91 +576,86 @@ assign_resolve_kernel(GridDev grid, const int* __restrict__ gt_offsets, const fl
           if (lane == 0) s_nsel[r] = -1;
           continue;
         }
-        const double x = draw(K);                                   // :112 choice(n, K, p, replace=True)
+        const unsigned long long x = draw(K);                       // :112 choice(n, K, p, replace=True)
         if (overflow) break;
-        const int c = lane < K ? cdf_search(x, n) : -1;
-        int cnt = 0;
-        bool first = lane < K;
-        for (int j = 0; j < K; ++j) {
-          const int cj = __shfl_sync(kFull, c, j);
-          if (lane < K && cj == c) {
-            ++cnt;
-            if (j < lane) first = false;
-          }
-        }
+        const int c = lane < K ? search(x, n) : -1;
+        const unsigned peers = __match_any_sync(kFull, c);          // np.unique(chosen, return_counts=True), :125 (idle lanes share -1)
+        const bool first = lane < K && lane == __ffs((int)peers) - 1;
         const unsigned fm = __ballot_sync(kFull, first);
         if (first) {
           const int slot = __popc(fm & ((1u << lane) - 1u));
           selpos[slot] = c;
-          selcnt[slot] = (unsigned char)cnt;
+          selcnt[slot] = (unsigned char)__popc(peers);
         }
         if (lane == 0) s_nsel[r] = __popc(fm);
       } else {                                                      // :119 choice(n, K, p, replace=False)
-        int found = -1;  // lane k holds found[k]
         int n_uniq = 0;
+        const bool stamp = dbg && dbg[(int64_t)blockIdx.x * 16 + 11] == 0;
+        if (stamp) RESOLVE_DBG(11);
         while (n_uniq < K) {
           const int d = K - n_uniq, m = n - n_uniq;
-          const double x = draw(d);
+          const unsigned long long x = draw(d);
+          if (stamp && n_uniq == 0) RESOLVE_DBG(12);
           if (overflow) break;
           int pos = -1;
           if (lane < d) {
-            const int t = cdf_search(x, m);  // rank among the not-yet-found entries
-            pos = t;
-          }
-          // skip over found entries: pos = t + #{f in found : f <= pos}, iterated to its fixed point
-          {
-            const int base = pos;
-            int cur_pos = base;
-            for (int it = 0; it <= n_uniq; ++it) {
+            // rank among the not-yet-found entries, then skip over the found ones:
+            // pos = t + #{f in found : f <= pos}, iterated to its fixed point (found[] is tiny)
+            const int t = search(x, m);
+            int cur = t;
+            while (true) {
               int le = 0;
-              for (int j = 0; j < n_uniq; ++j) {
-                const int f = __shfl_sync(kFull, found, j);
-                le += (f <= cur_pos) ? 1 : 0;
-              }
-              const int nxt = base + le;
-              const bool same = (nxt == cur_pos);
-              cur_pos = nxt;
-              if (__all_sync(kFull, same || lane >= d)) break;
+              for (int j = 0; j < n_uniq; ++j) le += (s_found[j] <= cur) ? 1 : 0;
+              if (t + le == cur) break;
+              cur = t + le;
             }
-            pos = cur_pos;
+            pos = cur;
           }
-          // keep the first occurrence of each value, in draw order
-          bool first = lane < d;
-          for (int j = 0; j < d; ++j) {
-            const int pj = __shfl_sync(kFull, pos, j);
-            if (lane < d && j < lane && pj == pos) first = false;
-          }
+          if (stamp && n_uniq == 0) RESOLVE_DBG(13);
+          // keep the first occurrence of each value, in draw order (np.unique(return_index) + sort in choice())
+          const unsigned peers = __match_any_sync(kFull, pos);      // idle lanes all hold -1: at most d+1 distinct values
+          const bool first = lane < d && lane == __ffs((int)peers) - 1;
           const unsigned fm = __ballot_sync(kFull, first);
-          const int slot = n_uniq + __popc(fm & ((1u << lane) - 1u));
-          // scatter: lane `slot` must receive pos of this lane
-          for (int j = 0; j < d; ++j) {
-            const int pj = __shfl_sync(kFull, pos, j);
-            const int sj = __shfl_sync(kFull, slot, j);
-            const bool fj = (fm >> j) & 1u;
-            if (fj && lane == sj) found = pj;
-          }
+          __syncwarp();
+          if (first) s_found[n_uniq + __popc(fm & ((1u << lane) - 1u))] = pos;
+          __syncwarp();
+          if (stamp && n_uniq == 0) RESOLVE_DBG(14);
           n_uniq += __popc(fm);
         }
         if (overflow) break;
+        if (stamp) RESOLVE_DBG(15);
         if (lane < K) {
-          selpos[lane] = found;
+          selpos[lane] = s_found[lane];
           selcnt[lane] = 1;
         }
         if (lane == 0) s_nsel[r] = K;
       }
       __syncwarp();
     }
-    if (lane == 0) consumed[b] = overflow ? -1 : used;
-    if (!ub && mt_states) {  // hand the advanced generator back
+    __syncwarp();
+    if (lane == 0) {
+      __threadfence_block();
+      S->done = G;
+      consumed[b] = overflow ? -1 : used;
+    }
+    RESOLVE_DBG(4);
+    if (dbg && lane == 0) {
+      dbg[(int64_t)blockIdx.x * 16 + 8] = G;
+      dbg[(int64_t)blockIdx.x * 16 + 9] = used;
+      dbg[(int64_t)blockIdx.x * 16 + 10] = M;
+    }
+    if (!ub && mt_states && state_writeback && used > 0) {  // hand the advanced generator back (untouched if nothing was drawn)
       uint32_t* st = mt_states + (int64_t)b * RADET_MT_STATE_WORDS;
       for (int i = lane; i < 624; i += 32) st[i] = s_key[i];
       if (lane == 0) st[624] = (uint32_t)mt.pos;
     }
   }
-  __syncthreads();
-
-  // 5. one warp per GT: walk its members in ascending point order, selected -> positive, others -> ignore
-  for (int r = wid; r < G; r += kResolveThreads / 32) {
+  // 5. (warps 1..31, overlapped with the sampling of later GTs) one warp per GT: walk its members in ascending point
+  //    order, selected -> positive, others -> ignore
+  if (wid > 0)
+  for (int r = wid - 1; r < G; r += kResolveThreads / 32 - 1) {
+    while (S->done <= r) __nanosleep(20);
+    __threadfence_block();
     if (s_nr[r] == 0) continue;
     const int gt1 = s_rank2gt[r] + 1;
     const int nsel = s_nsel[r];
@@ -560,6 +679,7 @@ assign_resolve_kernel(GridDev grid, const int* __restrict__ gt_offsets, const fl
       running += __popc(ball);
     }
   }
+  if (wid == 1) RESOLVE_DBG(5);
 }
 
 }  // namespace radet
@@ -596,7 +716,8 @@ extern "C" size_t radet_assign_workspace_bytes(const radet_grid_t* grid, int32_t
   if (make_grid_dev(grid, &g) != RADET_OK || batch <= 0) return 0;
   const size_t P = (size_t)g.off[g.num_levels];
   // pair bits (worst case 8 words x 2) + global fallback list (u32) + owners (u16)
-  return align_up((size_t)batch * P * 16 * 4, 256) + align_up((size_t)batch * P * 4, 256) + align_up((size_t)batch * P * 2, 256);
+  return align_up((size_t)batch * P * 16 * 4, 256) + align_up((size_t)batch * P * 4, 256) + align_up((size_t)batch * P * 2, 256) +
+         align_up((size_t)batch * RADET_MT_STATE_WORDS * 4, 256);
 }
 
 extern "C" int radet_assign(const radet_grid_t* grid, int32_t batch, const int32_t* gt_offsets, const int32_t* gt_offsets_host,
@@ -634,6 +755,8 @@ extern "C" int radet_assign(const radet_grid_t* grid, int32_t batch, const int32
   uint32_t* g_list = reinterpret_cast<uint32_t*>(ws);
   ws += align_up((size_t)batch * P * 4, 256);
   uint16_t* g_own = reinterpret_cast<uint16_t*>(ws);
+  ws += align_up((size_t)batch * P * 2, 256);
+  uint32_t* seeded_states = reinterpret_cast<uint32_t*>(ws);
   cudaStream_t st = (cudaStream_t)stream;
   const int W = words_for(maxG > 0 ? maxG : 1);
   const int mask_pitch = (mask_w + 31) / 32;
@@ -644,7 +767,9 @@ extern "C" int radet_assign(const radet_grid_t* grid, int32_t batch, const int32
     stage_masks = 0;
     pair_smem = (size_t)Gp * (16 + 16 + 4 + 4) + 32;
   }
-  dim3 pgrid((P + kPairThreads - 1) / kPairThreads, batch);
+  const int pair_blocks = (P + kPairThreads - 1) / kPairThreads;
+  dim3 pgrid(pair_blocks + (seeds ? 1 : 0), batch);
+  uint32_t* states_arg = seeds ? seeded_states : mt_states;
   const bool list_in_smem = P <= kListCap;
   const int mg = maxG > 0 ? maxG : 1;
   const size_t rs = resolve_smem_bytes(mg, positive_num, list_in_smem);
@@ -652,13 +777,17 @@ extern "C" int radet_assign(const radet_grid_t* grid, int32_t batch, const int32
   do {                                                                                                                   \
     cudaFuncSetAttribute(assign_pairs_kernel<WW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pair_smem);          \
     assign_pairs_kernel<WW><<<pgrid, kPairThreads, pair_smem, st>>>(g, gt_offsets, gt_bboxes, mask_bits, mask_h,         \
-                                                                     mask_pitch, mask_step, stage_masks, pair_bits);     \
+                                                                     mask_pitch, mask_step, stage_masks, pair_bits,      \
+                                                                     seeds, seeded_states, pair_blocks);                 \
     RADET_LAUNCH_CHECK();                                                                                                \
     cudaFuncSetAttribute(assign_resolve_kernel<WW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rs);               \
     assign_resolve_kernel<WW><<<batch, kResolveThreads, rs, st>>>(g, gt_offsets, gt_bboxes, pair_bits, mg, positive_num, \
-                                                                   balance_sample, uniforms, n_uniform, seeds, mt_states, \
+                                                                   balance_sample, uniforms, n_uniform, nullptr,          \
+                                                                   states_arg,                                            \
                                                                    g_list, g_own, list_in_smem ? 1 : 0,                  \
-                                                                   points_to_gt_index, points_weight, consumed);         \
+                                                                   points_to_gt_index, points_weight, consumed,          \
+                                                                   seeds ? 0 : 1,                                       \
+                                                                   static_cast<long long*>(g_debug_buf));               \
     RADET_LAUNCH_CHECK();                                                                                                \
   } while (0)
   switch (W) {

@@ -3,6 +3,7 @@
 
 namespace radet {
 std::atomic<uint64_t> g_launch_count{0};
+void* g_debug_buf = nullptr;
 }
 
 extern "C" const char* radet_version(void) { return "radet_b200 0.1.0 (sm_100a)"; }
@@ -14,3 +15,6 @@ extern "C" int64_t radet_num_points(const radet_grid_t* grid) {
   if (radet::make_grid_dev(grid, &g) != RADET_OK) return -1;
   return g.off[g.num_levels];
 }
+
+// Development aid (not part of the documented ABI): when set, some kernels write clock64() phase stamps there.
+extern "C" void radet_debug_set_buffer(void* device_buffer) { radet::g_debug_buf = device_buffer; }

@@ -10,6 +10,7 @@
 namespace radet {
 
 extern std::atomic<uint64_t> g_launch_count;
+extern void* g_debug_buf;  // optional device buffer for phase timestamps (development aid, see radet_debug_set_buffer)
 
 #define RADET_LAUNCH_CHECK()                      \
   do {                                            \

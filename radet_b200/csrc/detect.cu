@@ -2,22 +2,27 @@
 //
 // Reference semantics: ATSSHead.get_bboxes (atss_head.py:326-387) + RADetHead._get_bboxes_single
 // (radet_head.py:55-169), which loops over images and levels in Python, syncs the host per level, copies four
-// tensors per image to the CPU and runs the single-threaded O(n^2) vote_ext.cpp.  Here the whole batch is two
-// launches, nothing leaves the device:
+// tensors per image to the CPU and runs the single-threaded O(n^2) vote_ext.cpp (:70-353).  Class-aware NMS never
+// couples boxes of different labels, so the batch is decomposed into (image, class) problems.  Four launches,
+// nothing leaves the device:
 //
-//   detect_select_kernel  HBM-bound scan of the class logits IN PLACE (NCHW, 128-bit streaming loads): sigmoid,
-//                         strict `> score_thr`, survivors appended as (score, flat index) keys per (image, level).
-//   nms_image_kernel      one CTA per image, working set in shared memory: exact per-level top-k (radix select),
-//                         centerness gather, bitonic sort by cluster score, decode+clamp+rescale, grouping by label,
-//                         one warp per (image, class) segment doing the greedy clustering with warp-wide IoU tests,
-//                         seed ranking by block scan, then the sigma-filtered weighted box vote per kept cluster.
+//   detect_select_kernel   one CTA per (image, level, class chunk): HBM-bound scan of the class logits IN PLACE
+//                          (NCHW planes, 128-bit streaming loads), sigmoid, strict `> score_thr`; survivors are
+//                          staged in shared memory and appended with ONE global atomic per CTA.
+//   detect_bin_kernel      one CTA per (image, level): exact top-k (8-bit radix select on the unique
+//                          score|index keys) when a level has more than nms_pre candidates, centerness gather,
+//                          cluster-score key, append to the (image, class) bin.
+//   class_nms_kernel       one CTA per (image, class): bitonic sort by cluster score, decode+clamp+rescale,
+//                          warp-ballot IoU bit matrix in shared memory, sequential seed scan on bit rows by one
+//                          warp (member sets fall out as `row & alive`), sigma-filtered weighted box vote of every
+//                          cluster in member (= score) order.
+//   detect_rank_kernel     one CTA per image: top-max_per_img seeds over all classes (radix select + small sort),
+//                          writes dets / labels / count.
 //
 // All arithmetic that feeds a discrete decision or an output box uses explicit round-to-nearest intrinsics
 // (__fmul_rn/__fadd_rn/__fdiv_rn/__fsqrt_rn): no FMA contraction, same operation order as vote_ext.cpp, so keep
 // sets and voted boxes are bit-exact with the reference.
 #include <math.h>
-
-#include <type_traits>
 
 #include "common.cuh"
 
@@ -32,84 +37,204 @@ struct MapsDev {
 // torch's CUDA sigmoid: 1 / (1 + exp(-x)) in fp32 with IEEE division (radet_head.py:106-109 run on CUDA tensors)
 __device__ __forceinline__ float sigmoid_rn(float x) { return __fdiv_rn(1.0f, __fadd_rn(1.0f, expf(-x))); }
 
-constexpr int kSelThreads = 256;
 constexpr int kOrdLevelShift = 27;  // ord = level << 27 | flat (point*C + class)
+typedef unsigned long long u64;
 
-struct SelTable {
-  int uoff[RADET_MAX_LEVELS + 1];
-  int upl[RADET_MAX_LEVELS];
+// ------------------------------------------------------------------------------------------------ 1. select
+constexpr int kSelThreads = 256;
+constexpr int kSelChunk = 4;  // classes staged per flush
+
+struct SelPlan {
+  int bpl[RADET_MAX_LEVELS];       // CTAs per (image, level) plane = ceil(ceil(hw/4) / 256)
+  int boff[RADET_MAX_LEVELS + 1];  // CTA offset of each level inside one (image, class-chunk)
   int64_t coff[RADET_MAX_LEVELS + 1];  // candidate-buffer offset of each level inside one image (= C * off[l])
+  int cc, nj;
 };
 
 __global__ void __launch_bounds__(kSelThreads)
-detect_select_kernel(GridDev grid, SelTable tab, int B, int C, int cc, int nj, MapsDev maps, float thr, float x_lo,
-                     unsigned long long* __restrict__ cand, int* __restrict__ counts) {
-  const int U = tab.uoff[grid.num_levels];
-  const int64_t t = (int64_t)blockIdx.x * kSelThreads + threadIdx.x;
-  if (t >= (int64_t)U * nj) return;
-  const int j = (int)(t / U), u = (int)(t - (int64_t)j * U);
+detect_select_kernel(GridDev grid, SelPlan plan, int C, MapsDev maps, float thr, float x_lo, u64* __restrict__ cand,
+                     int* __restrict__ counts) {
+  __shared__ u64 s_keys[kSelThreads * 4 * kSelChunk];
+  __shared__ int s_cnt, s_base;
+  const int b = blockIdx.y, j = blockIdx.z;
   int l = 0;
 #pragma unroll
-  for (int k = 1; k < RADET_MAX_LEVELS; ++k) l += (k < grid.num_levels && u >= tab.uoff[k]) ? 1 : 0;
-  const int ul = u - tab.uoff[l];
-  const int b = ul / tab.upl[l];
-  const int q0 = 4 * (ul - b * tab.upl[l]);
+  for (int k = 1; k < RADET_MAX_LEVELS; ++k) l += (k < grid.num_levels && (int)blockIdx.x >= plan.boff[k]) ? 1 : 0;
   const int hw = grid.h[l] * grid.w[l];
-  const int nv = min(4, hw - q0);
+  const int q0 = 4 * (((int)blockIdx.x - plan.boff[l]) * kSelThreads + (int)threadIdx.x);
+  const int nv = min(4, hw - q0);  // <= 0: idle thread
   const bool vec = (hw & 3) == 0;
   const float* cp = maps.cls[l] + ((int64_t)b * C) * hw + q0;
-  unsigned long long* out = cand + (int64_t)b * tab.coff[grid.num_levels] + tab.coff[l];
+  u64* out = cand + (int64_t)b * plan.coff[grid.num_levels] + plan.coff[l];
   int* cnt = counts + b * RADET_MAX_LEVELS + l;
-  const int c0 = j * cc, c1 = min(C, c0 + cc);
-#pragma unroll 4
-  for (int c = c0; c < c1; ++c) {
-    float xv[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
-    if (vec) {
-      const float4 v4 = ldg_stream4(cp + (int64_t)c * hw);
-      xv[0] = v4.x; xv[1] = v4.y; xv[2] = v4.z; xv[3] = v4.w;
-    } else {
-      for (int i = 0; i < nv; ++i) xv[i] = cp[(int64_t)c * hw + i];
-    }
+  const int c0 = j * plan.cc, c1 = min(C, c0 + plan.cc);
+  for (int cb = c0; cb < c1; cb += kSelChunk) {
+    if (threadIdx.x == 0) s_cnt = 0;
+    __syncthreads();
+    const int ce = min(c1, cb + kSelChunk);
+    float xv[kSelChunk][4];
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      if (i < nv && xv[i] > x_lo) {                 // cheap conservative prefilter on the logit
-        const float s = sigmoid_rn(xv[i]);
-        if (s > thr) {                              // radet_head.py:111 (strict)
-          const unsigned flat = (unsigned)(q0 + i) * (unsigned)C + (unsigned)c;
-          const int slot = atomicAdd(cnt, 1);
-          out[slot] = ((unsigned long long)__float_as_uint(s) << 32) | (unsigned long long)(0xffffffffu - flat);
+    for (int k = 0; k < kSelChunk; ++k) {   // all loads of the chunk in flight first
+      xv[k][0] = xv[k][1] = xv[k][2] = xv[k][3] = -INFINITY;
+      if (cb + k < ce && nv > 0) {
+        if (vec) {
+          const float4 v4 = ldg_stream4(cp + (int64_t)(cb + k) * hw);
+          xv[k][0] = v4.x; xv[k][1] = v4.y; xv[k][2] = v4.z; xv[k][3] = v4.w;
+        } else {
+          for (int i = 0; i < nv; ++i) xv[k][i] = cp[(int64_t)(cb + k) * hw + i];
         }
       }
     }
+#pragma unroll
+    for (int k = 0; k < kSelChunk; ++k) {
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        if (i < nv && xv[k][i] > x_lo) {            // conservative prefilter on the logit
+          const float s = sigmoid_rn(xv[k][i]);
+          if (s > thr) {                            // radet_head.py:111 (strict)
+            const unsigned flat = (unsigned)(q0 + i) * (unsigned)C + (unsigned)(cb + k);
+            s_keys[atomicAdd(&s_cnt, 1)] = ((u64)__float_as_uint(s) << 32) | (u64)(0xffffffffu - flat);
+          }
+        }
+      }
+    }
+    __syncthreads();
+    const int n = s_cnt;
+    if (threadIdx.x == 0 && n) s_base = atomicAdd(cnt, n);
+    __syncthreads();
+    for (int i = threadIdx.x; i < n; i += kSelThreads) out[s_base + i] = s_keys[i];
+    __syncthreads();
   }
 }
 
-// ------------------------------------------------------------------------------------------------ per-image NMS
-constexpr int kNmsThreads = 1024;
-constexpr int kNmsCap = 5120;       // shared-memory capacity (>= 5 levels x nms_pre 1000)
-constexpr int kNmsCapPad = 8192;
+// ------------------------------------------------------------------------------------------------ 2. top-k + binning
+constexpr int kBinThreads = 1024;
 
-template <typename IdxT>
-struct NmsArrays {
-  unsigned long long* keys;  // [pad]
-  float4* box;               // [cap] sorted by cluster score
-  float* cs;                 // [cap]
-  int* lab;                  // [cap]
-  IdxT* owner;               // [cap] -1 free, -2 dropped, else seed position
-  IdxT* perm;                // [cap] label-grouped order -> score order
-  IdxT* ipos;                // [cap] inverse of perm
-  float* vs;                 // [cap] (global) vote score, possibly iou-weighted
-  int* orig;                 // [cap] (global) row of the input list / ord
+// k-th largest of `n` unique 64-bit keys (k >= 1): returns the smallest key to keep.  Block-wide, 8-bit radix passes
+// from the top; stops as soon as the selected bucket is needed entirely.
+__device__ u64 radix_select_kth(const u64* __restrict__ src, int n, int k, int* s_hist, int* s_misc) {
+  u64 prefix = 0ull, pmask = 0ull;
+  const int tid = threadIdx.x, nt = blockDim.x, lane = tid & 31;
+  for (int shift = 56; shift >= 0; shift -= 8) {
+    for (int i = tid; i < 256; i += nt) s_hist[i] = 0;
+    __syncthreads();
+    for (int i = tid; i < n; i += nt) {
+      const u64 key = src[i];
+      if ((key & pmask) == prefix) atomicAdd(&s_hist[(int)((key >> shift) & 0xffull)], 1);
+    }
+    __syncthreads();
+    if (tid < 32) {  // suffix sums over 256 bins: lane holds bins [8*lane, 8*lane+8)
+      int h[8], s = 0;
+#pragma unroll
+      for (int q = 0; q < 8; ++q) {
+        h[q] = s_hist[8 * lane + q];
+        s += h[q];
+      }
+      int suf = s;  // inclusive suffix over lanes >= lane
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const int t = __shfl_down_sync(kFull, suf, o);
+        if (lane + o < 32) suf += t;
+      }
+      const int above = suf - s;  // elements in bins of higher lanes
+      if (above < k && k <= suf) {
+        int acc = above, bin = 7;
+        for (; bin > 0; --bin) {
+          if (acc + h[bin] >= k) break;
+          acc += h[bin];
+        }
+        s_misc[0] = 8 * lane + bin;
+        s_misc[1] = k - acc;      // rank inside the bucket
+        s_misc[2] = h[bin];       // bucket population
+      }
+    }
+    __syncthreads();
+    prefix |= (u64)s_misc[0] << shift;
+    pmask |= 0xffull << shift;
+    k = s_misc[1];
+    const bool whole = (s_misc[2] == k);
+    __syncthreads();
+    if (whole) break;  // every key of this bucket is kept: threshold = prefix with zero low bits
+  }
+  return prefix;
+}
+
+struct BinParams {
+  GridDev grid;
+  MapsDev maps;
+  int64_t coff[RADET_MAX_LEVELS + 1];
+  int C, nms_pre, cs_mode, class_cap;
+  const u64* cand;
+  int* counts;        // [B][8] candidates per (image, level); re-armed here
+  u64* bins;          // [B][C][class_cap]
+  int* class_counts;  // [B][C]; re-armed by detect_rank_kernel
 };
 
-__device__ __forceinline__ void bitonic_sort_desc(unsigned long long* keys, int npad) {
+__global__ void __launch_bounds__(kBinThreads)
+detect_bin_kernel(BinParams p) {
+  __shared__ int s_hist[256], s_misc[4];
+  const int l = blockIdx.x, b = blockIdx.y, tid = threadIdx.x;
+  const GridDev& g = p.grid;
+  const u64* src = p.cand + (int64_t)b * p.coff[g.num_levels] + p.coff[l];
+  const int nl = p.counts[b * RADET_MAX_LEVELS + l];
+  __syncthreads();
+  if (tid == 0) p.counts[b * RADET_MAX_LEVELS + l] = 0;  // re-arm for the next call
+  if (nl == 0) return;
+  u64 kth = 0ull;
+  if (p.nms_pre > 0 && nl > p.nms_pre) kth = radix_select_kth(src, nl, p.nms_pre, s_hist, s_misc);  // radet_head.py:112-122
+  const int hw = g.h[l] * g.w[l];
+  for (int i = tid; i < nl; i += kBinThreads) {
+    const u64 key = src[i];
+    if (key < kth) continue;
+    const float S = __uint_as_float((unsigned)(key >> 32));
+    const unsigned flat = 0xffffffffu - (unsigned)(key & 0xffffffffull);
+    const int q = (int)(flat / (unsigned)p.C);
+    const int c = (int)(flat - (unsigned)q * (unsigned)p.C);
+    float cs = S;
+    if (p.cs_mode != 1) {
+      const float ctr = sigmoid_rn(p.maps.iou[l][(int64_t)b * hw + q]);        // radet_head.py:109
+      cs = p.cs_mode == 0 ? __fmul_rn(S, ctr) : ctr;                            // vote_wrapper.py:14-21
+    }
+    const unsigned ord = ((unsigned)l << kOrdLevelShift) | flat;
+    const int slot = atomicAdd(&p.class_counts[b * p.C + c], 1);
+    if (slot < p.class_cap)
+      p.bins[((int64_t)b * p.C + c) * p.class_cap + slot] = ((u64)float_order_key(cs) << 32) | (u64)(0xffffffffu - ord);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ 3. per-class NMS + vote
+constexpr int kClsThreads = 512;
+constexpr int kMaskItems = 512;                  // bit-matrix path: up to 512 boxes of one class in one image
+constexpr int kMaskWords = kMaskItems / 32;
+
+struct ClsParams {
+  GridDev grid;
+  MapsDev maps;
+  int C, class_cap, rescale, cs_mode, vs_mode, mode, iou_enable;
+  float thr, sigma;
+  const int* img_shapes;
+  const float* scale_factors;
+  const int* class_counts;
+  u64* bins;           // sorted in place
+  int img_cap;         // seeds per image <= candidates per image
+  float* seed_out;     // [B][img_cap][5]  voted box + score of every cluster of the image (any order)
+  u64* seed_keys;      // [B][img_cap]     sort key of the seed
+  int* img_seed_count; // [B]              append cursor; re-armed by detect_rank_kernel
+  long long* dbg;      // optional phase timestamps (radet_debug_set_buffer)
+  // large-class fallback (m > kMaskItems): records in global memory
+  float4* g_box;       // [B][C][class_cap]
+  float* g_vs;         // [B][C][class_cap]
+  int* g_owner;        // [B][C][class_cap]
+};
+
+__device__ __forceinline__ void bitonic_sort_desc(u64* keys, int npad) {
   for (int k = 2; k <= npad; k <<= 1) {
     for (int j = k >> 1; j > 0; j >>= 1) {
       for (int t = threadIdx.x; t < (npad >> 1); t += blockDim.x) {
         const int i = ((t & ~(j - 1)) << 1) | (t & (j - 1));
         const int ixj = i | j;
         const bool desc = (i & k) == 0;
-        const unsigned long long a = keys[i], b = keys[ixj];
+        const u64 a = keys[i], b = keys[ixj];
         if ((a < b) == desc) {
           keys[i] = b;
           keys[ixj] = a;
@@ -120,382 +245,493 @@ __device__ __forceinline__ void bitonic_sort_desc(unsigned long long* keys, int 
   }
 }
 
-// vote_single_dim (vote_ext.cpp:8-35), fp32, sequential in member order, one rounding per operation
-template <typename IdxT>
-__device__ float vote_axis(const NmsArrays<IdxT>& A, int seed, int n, int axis) {
-  const int lab = A.lab[seed];
-  const int j0 = (int)A.ipos[seed];
+__device__ __forceinline__ float iou_rn(const float4& bi, float area_i, const float4& bj) {
+  // vote_ext.cpp:152-162 (no +1, no eps; 0/0 = NaN compares false)
+  const float xl = fmaxf(bj.x, bi.x), yt = fmaxf(bj.y, bi.y), xr = fminf(bj.z, bi.z), yb = fminf(bj.w, bi.w);
+  const float iw = fmaxf(0.f, __fsub_rn(xr, xl)), ih = fmaxf(0.f, __fsub_rn(yb, yt));
+  const float inter = __fmul_rn(iw, ih);
+  const float area_j = __fmul_rn(__fsub_rn(bj.z, bj.x), __fsub_rn(bj.w, bj.y));
+  return __fdiv_rn(inter, __fsub_rn(__fadd_rn(area_j, area_i), inter));
+}
+__device__ __forceinline__ float box_area_rn(const float4& b) { return __fmul_rn(__fsub_rn(b.z, b.x), __fsub_rn(b.w, b.y)); }
+// `iou > thr` with the division skipped for disjoint boxes: inter == 0 gives iou = +0 (or NaN for two empty boxes),
+// which is never > thr when thr >= 0 -- same decision, no rounding involved.
+__device__ __forceinline__ bool iou_gt(const float4& bi, float area_i, const float4& bj, float thr) {
+  const float xl = fmaxf(bj.x, bi.x), yt = fmaxf(bj.y, bi.y), xr = fminf(bj.z, bi.z), yb = fminf(bj.w, bi.w);
+  const float iw = fmaxf(0.f, __fsub_rn(xr, xl)), ih = fmaxf(0.f, __fsub_rn(yb, yt));
+  const float inter = __fmul_rn(iw, ih);
+  if (inter == 0.f && thr >= 0.f) return false;
+  const float area_j = __fmul_rn(__fsub_rn(bj.z, bj.x), __fsub_rn(bj.w, bj.y));
+  return __fdiv_rn(inter, __fsub_rn(__fadd_rn(area_j, area_i), inter)) > thr;
+}
+
+// decode one sorted key into box / cluster score / vote score (radet_head.py:123-143, tblr_bbox_coder.py:154-171)
+__device__ __forceinline__ void decode_item(const ClsParams& p, int b, int cls, u64 key, float4& bx, float& cs, float& vs) {
+  const GridDev& g = p.grid;
+  const unsigned ord = 0xffffffffu - (unsigned)(key & 0xffffffffull);
+  const int l = (int)(ord >> kOrdLevelShift);
+  const unsigned flat = ord & ((1u << kOrdLevelShift) - 1u);
+  const int q = (int)(flat / (unsigned)p.C);
+  const int hw = g.h[l] * g.w[l];
+  const int y = q / g.w[l], x = q - y * g.w[l];
+  const float st = (float)g.stride[l];
+  const float cx = (float)x * st, cy = (float)y * st;
+  const float side = __fmul_rn(g.anchor_scale, st);
+  const float* bp = p.maps.bbox[l] + (int64_t)b * 4 * hw + q;
+  const float T = __fmul_rn(__fmul_rn(bp[0], g.nrm), side), Bt = __fmul_rn(__fmul_rn(bp[hw], g.nrm), side);
+  const float L = __fmul_rn(__fmul_rn(bp[2 * hw], g.nrm), side), R = __fmul_rn(__fmul_rn(bp[3 * hw], g.nrm), side);
+  const float H = (float)p.img_shapes[2 * b], W = (float)p.img_shapes[2 * b + 1];
+  bx.x = fminf(fmaxf(__fsub_rn(cx, L), 0.f), W);
+  bx.y = fminf(fmaxf(__fsub_rn(cy, T), 0.f), H);
+  bx.z = fminf(fmaxf(__fadd_rn(cx, R), 0.f), W);
+  bx.w = fminf(fmaxf(__fadd_rn(cy, Bt), 0.f), H);
+  if (p.rescale) {                                                    // radet_head.py:141-143
+    const float4 sf = *reinterpret_cast<const float4*>(p.scale_factors + 4 * b);
+    bx.x = __fdiv_rn(bx.x, sf.x); bx.y = __fdiv_rn(bx.y, sf.y);
+    bx.z = __fdiv_rn(bx.z, sf.z); bx.w = __fdiv_rn(bx.w, sf.w);
+  }
+  const float S = sigmoid_rn(p.maps.cls[l][((int64_t)b * p.C + cls) * hw + q]);
+  const float ctr = sigmoid_rn(p.maps.iou[l][(int64_t)b * hw + q]);
+  cs = p.cs_mode == 0 ? __fmul_rn(S, ctr) : (p.cs_mode == 1 ? S : ctr);
+  vs = p.vs_mode == 0 ? __fmul_rn(S, ctr) : (p.vs_mode == 1 ? S : ctr);
+}
+
+// vote_single_dim (vote_ext.cpp:8-35) over a member list given as "seed + set bits of `mem` words" (ascending index =
+// descending cluster score = the reference's member order).  fp32, one rounding per operation.
+struct MemberIter {
+  const unsigned* words;
+  int nw, seed;
+  int w;
+  unsigned cur;
+  bool first;
+  __device__ MemberIter(const unsigned* words_, int nw_, int seed_) : words(words_), nw(nw_), seed(seed_), w(-1), cur(0u), first(true) {}
+  __device__ int next() {  // -1 when exhausted
+    if (first) {
+      first = false;
+      return seed;
+    }
+    while (cur == 0u) {
+      if (++w >= nw) return -1;
+      cur = words[w];
+    }
+    const int bit = __ffs((int)cur) - 1;
+    cur &= cur - 1u;
+    return w * 32 + bit;
+  }
+};
+
+template <typename GetS, typename GetX>
+__device__ float vote_axis_members(const unsigned* words, int nw, int seed, GetS gs, GetX gx) {
   float ss = 0.f, acc = 0.f;
-  for (int j = j0; j < n; ++j) {
-    const int i = (int)A.perm[j];
-    if (A.lab[i] != lab) break;
-    if ((int)A.owner[i] != seed) continue;
-    const float s = A.vs[i];
-    const float x = reinterpret_cast<const float*>(&A.box[i])[axis];
-    ss = __fadd_rn(ss, s);
-    acc = __fadd_rn(acc, __fmul_rn(s, x));
+  {
+    MemberIter it(words, nw, seed);
+    for (int j = it.next(); j >= 0; j = it.next()) {
+      const float s = gs(j), x = gx(j);
+      ss = __fadd_rn(ss, s);
+      acc = __fadd_rn(acc, __fmul_rn(s, x));
+    }
   }
   const float mean = __fdiv_rn(acc, ss);
   float var = 0.f;
-  for (int j = j0; j < n; ++j) {
-    const int i = (int)A.perm[j];
-    if (A.lab[i] != lab) break;
-    if ((int)A.owner[i] != seed) continue;
-    const float s = A.vs[i];
-    const float x = reinterpret_cast<const float*>(&A.box[i])[axis];
-    const float d = __fsub_rn(x, mean);
-    var = __fadd_rn(var, __fmul_rn(__fmul_rn(s, d), d));
+  {
+    MemberIter it(words, nw, seed);
+    for (int j = it.next(); j >= 0; j = it.next()) {
+      const float d = __fsub_rn(gx(j), mean);
+      var = __fadd_rn(var, __fmul_rn(__fmul_rn(gs(j), d), d));
+    }
   }
   const float sd = __fsqrt_rn(__fdiv_rn(var, ss));
   const float lo = __fsub_rn(mean, sd), hi = __fadd_rn(mean, sd);
   float fs = 0.f, fx = 0.f;
-  for (int j = j0; j < n; ++j) {
-    const int i = (int)A.perm[j];
-    if (A.lab[i] != lab) break;
-    if ((int)A.owner[i] != seed) continue;
-    const float x = reinterpret_cast<const float*>(&A.box[i])[axis];
-    if (lo <= x && x <= hi) {
-      const float s = A.vs[i];
-      fx = __fadd_rn(fx, __fmul_rn(s, x));
-      fs = __fadd_rn(fs, s);
+  {
+    MemberIter it(words, nw, seed);
+    for (int j = it.next(); j >= 0; j = it.next()) {
+      const float x = gx(j);
+      if (lo <= x && x <= hi) {
+        const float s = gs(j);
+        fx = __fadd_rn(fx, __fmul_rn(s, x));
+        fs = __fadd_rn(fs, s);
+      }
     }
   }
   return __fdiv_rn(fx, fs);
 }
 
-struct NmsParams {
-  // head source
-  GridDev grid;
-  SelTable tab;
-  MapsDev maps;
-  int C;
-  const unsigned long long* cand;
-  int* counts;
-  const int* img_shapes;
-  const float* scale_factors;
-  int nms_pre, rescale, cs_mode, vs_mode;
-  // list source
-  const int* offsets;  // device copy of list offsets [batch+1]
-  const float* in_boxes;
-  const float* in_cs;
-  const float* in_vs;
-  const int64_t* in_labels;
-  // common
-  float thr, sigma;
-  int iou_enable, mode, max_num;
-  int cap;          // capacity of the per-image arrays
-  int out_stride;   // rows of out_* per image (head) ; list: rows start at offsets[b]
-  float* out_dets;
-  int64_t* out_labels;
-  int64_t* out_index;
-  int* num_out;
-  int64_t* instance_ids;
-  int64_t* clusters_num;
-  // global arrays (vs/orig always; everything when !kSmem)
-  unsigned char* gws;
-  size_t gws_per_image;
-};
-
-__host__ __device__ inline size_t nms_global_bytes(int cap, bool smem_variant) {
-  size_t s = (size_t)cap * 8;  // vs + orig
-  if (!smem_variant) {
-    int pad = 32;
-    while (pad < cap) pad <<= 1;
-    s += (size_t)pad * 8 + (size_t)cap * (16 + 4 + 4 + 4 + 4 + 4);
-  }
-  return (s + 255) & ~size_t(255);
-}
-
-template <bool kHead, bool kSmem>
-__global__ void __launch_bounds__(kNmsThreads)
-nms_image_kernel(NmsParams p) {
-  using IdxT = typename std::conditional<kSmem, short, int>::type;
+__global__ void __launch_bounds__(kClsThreads)
+class_nms_kernel(ClsParams p) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  __shared__ int s_scan[34];
-  __shared__ int s_n, s_nseg, s_hist[256], s_misc[4];
-  __shared__ unsigned long long s_prefix;
-  const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-  const int cap = p.cap;
-  NmsArrays<IdxT> A;
-  unsigned char* gw = p.gws + (size_t)b * p.gws_per_image;
-  A.vs = reinterpret_cast<float*>(gw);
-  A.orig = reinterpret_cast<int*>(gw + (size_t)cap * 4);
-  if (kSmem) {
-    unsigned char* c = smem_raw;
-    A.keys = reinterpret_cast<unsigned long long*>(c); c += (size_t)kNmsCapPad * 8;
-    A.box = reinterpret_cast<float4*>(c); c += (size_t)kNmsCap * 16;
-    A.cs = reinterpret_cast<float*>(c); c += (size_t)kNmsCap * 4;
-    A.lab = reinterpret_cast<int*>(c); c += (size_t)kNmsCap * 4;
-    A.owner = reinterpret_cast<IdxT*>(c); c += (size_t)kNmsCap * sizeof(IdxT);
-    A.perm = reinterpret_cast<IdxT*>(c); c += (size_t)kNmsCap * sizeof(IdxT);
-    A.ipos = reinterpret_cast<IdxT*>(c);
-  } else {
-    int pad = 32;
-    while (pad < cap) pad <<= 1;
-    unsigned char* c = gw + (size_t)cap * 8;
-    A.keys = reinterpret_cast<unsigned long long*>(c); c += (size_t)pad * 8;
-    A.box = reinterpret_cast<float4*>(c); c += (size_t)cap * 16;
-    A.cs = reinterpret_cast<float*>(c); c += (size_t)cap * 4;
-    A.lab = reinterpret_cast<int*>(c); c += (size_t)cap * 4;
-    A.owner = reinterpret_cast<IdxT*>(c); c += (size_t)cap * 4;
-    A.perm = reinterpret_cast<IdxT*>(c); c += (size_t)cap * 4;
-    A.ipos = reinterpret_cast<IdxT*>(c);
-  }
-  if (tid == 0) s_n = 0;
-  __syncthreads();
+  __shared__ int s_nseed, s_base;
+  const int c = blockIdx.x, b = blockIdx.y, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  const int bc = b * p.C + c;
+  const int m = min(p.class_counts[bc], p.class_cap);
+  if (m == 0) return;
+  u64* gkeys = p.bins + (int64_t)bc * p.class_cap;
+#define RADET_DBG(k) do { if (p.dbg && tid == 0) p.dbg[(int64_t)bc * 16 + (k)] = clock64(); } while (0)
+  RADET_DBG(0);
 
-  // ---------------------------------------------------------------- A. gather items, build sort keys
-  int n;
-  if (kHead) {
-    const GridDev& g = p.grid;
-    for (int l = 0; l < g.num_levels; ++l) {
-      const unsigned long long* src = p.cand + (int64_t)b * p.tab.coff[g.num_levels] + p.tab.coff[l];
-      const int nl = p.counts[b * RADET_MAX_LEVELS + l];
-      unsigned long long kth = 0ull;  // keep keys >= kth
-      if (p.nms_pre > 0 && nl > p.nms_pre) {
-        // exact k-th largest key by 8-bit radix select (keys are unique: score bits | ~flat index)
-        int k = p.nms_pre;
-        unsigned long long prefix = 0ull, pmask = 0ull;
-        for (int shift = 56; shift >= 0; shift -= 8) {
-          for (int i = tid; i < 256; i += kNmsThreads) s_hist[i] = 0;
-          __syncthreads();
-          for (int i = tid; i < nl; i += kNmsThreads) {
-            const unsigned long long key = src[i];
-            if ((key & pmask) == prefix) atomicAdd(&s_hist[(int)((key >> shift) & 0xffull)], 1);
-          }
-          __syncthreads();
-          if (tid == 0) {
-            int acc = 0, bin = 255;
-            for (; bin > 0; --bin) {
-              if (acc + s_hist[bin] >= k) break;
-              acc += s_hist[bin];
+  if (m <= kMaskItems) {
+    // ---------------- shared-memory path
+    u64* keys = reinterpret_cast<u64*>(smem_raw);                                   // [512]
+    float4* box = reinterpret_cast<float4*>(keys + kMaskItems);                     // [512]
+    float* vs = reinterpret_cast<float*>(box + kMaskItems);                         // [512]
+    float* cs = vs + kMaskItems;                                                    // [512]
+    unsigned* mask = reinterpret_cast<unsigned*>(cs + kMaskItems);                  // [512][W]
+    short* seeds = reinterpret_cast<short*>(mask + kMaskItems * kMaskWords);        // [512]
+    int npad = 32;
+    while (npad < m) npad <<= 1;
+    const int W = (m + 31) >> 5;
+    for (int i = tid; i < npad; i += kClsThreads) keys[i] = i < m ? gkeys[i] : 0ull;
+    __syncthreads();
+    RADET_DBG(1);
+    {
+      // bitonic sort by the first npad/2 threads only, synchronised on a named barrier of just those warps
+      const int nsort = max(32, npad >> 1);
+      if (tid < nsort) {
+        for (int k = 2; k <= npad; k <<= 1) {
+          for (int j = k >> 1; j > 0; j >>= 1) {
+            if (tid < (npad >> 1)) {
+              const int i = ((tid & ~(j - 1)) << 1) | (tid & (j - 1));
+              const int ixj = i | j;
+              const bool desc = (i & k) == 0;
+              const u64 a = keys[i], b2 = keys[ixj];
+              if ((a < b2) == desc) {
+                keys[i] = b2;
+                keys[ixj] = a;
+              }
             }
-            s_misc[0] = bin;
-            s_misc[1] = k - acc;
+            if (nsort > 32) asm volatile("bar.sync 2, %0;" ::"r"(nsort) : "memory");
+            else __syncwarp();
           }
-          __syncthreads();
-          prefix |= (unsigned long long)s_misc[0] << shift;
-          pmask |= 0xffull << shift;
-          k = s_misc[1];
-          __syncthreads();
         }
-        kth = prefix;
       }
-      const int hw = g.h[l] * g.w[l];
-      for (int i = tid; i < nl; i += kNmsThreads) {
-        const unsigned long long key = src[i];
-        if (key < kth) continue;
-        const float S = __uint_as_float((unsigned)(key >> 32));
-        const unsigned flat = 0xffffffffu - (unsigned)(key & 0xffffffffull);
-        const int q = (int)(flat / (unsigned)p.C);
-        float cs = S;
-        if (p.cs_mode != 1) {
-          const float ctr = sigmoid_rn(p.maps.iou[l][(int64_t)b * hw + q]);      // radet_head.py:109
-          cs = p.cs_mode == 0 ? __fmul_rn(S, ctr) : ctr;                          // vote_wrapper.py:14-21
+      __syncthreads();
+    }
+    RADET_DBG(2);
+    for (int i = tid; i < m; i += kClsThreads) {
+      float4 bx;
+      float c_, v_;
+      decode_item(p, b, c, keys[i], bx, c_, v_);
+      box[i] = bx;
+      cs[i] = c_;
+      vs[i] = v_;
+    }
+    __syncthreads();
+    RADET_DBG(3);
+    // IoU bit matrix, upper triangle: one warp per row i (round-robin), lane = column inside each 32-wide word.
+    // nzrow collects which rows have any overlap at all: only those take part in the sequential scan below.
+    unsigned* nzrow = reinterpret_cast<unsigned*>(seeds + kMaskItems);              // [W]
+    unsigned* seedbits = nzrow + kMaskWords;                                        // [W]
+    if (tid < kMaskWords) nzrow[tid] = 0u;
+    __syncthreads();
+    for (int i = wid; i < m; i += kClsThreads / 32) {
+      const float4 bi = box[i];
+      const float area_i = box_area_rn(bi);
+      unsigned any = 0u;
+      if (lane < (i >> 5)) mask[i * W + lane] = 0u;                 // words below the diagonal
+#pragma unroll 4
+      for (int wj = i >> 5; wj < W; ++wj) {
+        const int j = wj * 32 + lane;
+        const bool hit = (j > i && j < m) && iou_gt(bi, area_i, box[j], p.thr);     // vote_ext.cpp:169
+        const unsigned word = __ballot_sync(kFull, hit);
+        if (lane == 0) mask[i * W + wj] = word;
+        any |= word;
+      }
+      if (lane == 0 && any) atomicOr(&nzrow[i >> 5], 1u << (i & 31));
+    }
+    __syncthreads();
+    RADET_DBG(4);
+    // Sequential seed scan (warp 0, lanes = words of the alive set).  A box still alive when reached is a seed and
+    // removes `row & alive`; boxes whose row is empty cannot remove anything, so only non-empty rows are visited.
+    if (wid == 0) {
+      unsigned alive = 0u;
+      if (lane < W) {
+        const int rem = m - lane * 32;
+        alive = rem >= 32 ? 0xffffffffu : ((1u << rem) - 1u);
+      }
+      if (p.mode == RADET_NMS_GLOBAL_VOTE) {
+        // vote_ext.cpp:257-263: once a label has been emitted every later seed of it is dropped -> only box 0 clusters
+        alive = lane == 0 ? 1u : 0u;    // row 0 already is its member set (everything was alive)
+      } else {
+        const unsigned nz = lane < W ? nzrow[lane] : 0u;
+        int i = -1;
+        while (true) {
+          const int t = i + 1, wi = t >> 5;
+          unsigned wmask = lane > wi ? 0xffffffffu : 0u;
+          if (lane == wi) wmask = ~((1u << (t & 31)) - 1u);
+          const unsigned cand = alive & nz & wmask;
+          const int mine = cand ? lane * 32 + __ffs((int)cand) - 1 : 0x7fffffff;
+          const int nxt = __reduce_min_sync(kFull, mine);
+          if (nxt == 0x7fffffff) break;
+          i = nxt;
+          const unsigned row = (lane < W && lane >= (i >> 5)) ? mask[i * W + lane] : 0u;
+          if (lane < W) mask[i * W + lane] = row & alive;          // row i now holds the member set of cluster i
+          alive &= ~row;
         }
-        const unsigned ord = ((unsigned)l << kOrdLevelShift) | flat;
-        const int slot = atomicAdd(&s_n, 1);
-        if (slot < cap) A.keys[slot] = ((unsigned long long)float_order_key(cs) << 32) | (unsigned long long)(0xffffffffu - ord);
+      }
+      if (lane < kMaskWords) seedbits[lane] = alive;               // seeds = everything still alive
+      const int ns_ = __reduce_add_sync(kFull, __popc(alive));
+      if (lane == 0) {
+        s_nseed = ns_;
+        s_base = atomicAdd(&p.img_seed_count[b], ns_);            // this class's slice of the image's seed list
       }
     }
     __syncthreads();
-    n = min(s_n, cap);
-  } else {
-    const int r0 = p.offsets[b];
-    n = min(p.offsets[b + 1] - r0, cap);
-    for (int i = tid; i < n; i += kNmsThreads)
-      A.keys[i] = ((unsigned long long)float_order_key(p.in_cs[r0 + i]) << 32) | (unsigned long long)(0xffffffffu - (unsigned)i);
-  }
-  int npad = 32;
-  while (npad < n) npad <<= 1;
-  for (int i = n + tid; i < npad; i += kNmsThreads) A.keys[i] = 0ull;
-  __syncthreads();
-
-  const int out_base = kHead ? b * p.out_stride : p.offsets[b];
-  const int out_cap = kHead ? p.out_stride : (p.offsets[b + 1] - p.offsets[b]);
-  if (n == 0) {
-    if (tid == 0) p.num_out[b] = 0;
-    if (kHead && tid == 0)
-      for (int l = 0; l < p.grid.num_levels; ++l) p.counts[b * RADET_MAX_LEVELS + l] = 0;  // re-arm
+    RADET_DBG(5);
+    const int ns = s_nseed;
+    float* sout = p.seed_out + ((int64_t)b * p.img_cap + s_base) * 5;
+    u64* skeys_out = p.seed_keys + (int64_t)b * p.img_cap + s_base;
+    for (int i = tid; i < m; i += kClsThreads) {                    // seed list in index (= score) order
+      const unsigned wbits = seedbits[i >> 5];
+      if ((wbits >> (i & 31)) & 1u) {
+        int r = __popc(wbits & ((1u << (i & 31)) - 1u));
+        for (int w_ = 0; w_ < (i >> 5); ++w_) r += __popc(seedbits[w_]);
+        seeds[r] = (short)i;
+      }
+    }
+    __syncthreads();
+    // vote (all clusters; 4 threads per cluster, one per coordinate)
+    for (int t = tid; t < ns * 4; t += kClsThreads) {
+      const int s = t >> 2, axis = t & 3;
+      const int i = seeds[s];
+      float v;
+      if (p.mode == RADET_NMS_PLAIN) {
+        v = reinterpret_cast<const float*>(&box[i])[axis];
+      } else {
+        const float4 bi = box[i];
+        const float area_i = box_area_rn(bi);
+        auto gs = [&](int j) -> float {
+          float s_ = vs[j];
+          if (p.iou_enable && j != i) {   // vote_ext.cpp:164-167, exp() in double as in the reference build
+            const float d = __fsub_rn(1.f, iou_rn(bi, area_i, box[j]));
+            const float e = __fdiv_rn(-__fmul_rn(d, d), p.sigma);
+            s_ = (float)((double)s_ * exp((double)e));
+          }
+          return s_;
+        };
+        auto gx = [&](int j) -> float { return reinterpret_cast<const float*>(&box[j])[axis]; };
+        unsigned anym = 0u;
+        for (int w_ = i >> 5; w_ < W; ++w_) anym |= mask[i * W + w_];
+        if (anym == 0u) {
+          // singleton cluster: the same operation sequence as vote_single_dim with n = 1 (vote_ext.cpp:8-35)
+          const float s1 = vs[i], x = gx(i);
+          const float mean = __fdiv_rn(__fadd_rn(0.f, __fmul_rn(s1, x)), __fadd_rn(0.f, s1));
+          const float d = __fsub_rn(x, mean);
+          const float sd = __fsqrt_rn(__fdiv_rn(__fadd_rn(0.f, __fmul_rn(__fmul_rn(s1, d), d)), __fadd_rn(0.f, s1)));
+          const bool in = (__fsub_rn(mean, sd) <= x) && (x <= __fadd_rn(mean, sd));
+          v = in ? __fdiv_rn(__fadd_rn(0.f, __fmul_rn(s1, x)), __fadd_rn(0.f, s1)) : __fdiv_rn(0.f, 0.f);
+        } else {
+          v = vote_axis_members(mask + i * W, W, i, gs, gx);
+        }
+      }
+      sout[s * 5 + axis] = v;
+      if (axis == 0) {
+        sout[s * 5 + 4] = cs[i];       // cluster score = max over members = the seed's (vote_ext.cpp:196-197)
+        skeys_out[s] = keys[i];
+      }
+    }
+    __syncthreads();
+    RADET_DBG(6);
+    if (p.dbg && tid == 0) {
+      p.dbg[(int64_t)bc * 16 + 8] = m;
+      p.dbg[(int64_t)bc * 16 + 9] = ns;
+    }
     return;
   }
 
-  // ---------------------------------------------------------------- B. sort by cluster score (desc), ties by order
-  bitonic_sort_desc(A.keys, npad);
-
-  // ---------------------------------------------------------------- C. records in score order
-  for (int i = tid; i < n; i += kNmsThreads) {
-    const unsigned long long key = A.keys[i];
-    const unsigned ord = 0xffffffffu - (unsigned)(key & 0xffffffffull);
-    float4 bx;
-    float cs, vs;
-    int lab;
-    if (kHead) {
-      const GridDev& g = p.grid;
-      const int l = (int)(ord >> kOrdLevelShift);
-      const unsigned flat = ord & ((1u << kOrdLevelShift) - 1u);
-      const int q = (int)(flat / (unsigned)p.C);
-      lab = (int)(flat - (unsigned)q * (unsigned)p.C);
-      const int hw = g.h[l] * g.w[l];
-      const int y = q / g.w[l], x = q - y * g.w[l];
-      const float st = (float)g.stride[l];
-      const float cx = (float)x * st, cy = (float)y * st;
-      const float side = __fmul_rn(g.anchor_scale, st);
-      const float* bp = p.maps.bbox[l] + (int64_t)b * 4 * hw + q;
-      // tblr2bboxes (tblr_bbox_coder.py:154-171): (v * normalizer) * side, then centre -/+
-      const float T = __fmul_rn(__fmul_rn(bp[0], g.nrm), side), Bt = __fmul_rn(__fmul_rn(bp[hw], g.nrm), side);
-      const float L = __fmul_rn(__fmul_rn(bp[2 * hw], g.nrm), side), R = __fmul_rn(__fmul_rn(bp[3 * hw], g.nrm), side);
-      const float H = (float)p.img_shapes[2 * b], W = (float)p.img_shapes[2 * b + 1];
-      bx.x = fminf(fmaxf(__fsub_rn(cx, L), 0.f), W);
-      bx.y = fminf(fmaxf(__fsub_rn(cy, T), 0.f), H);
-      bx.z = fminf(fmaxf(__fadd_rn(cx, R), 0.f), W);
-      bx.w = fminf(fmaxf(__fadd_rn(cy, Bt), 0.f), H);
-      if (p.rescale) {                                                    // radet_head.py:141-143
-        const float4 sf = *reinterpret_cast<const float4*>(p.scale_factors + 4 * b);
-        bx.x = __fdiv_rn(bx.x, sf.x); bx.y = __fdiv_rn(bx.y, sf.y);
-        bx.z = __fdiv_rn(bx.z, sf.z); bx.w = __fdiv_rn(bx.w, sf.w);
-      }
-      const float S = sigmoid_rn(p.maps.cls[l][((int64_t)b * p.C + lab) * hw + q]);
-      const float ctr = sigmoid_rn(p.maps.iou[l][(int64_t)b * hw + q]);
-      cs = p.cs_mode == 0 ? __fmul_rn(S, ctr) : (p.cs_mode == 1 ? S : ctr);
-      vs = p.vs_mode == 0 ? __fmul_rn(S, ctr) : (p.vs_mode == 1 ? S : ctr);
-      A.orig[i] = (int)ord;
-    } else {
-      const int r = p.offsets[b] + (int)ord;
-      bx = *reinterpret_cast<const float4*>(p.in_boxes + 4 * (int64_t)r);
-      cs = p.in_cs[r];
-      vs = p.in_vs[r];
-      lab = (int)p.in_labels[r];
-      A.orig[i] = (int)ord;
-    }
-    A.box[i] = bx;
-    A.cs[i] = cs;
-    A.vs[i] = vs;
-    A.lab[i] = lab;
-    A.owner[i] = (IdxT)-1;
-  }
-  __syncthreads();
-
-  // ---------------------------------------------------------------- D. group by label (stable in score order)
-  for (int i = tid; i < npad; i += kNmsThreads)
-    A.keys[i] = i < n ? (((unsigned long long)(0xffffffffu - ((unsigned)A.lab[i] ^ 0x80000000u)) << 32) |
-                         (unsigned long long)(0xffffffffu - (unsigned)i))
-                      : 0ull;
-  __syncthreads();
-  bitonic_sort_desc(A.keys, npad);
-  for (int j = tid; j < n; j += kNmsThreads) {
-    const int i = (int)(0xffffffffu - (unsigned)(A.keys[j] & 0xffffffffull));
-    A.perm[j] = (IdxT)i;
-    A.ipos[i] = (IdxT)j;
-  }
-  __syncthreads();
-  // segment starts -> compacted into keys[] (reused as int list)
-  int* seg_start = reinterpret_cast<int*>(A.keys);
-  __syncthreads();
-  int nseg = 0;
-  for (int base = 0; base < n; base += kNmsThreads) {
-    const int j = base + tid;
-    int flag = 0;
-    if (j < n) flag = (j == 0) || (A.lab[(int)A.perm[j]] != A.lab[(int)A.perm[j - 1]]);
-    int total;
-    const int pos = block_exclusive_scan(flag, s_scan, &total);
-    // keys[] still holds sort output needed above only for perm (already extracted) -> safe to overwrite,
-    // but perm extraction of other threads must be complete: guaranteed by the __syncthreads before this loop
-    if (flag) seg_start[nseg + pos] = j;
-    nseg += total;
-  }
-  __syncthreads();
-
-  // ---------------------------------------------------------------- E. greedy clustering, one warp per segment
-  for (int sg = wid; sg < nseg; sg += kNmsThreads / 32) {
-    const int s0 = seg_start[sg], s1 = (sg + 1 < nseg) ? seg_start[sg + 1] : n;
-    for (int a = s0; a < s1; ++a) {
-      const int ia = (int)A.perm[a];
-      if ((int)A.owner[ia] != -1) continue;                 // warp-uniform
-      if (p.mode == RADET_NMS_GLOBAL_VOTE && a != s0) {     // vote_ext.cpp:257-263: label already emitted
-        if (lane == 0) A.owner[ia] = (IdxT)-2;
-        __syncwarp();
-        continue;
-      }
-      if (lane == 0) A.owner[ia] = (IdxT)ia;
-      const float4 bi = A.box[ia];
-      const float area_i = __fmul_rn(__fsub_rn(bi.z, bi.x), __fsub_rn(bi.w, bi.y));
-      for (int jj = a + 1 + lane; jj < s1; jj += 32) {
-        const int ij = (int)A.perm[jj];
-        if ((int)A.owner[ij] != -1) continue;
-        const float4 bj = A.box[ij];
-        const float xl = fmaxf(bj.x, bi.x), yt = fmaxf(bj.y, bi.y), xr = fminf(bj.z, bi.z), yb = fminf(bj.w, bi.w);
-        const float iw = fmaxf(0.f, __fsub_rn(xr, xl)), ih = fmaxf(0.f, __fsub_rn(yb, yt));
-        const float inter = __fmul_rn(iw, ih);
-        const float area_j = __fmul_rn(__fsub_rn(bj.z, bj.x), __fsub_rn(bj.w, bj.y));
-        const float iou = __fdiv_rn(inter, __fsub_rn(__fadd_rn(area_j, area_i), inter));  // vote_ext.cpp:162
-        if (iou > p.thr) {                                                                // :169 (strict; NaN -> false)
-          A.owner[ij] = (IdxT)ia;
-          if (p.iou_enable) {  // :164-167, exp() evaluated in double as in the reference build
-            const float d = __fsub_rn(1.f, iou);
-            const float e = __fdiv_rn(-__fmul_rn(d, d), p.sigma);
-            A.vs[ij] = (float)((double)A.vs[ij] * exp((double)e));
-          }
+  // ---------------- large-class fallback (m > 512): records in global memory, per-seed block-wide scan
+  float4* box = p.g_box + (int64_t)bc * p.class_cap;
+  float* vs = p.g_vs + (int64_t)bc * p.class_cap;
+  int* owner = p.g_owner + (int64_t)bc * p.class_cap;
+  int npad = 32;
+  while (npad < m) npad <<= 1;
+  // sort in place in the bin (padding lives beyond m only if npad <= class_cap; otherwise sort via odd-even fallback)
+  if (npad <= p.class_cap) {
+    for (int i = m + tid; i < npad; i += kClsThreads) gkeys[i] = 0ull;
+    __syncthreads();
+    bitonic_sort_desc(gkeys, npad);
+  } else {
+    // odd-even transposition sort (m steps); only reached when class_cap is not a power of two and m is close to it
+    for (int step = 0; step < m; ++step) {
+      for (int t = tid; 2 * t + (step & 1) + 1 < m; t += kClsThreads) {
+        const int i = 2 * t + (step & 1);
+        const u64 a = gkeys[i], b2 = gkeys[i + 1];
+        if (a < b2) {
+          gkeys[i] = b2;
+          gkeys[i + 1] = a;
         }
       }
-      __syncwarp();
+      __syncthreads();
     }
+  }
+  for (int i = tid; i < m; i += kClsThreads) {
+    float4 bx;
+    float c_, v_;
+    decode_item(p, b, c, gkeys[i], bx, c_, v_);
+    box[i] = bx;
+    vs[i] = v_;
+    owner[i] = -1;
   }
   __syncthreads();
-
-  // ---------------------------------------------------------------- F. rank seeds in score order
-  int nclu = 0;
-  // slots are written into keys[] region (as int) beyond the segment list: nseg <= n, so offset by n ints
-  int* slot = reinterpret_cast<int*>(A.keys) + n;
-  for (int base = 0; base < n; base += kNmsThreads) {
-    const int i = base + tid;
-    const int flag = (i < n && (int)A.owner[i] == i) ? 1 : 0;
-    int total;
-    const int pos = block_exclusive_scan(flag, s_scan, &total);
-    if (i < n) slot[i] = flag ? nclu + pos : -1;
-    nclu += total;
-  }
-  __syncthreads();
-  int nkeep = nclu;
-  if (p.max_num > 0 && nkeep > p.max_num) nkeep = p.max_num;
-  if (nkeep > out_cap) nkeep = out_cap;
-  if (tid == 0) p.num_out[b] = nkeep;
-
-  // ---------------------------------------------------------------- G. box voting for the kept clusters
-  for (int wk = tid; wk < n * 4; wk += kNmsThreads) {
-    const int i = wk >> 2, axis = wk & 3;
-    const int sl = slot[i];
-    if (sl < 0 || sl >= nkeep) continue;
-    float v;
-    if (p.mode == RADET_NMS_PLAIN) v = reinterpret_cast<const float*>(&A.box[i])[axis];
-    else v = vote_axis<IdxT>(A, i, n, axis);
-    float* o = p.out_dets + (int64_t)(out_base + sl) * 5;
-    o[axis] = v;
-    if (axis == 0) {
-      o[4] = A.cs[i];  // max cluster score of the cluster = the seed's (vote_ext.cpp:196-197)
-      p.out_labels[out_base + sl] = (int64_t)A.lab[i];
-      if (p.out_index) p.out_index[out_base + sl] = (int64_t)A.orig[i];
-    }
-  }
-  // ---------------------------------------------------------------- H. cluster ids / sizes (cluster_ext.cpp:4-87)
-  if (!kHead && p.instance_ids) {
-    const int r0 = p.offsets[b];
-    for (int i = tid; i < n; i += kNmsThreads) {
-      const int ow = (int)A.owner[i];
-      p.instance_ids[r0 + A.orig[i]] = ow >= 0 ? (int64_t)slot[ow] : 0;
-      if (p.clusters_num) p.clusters_num[r0 + A.orig[i]] = 0;
-    }
-    __syncthreads();
-    if (p.clusters_num) {
-      for (int i = tid; i < n; i += kNmsThreads) {
-        const int ow = (int)A.owner[i];
-        if (ow >= 0) atomicAdd(reinterpret_cast<unsigned long long*>(&p.clusters_num[r0 + A.orig[ow]]), 1ull);
+  int ns = 0;
+  for (int a = 0; a < m; ++a) {
+    if (owner[a] != -1) continue;                          // block-uniform (written before the last barrier)
+    if (p.mode == RADET_NMS_GLOBAL_VOTE && ns == 1) break;
+    const float4 bi = box[a];
+    const float area_i = box_area_rn(bi);
+    for (int j = a + 1 + tid; j < m; j += kClsThreads) {
+      if (owner[j] != -1) continue;
+      const float iou = iou_rn(bi, area_i, box[j]);
+      if (iou > p.thr) {
+        owner[j] = a;
+        if (p.iou_enable) {
+          const float d = __fsub_rn(1.f, iou);
+          const float e = __fdiv_rn(-__fmul_rn(d, d), p.sigma);
+          vs[j] = (float)((double)vs[j] * exp((double)e));
+        }
       }
     }
-  }
-  if (kHead) {
+    if (tid == 0) owner[a] = a;
+    ++ns;
     __syncthreads();
-    if (tid < p.grid.num_levels) p.counts[b * RADET_MAX_LEVELS + tid] = 0;  // re-arm the candidate counters
+  }
+  if (tid == 0) s_base = atomicAdd(&p.img_seed_count[b], ns);
+  __syncthreads();
+  float* sout = p.seed_out + ((int64_t)b * p.img_cap + s_base) * 5;
+  u64* skeys_out = p.seed_keys + (int64_t)b * p.img_cap + s_base;
+  // vote: thread per (cluster, axis), members found by scanning owners (O(m) per cluster; rare path)
+  for (int t = tid; t < ns * 4; t += kClsThreads) {
+    const int s = t >> 2, axis = t & 3;
+    // locate the s-th seed: seeds are the boxes with owner == self, in order
+    int i = -1, seen = 0;
+    for (int a = 0; a < m; ++a) {
+      if (owner[a] == a) {
+        if (seen == s) {
+          i = a;
+          break;
+        }
+        ++seen;
+      }
+    }
+    float v;
+    if (p.mode == RADET_NMS_PLAIN) {
+      v = reinterpret_cast<const float*>(&box[i])[axis];
+    } else {
+      float ss = 0.f, acc = 0.f;
+      for (int j = i; j < m; ++j)
+        if (owner[j] == i) {
+          const float s_ = vs[j], x = reinterpret_cast<const float*>(&box[j])[axis];
+          ss = __fadd_rn(ss, s_);
+          acc = __fadd_rn(acc, __fmul_rn(s_, x));
+        }
+      const float mean = __fdiv_rn(acc, ss);
+      float var = 0.f;
+      for (int j = i; j < m; ++j)
+        if (owner[j] == i) {
+          const float d = __fsub_rn(reinterpret_cast<const float*>(&box[j])[axis], mean);
+          var = __fadd_rn(var, __fmul_rn(__fmul_rn(vs[j], d), d));
+        }
+      const float sd = __fsqrt_rn(__fdiv_rn(var, ss));
+      const float lo = __fsub_rn(mean, sd), hi = __fadd_rn(mean, sd);
+      float fs = 0.f, fx = 0.f;
+      for (int j = i; j < m; ++j)
+        if (owner[j] == i) {
+          const float x = reinterpret_cast<const float*>(&box[j])[axis];
+          if (lo <= x && x <= hi) {
+            fx = __fadd_rn(fx, __fmul_rn(vs[j], x));
+            fs = __fadd_rn(fs, vs[j]);
+          }
+        }
+      v = __fdiv_rn(fx, fs);
+    }
+    sout[s * 5 + axis] = v;
+    if (axis == 0) {
+      float4 bx;
+      float c_, v_;
+      decode_item(p, b, c, gkeys[i], bx, c_, v_);
+      sout[s * 5 + 4] = c_;
+      skeys_out[s] = gkeys[i];
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ 4. rank + emit
+constexpr int kRankThreads = 1024;
+constexpr int kRankMaxOut = 4096;
+
+struct RankParams {
+  int C, img_cap, max_num;
+  const float* seed_out;
+  const u64* seed_keys;
+  int* img_seed_count;  // re-armed here
+  int* class_counts;    // re-armed here
+  float* dets;          // [B][max_num][5]
+  int64_t* labels;      // [B][max_num]
+  int* num_dets;        // [B]
+};
+
+__global__ void __launch_bounds__(kRankThreads)
+detect_rank_kernel(RankParams p) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  __shared__ int s_hist[256], s_misc[4], s_tot;
+  const int b = blockIdx.x, tid = threadIdx.x;
+  u64* sel = reinterpret_cast<u64*>(smem_raw);          // [pad(max_num)] selected keys
+  int* selidx = reinterpret_cast<int*>(sel + kRankMaxOut);  // position of each selected seed in the image's list
+  const int S = min(p.img_seed_count[b], p.img_cap);
+  __syncthreads();
+  if (tid == 0) {
+    p.img_seed_count[b] = 0;                               // re-arm for the next call
+    s_tot = 0;
+  }
+  for (int c = tid; c < p.C; c += kRankThreads) p.class_counts[b * p.C + c] = 0;
+  const int nkeep = min(S, p.max_num);
+  if (tid == 0) p.num_dets[b] = nkeep;
+  if (nkeep == 0) return;
+  const u64* all = p.seed_keys + (int64_t)b * p.img_cap;
+  u64 kth = 0ull;
+  if (S > nkeep) kth = radix_select_kth(all, S, nkeep, s_hist, s_misc);
+  int npad = 32;
+  while (npad < nkeep) npad <<= 1;
+  for (int i = tid; i < npad; i += kRankThreads) {
+    sel[i] = 0ull;
+    selidx[i] = 0;
+  }
+  __syncthreads();
+  for (int i = tid; i < S; i += kRankThreads) {
+    const u64 key = all[i];
+    if (key >= kth) {
+      const int slot = atomicAdd(&s_tot, 1);
+      sel[slot] = key;
+      selidx[slot] = i;
+    }
+  }
+  __syncthreads();
+  // descending bitonic sort of (key, index) pairs
+  for (int k = 2; k <= npad; k <<= 1) {
+    for (int j = k >> 1; j > 0; j >>= 1) {
+      for (int t = tid; t < (npad >> 1); t += kRankThreads) {
+        const int i = ((t & ~(j - 1)) << 1) | (t & (j - 1));
+        const int ixj = i | j;
+        const bool desc = (i & k) == 0;
+        const u64 a = sel[i], bk = sel[ixj];
+        if ((a < bk) == desc) {
+          sel[i] = bk;
+          sel[ixj] = a;
+          const int ti = selidx[i];
+          selidx[i] = selidx[ixj];
+          selidx[ixj] = ti;
+        }
+      }
+      __syncthreads();
+    }
+  }
+  for (int t = tid; t < nkeep * 5; t += kRankThreads) {
+    const int r = t / 5, k = t - 5 * r;
+    p.dets[((int64_t)b * p.max_num + r) * 5 + k] = p.seed_out[((int64_t)b * p.img_cap + selidx[r]) * 5 + k];
+    if (k == 0) {
+      // the class is part of the key's order field: ord = level << 27 | (point * C + class)
+      const unsigned ord = 0xffffffffu - (unsigned)(sel[r] & 0xffffffffull);
+      p.labels[(int64_t)b * p.max_num + r] = (int64_t)((ord & ((1u << kOrdLevelShift) - 1u)) % (unsigned)p.C);
+    }
   }
 }
 
@@ -504,36 +740,57 @@ nms_image_kernel(NmsParams p) {
 // ================================================================================================ C ABI
 using namespace radet;
 
-static size_t nms_smem_bytes() {
-  return (size_t)kNmsCapPad * 8 + (size_t)kNmsCap * (16 + 4 + 4 + 2 + 2 + 2);
+static int class_cap_of(const GridDev& g, int nms_pre) {
+  // one class can hold at most one candidate per point and level, and at most nms_pre per level
+  int64_t cap = 0;
+  for (int l = 0; l < g.num_levels; ++l) {
+    const int64_t hw = (int64_t)g.h[l] * g.w[l];
+    cap += (nms_pre > 0 && nms_pre < hw) ? nms_pre : hw;
+  }
+  return (int)(cap > (1 << 24) ? (1 << 24) : cap);
 }
 
-static int sel_plan(const GridDev& g, int B, int C, SelTable* tab, int* cc, int* nj) {
-  int64_t u = 0;
+static int sel_plan(const GridDev& g, int B, int C, SelPlan* plan) {
+  int blocks = 0;
   for (int l = 0; l < g.num_levels; ++l) {
     const int hw = g.h[l] * g.w[l];
     if ((int64_t)hw * C >= (1ll << kOrdLevelShift)) return RADET_E_UNSUPPORTED;
-    tab->uoff[l] = (int)u;
-    tab->upl[l] = (hw + 3) / 4;
-    tab->coff[l] = (int64_t)C * g.off[l];
-    u += (int64_t)B * tab->upl[l];
-    if (u > (1ll << 30)) return RADET_E_BADARG;
+    plan->bpl[l] = ((hw + 3) / 4 + kSelThreads - 1) / kSelThreads;
+    plan->boff[l] = blocks;
+    plan->coff[l] = (int64_t)C * g.off[l];
+    blocks += plan->bpl[l];
   }
   for (int l = g.num_levels; l <= RADET_MAX_LEVELS; ++l) {
-    tab->uoff[l] = (int)u;
-    tab->coff[l] = (int64_t)C * g.off[g.num_levels];
+    plan->boff[l] = blocks;
+    plan->coff[l] = (int64_t)C * g.off[g.num_levels];
   }
-  for (int l = g.num_levels; l < RADET_MAX_LEVELS; ++l) tab->upl[l] = 1;
-  const int64_t target_threads = 148ll * 2048 * 2;
-  int c = (int)((u * (int64_t)C + target_threads - 1) / target_threads);
-  if (c < 1) c = 1;
-  if (c > C) c = C;
-  *cc = c;
-  *nj = (C + c - 1) / c;
+  for (int l = g.num_levels; l < RADET_MAX_LEVELS; ++l) plan->bpl[l] = 0;
+  // class chunks: enough CTAs for ~4 per SM, otherwise as many classes per thread as possible (deeper load queues)
+  const int per_j = blocks * B;
+  int nj_target = (4 * 148 + per_j - 1) / per_j;
+  if (nj_target < 1) nj_target = 1;
+  int cc = (C + nj_target - 1) / nj_target;
+  if (cc < 1) cc = 1;
+  plan->cc = cc;
+  plan->nj = (C + cc - 1) / cc;
   return RADET_OK;
 }
 
-static int head_item_cap(const GridDev& g, int C, int nms_pre) {
+struct DetWs {
+  int* counts;        // [B][8]
+  int* class_counts;  // [B][C]
+  int* img_seed_count;  // [B]
+  u64* cand;          // [B][C*P]
+  u64* bins;          // [B][C][cap]
+  u64* seed_keys;     // [B][img_cap]
+  float* seed_out;    // [B][img_cap][5]
+  float4* g_box;      // [B][C][cap]
+  float* g_vs;
+  int* g_owner;
+  size_t total;
+};
+
+static int img_cap_of(const GridDev& g, int C, int nms_pre) {
   int64_t cap = 0;
   for (int l = 0; l < g.num_levels; ++l) {
     const int64_t full = (int64_t)g.h[l] * g.w[l] * C;
@@ -542,14 +799,34 @@ static int head_item_cap(const GridDev& g, int C, int nms_pre) {
   return (int)(cap > (1 << 28) ? (1 << 28) : cap);
 }
 
+static DetWs det_ws_layout(unsigned char* base, const GridDev& g, int B, int C, int cap, int img_cap) {
+  DetWs w{};
+  size_t off = 0;
+  auto take = [&](size_t bytes) {
+    unsigned char* p = base ? base + off : nullptr;
+    off += align_up(bytes, 256);
+    return p;
+  };
+  // the three counter arrays first: they are what must be zero before the first call
+  w.counts = reinterpret_cast<int*>(take((size_t)B * RADET_MAX_LEVELS * 4));
+  w.class_counts = reinterpret_cast<int*>(take((size_t)B * C * 4));
+  w.img_seed_count = reinterpret_cast<int*>(take((size_t)B * 4));
+  w.cand = reinterpret_cast<u64*>(take((size_t)B * g.off[g.num_levels] * C * 8));
+  w.bins = reinterpret_cast<u64*>(take((size_t)B * C * cap * 8));
+  w.seed_keys = reinterpret_cast<u64*>(take((size_t)B * img_cap * 8));
+  w.seed_out = reinterpret_cast<float*>(take((size_t)B * img_cap * 20));
+  w.g_box = reinterpret_cast<float4*>(take((size_t)B * C * cap * 16));
+  w.g_vs = reinterpret_cast<float*>(take((size_t)B * C * cap * 4));
+  w.g_owner = reinterpret_cast<int*>(take((size_t)B * C * cap * 4));
+  w.total = off;
+  return w;
+}
+
 extern "C" size_t radet_get_bboxes_workspace_bytes(const radet_grid_t* grid, int32_t batch, int32_t num_classes,
                                                    const radet_detect_cfg_t* cfg) {
   GridDev g;
   if (make_grid_dev(grid, &g) != RADET_OK || batch <= 0 || num_classes <= 0 || !cfg) return 0;
-  const int cap = head_item_cap(g, num_classes, cfg->nms_pre);
-  const bool smem = cap <= kNmsCap;
-  return align_up((size_t)batch * RADET_MAX_LEVELS * 4, 256) +
-         align_up((size_t)batch * g.off[g.num_levels] * num_classes * 8, 256) + (size_t)batch * nms_global_bytes(cap, smem);
+  return det_ws_layout(nullptr, g, batch, num_classes, class_cap_of(g, cfg->nms_pre), img_cap_of(g, num_classes, cfg->nms_pre)).total;
 }
 
 extern "C" int radet_get_bboxes(const radet_grid_t* grid, int32_t batch, int32_t num_classes, const radet_maps_t* maps,
@@ -562,28 +839,26 @@ extern "C" int radet_get_bboxes(const radet_grid_t* grid, int32_t batch, int32_t
   if (batch <= 0 || num_classes <= 0 || !maps || !img_shapes || !cfg || !dets || !labels || !num_dets || !workspace) return RADET_E_BADARG;
   if (cfg->rescale && !scale_factors) return RADET_E_BADARG;
   if (cfg->max_per_img <= 0 || cfg->nms_mode < 0 || cfg->nms_mode > 2) return RADET_E_BADARG;
+  if (cfg->max_per_img > kRankMaxOut || batch > 65535 || num_classes > 65535) return RADET_E_UNSUPPORTED;
   if (cfg->cluster_score_mode < 0 || cfg->cluster_score_mode > 2 || cfg->vote_score_mode < 0 || cfg->vote_score_mode > 2) return RADET_E_BADARG;
   if (workspace_bytes < radet_get_bboxes_workspace_bytes(grid, batch, num_classes, cfg) || (reinterpret_cast<uintptr_t>(workspace) & 255))
     return RADET_E_WORKSPACE;
-  NmsParams p{};
-  SelTable tab;
-  int cc, nj;
-  rc = sel_plan(g, batch, num_classes, &tab, &cc, &nj);
-  if (rc != RADET_OK) return rc;
+  MapsDev md;
   for (int l = 0; l < RADET_MAX_LEVELS; ++l) {
     const bool on = l < g.num_levels;
-    p.maps.cls[l] = on ? maps->cls[l] : nullptr;
-    p.maps.bbox[l] = on ? maps->bbox[l] : nullptr;
-    p.maps.iou[l] = on ? maps->iou[l] : nullptr;
-    if (on && (!p.maps.cls[l] || !p.maps.bbox[l] || !p.maps.iou[l])) return RADET_E_BADARG;
-    if (on && ((g.h[l] * g.w[l]) & 3) == 0 && (reinterpret_cast<uintptr_t>(p.maps.cls[l]) & 15)) return RADET_E_BADARG;
+    md.cls[l] = on ? maps->cls[l] : nullptr;
+    md.bbox[l] = on ? maps->bbox[l] : nullptr;
+    md.iou[l] = on ? maps->iou[l] : nullptr;
+    if (on && (!md.cls[l] || !md.bbox[l] || !md.iou[l])) return RADET_E_BADARG;
+    if (on && ((g.h[l] * g.w[l]) & 3) == 0 && (reinterpret_cast<uintptr_t>(md.cls[l]) & 15)) return RADET_E_BADARG;
   }
+  SelPlan plan;
+  rc = sel_plan(g, batch, num_classes, &plan);
+  if (rc != RADET_OK) return rc;
+  const int cap = class_cap_of(g, cfg->nms_pre);
+  const int img_cap = img_cap_of(g, num_classes, cfg->nms_pre);
+  DetWs w = det_ws_layout(static_cast<unsigned char*>(workspace), g, batch, num_classes, cap, img_cap);
   cudaStream_t st = (cudaStream_t)stream;
-  unsigned char* ws = static_cast<unsigned char*>(workspace);
-  int* counts = reinterpret_cast<int*>(ws);
-  ws += align_up((size_t)batch * RADET_MAX_LEVELS * 4, 256);
-  unsigned long long* cand = reinterpret_cast<unsigned long long*>(ws);
-  ws += align_up((size_t)batch * g.off[g.num_levels] * num_classes * 8, 256);
   // conservative logit prefilter: sigmoid(x) > thr  =>  x > logit(thr) - margin
   float x_lo = -INFINITY;
   const double thr = (double)cfg->score_thr;
@@ -592,102 +867,66 @@ extern "C" int radet_get_bboxes(const radet_grid_t* grid, int32_t batch, int32_t
     const double lg = log(thr / (1.0 - thr));
     x_lo = (float)(lg - 1e-3 * (1.0 + fabs(lg)));
   }
-  const int64_t sthreads = (int64_t)tab.uoff[g.num_levels] * nj;
-  detect_select_kernel<<<(unsigned)((sthreads + kSelThreads - 1) / kSelThreads), kSelThreads, 0, st>>>(
-      g, tab, batch, num_classes, cc, nj, p.maps, cfg->score_thr, x_lo, cand, counts);
+  detect_select_kernel<<<dim3(plan.boff[g.num_levels], batch, plan.nj), kSelThreads, 0, st>>>(g, plan, num_classes, md, cfg->score_thr,
+                                                                                              x_lo, w.cand, w.counts);
   RADET_LAUNCH_CHECK();
-  p.grid = g;
-  p.tab = tab;
-  p.C = num_classes;
-  p.cand = cand;
-  p.counts = counts;
-  p.img_shapes = img_shapes;
-  p.scale_factors = scale_factors;
-  p.nms_pre = cfg->nms_pre;
-  p.rescale = cfg->rescale;
-  p.cs_mode = cfg->cluster_score_mode;
-  p.vs_mode = cfg->vote_score_mode;
-  p.thr = cfg->iou_threshold;
-  p.sigma = cfg->sigma;
-  p.iou_enable = cfg->iou_enable;
-  p.mode = cfg->nms_mode;
-  p.max_num = cfg->max_per_img;
-  p.cap = head_item_cap(g, num_classes, cfg->nms_pre);
-  p.out_stride = cfg->max_per_img;
-  p.out_dets = dets;
-  p.out_labels = labels;
-  p.out_index = nullptr;
-  p.num_out = num_dets;
-  p.gws = ws;
-  const bool smem = p.cap <= kNmsCap;
-  p.gws_per_image = nms_global_bytes(p.cap, smem);
-  if (smem) {
-    cudaFuncSetAttribute(nms_image_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)nms_smem_bytes());
-    nms_image_kernel<true, true><<<batch, kNmsThreads, nms_smem_bytes(), st>>>(p);
-  } else {
-    nms_image_kernel<true, false><<<batch, kNmsThreads, 0, st>>>(p);
-  }
+  BinParams bp{};
+  bp.grid = g;
+  bp.maps = md;
+  for (int l = 0; l <= RADET_MAX_LEVELS; ++l) bp.coff[l] = plan.coff[l];
+  bp.C = num_classes;
+  bp.nms_pre = cfg->nms_pre;
+  bp.cs_mode = cfg->cluster_score_mode;
+  bp.class_cap = cap;
+  bp.cand = w.cand;
+  bp.counts = w.counts;
+  bp.bins = w.bins;
+  bp.class_counts = w.class_counts;
+  detect_bin_kernel<<<dim3(g.num_levels, batch), kBinThreads, 0, st>>>(bp);
   RADET_LAUNCH_CHECK();
-  return RADET_OK;
-}
-
-extern "C" size_t radet_vote_nms_workspace_bytes(int32_t batch, int64_t total_boxes, int64_t max_boxes_per_list) {
-  if (batch <= 0 || total_boxes < 0 || max_boxes_per_list < 0) return 0;
-  const int cap = (int)(max_boxes_per_list < 1 ? 1 : max_boxes_per_list);
-  return align_up((size_t)(batch + 1) * 4, 256) + (size_t)batch * nms_global_bytes(cap, cap <= kNmsCap);
-}
-
-extern "C" int radet_vote_nms(int32_t batch, const int32_t* offsets_host, const float* boxes, const float* cluster_scores,
-                              const float* vote_scores, const int64_t* labels, float iou_threshold, int32_t iou_enable,
-                              float sigma, int32_t mode, int32_t max_num, float* out_dets, int64_t* out_labels,
-                              int64_t* out_index, int32_t* num_out, int64_t* instance_ids, int64_t* clusters_num,
-                              void* workspace, size_t workspace_bytes, void* stream) {
-  if (batch == 0) return RADET_OK;
-  if (batch < 0 || !offsets_host || !num_out || !workspace || mode < 0 || mode > 2) return RADET_E_BADARG;
-  int64_t maxn = 0;
-  for (int b = 0; b < batch; ++b) {
-    const int64_t nb = (int64_t)offsets_host[b + 1] - offsets_host[b];
-    if (nb < 0) return RADET_E_BADARG;
-    maxn = nb > maxn ? nb : maxn;
-  }
-  const int64_t total = offsets_host[batch];
-  if (total > 0 && (!boxes || !cluster_scores || !vote_scores || !labels || !out_dets || !out_labels)) return RADET_E_BADARG;
-  if (maxn >= (1ll << 28)) return RADET_E_UNSUPPORTED;
-  if (workspace_bytes < radet_vote_nms_workspace_bytes(batch, total, maxn) || (reinterpret_cast<uintptr_t>(workspace) & 255))
-    return RADET_E_WORKSPACE;
-  cudaStream_t st = (cudaStream_t)stream;
-  unsigned char* ws = static_cast<unsigned char*>(workspace);
-  int* d_off = reinterpret_cast<int*>(ws);
-  ws += align_up((size_t)(batch + 1) * 4, 256);
-  cudaError_t ce = cudaMemcpyAsync(d_off, offsets_host, (size_t)(batch + 1) * 4, cudaMemcpyHostToDevice, st);
-  if (ce != cudaSuccess) return (int)ce;
-  NmsParams p{};
-  p.offsets = d_off;
-  p.in_boxes = boxes;
-  p.in_cs = cluster_scores;
-  p.in_vs = vote_scores;
-  p.in_labels = labels;
-  p.thr = iou_threshold;
-  p.sigma = sigma;
-  p.iou_enable = iou_enable;
-  p.mode = mode;
-  p.max_num = max_num;
-  p.cap = (int)(maxn < 1 ? 1 : maxn);
-  p.out_dets = out_dets;
-  p.out_labels = out_labels;
-  p.out_index = out_index;
-  p.num_out = num_out;
-  p.instance_ids = instance_ids;
-  p.clusters_num = clusters_num;
-  p.gws = ws;
-  const bool smem = p.cap <= kNmsCap;
-  p.gws_per_image = nms_global_bytes(p.cap, smem);
-  if (smem) {
-    cudaFuncSetAttribute(nms_image_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)nms_smem_bytes());
-    nms_image_kernel<false, true><<<batch, kNmsThreads, nms_smem_bytes(), st>>>(p);
-  } else {
-    nms_image_kernel<false, false><<<batch, kNmsThreads, 0, st>>>(p);
-  }
+  ClsParams cp{};
+  cp.grid = g;
+  cp.maps = md;
+  cp.C = num_classes;
+  cp.class_cap = cap;
+  cp.rescale = cfg->rescale;
+  cp.cs_mode = cfg->cluster_score_mode;
+  cp.vs_mode = cfg->vote_score_mode;
+  cp.mode = cfg->nms_mode;
+  cp.iou_enable = cfg->iou_enable;
+  cp.thr = cfg->iou_threshold;
+  cp.sigma = cfg->sigma;
+  cp.img_shapes = img_shapes;
+  cp.scale_factors = scale_factors;
+  cp.class_counts = w.class_counts;
+  cp.bins = w.bins;
+  cp.img_cap = img_cap;
+  cp.seed_out = w.seed_out;
+  cp.seed_keys = w.seed_keys;
+  cp.img_seed_count = w.img_seed_count;
+  cp.dbg = static_cast<long long*>(g_debug_buf);
+  cp.g_box = w.g_box;
+  cp.g_vs = w.g_vs;
+  cp.g_owner = w.g_owner;
+  const size_t cls_smem = (size_t)kMaskItems * (8 + 16 + 4 + 4 + kMaskWords * 4 + 2) + 2 * kMaskWords * 4;
+  cudaFuncSetAttribute(class_nms_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cls_smem);
+  cudaFuncSetAttribute(class_nms_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+  class_nms_kernel<<<dim3(num_classes, batch), kClsThreads, cls_smem, st>>>(cp);
+  RADET_LAUNCH_CHECK();
+  RankParams rp{};
+  rp.C = num_classes;
+  rp.img_cap = img_cap;
+  rp.max_num = cfg->max_per_img;
+  rp.seed_out = w.seed_out;
+  rp.seed_keys = w.seed_keys;
+  rp.img_seed_count = w.img_seed_count;
+  rp.class_counts = w.class_counts;
+  rp.dets = dets;
+  rp.labels = labels;
+  rp.num_dets = num_dets;
+  const size_t rank_smem = (size_t)kRankMaxOut * 12;
+  cudaFuncSetAttribute(detect_rank_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rank_smem);
+  detect_rank_kernel<<<batch, kRankThreads, rank_smem, st>>>(rp);
   RADET_LAUNCH_CHECK();
   return RADET_OK;
 }
