@@ -165,25 +165,64 @@ __device__ __forceinline__ float sigmoidf_(float x) { return 1.0f / (1.0f + expf
 
 // workspace layout (doubles): [0..7] final sums / normalisers, then block partials
 constexpr int kPosThreads = 256;
+constexpr int kPosPerThread = 4;
 constexpr int kNormSlots = 8;   // S0 num_pos, S1 sum wq, S2 sum wq(1-giou), S3 sum w*bce, S4 sum pred, S5 sum iou logit
 struct LossWs {
   double norm[kNormSlots];
   unsigned int counter_pos, counter_dense;
-  unsigned int pad[2];
+  unsigned int num_rec;   // positives recorded by loss_pos_kernel (consumed + re-armed by loss_dense_kernel)
+  unsigned int pad;
+};
+
+// One record per positive (idx >= 0) point: where its 5 gradient values go and their un-normalised values.
+struct __align__(16) PosRec {
+  int lb;        // level << 24 | image
+  int q;         // cell inside the (image, level) plane
+  float g[5];    // -wq * d giou/d(T,B,L,R),  w * (sigmoid(iou_logit) - iou_target)
+  float pad;
 };
 
 __global__ void __launch_bounds__(kPosThreads)
 loss_pos_kernel(GridDev grid, int B, MapsDev maps, const int* __restrict__ gt_offsets,
                 const float* __restrict__ gt_bboxes, const int64_t* __restrict__ pidx, const float* __restrict__ pw,
-                radet_loss_cfg_t cfg, LossWs* __restrict__ ws, double* __restrict__ partials) {
+                radet_loss_cfg_t cfg, LossWs* __restrict__ ws, double* __restrict__ partials, PosRec* __restrict__ recs,
+                int want_grad) {
+  // Phase 1: every thread scans kPosPerThread consecutive points and the CTA compacts the (sparse, spatially
+  // clustered) positives into shared memory.  Phase 2: one positive per thread -- IoU target, GIoU and BCE terms and
+  // their gradients, evaluated ONCE here and parked in `recs` (one global atomic per CTA); the dense kernel writes
+  // the zero-filled gradient planes and its last CTA scatters the normalised records on top.
+  __shared__ int s_scan[34];
+  __shared__ int s_list[kPosThreads * kPosPerThread];
+  __shared__ unsigned s_base;
   const int P = grid.off[grid.num_levels];
-  const int64_t t = (int64_t)blockIdx.x * kPosThreads + threadIdx.x;
+  const int64_t n = (int64_t)B * P;
+  const int64_t blk0 = (int64_t)blockIdx.x * kPosThreads * kPosPerThread;
+  const int64_t t0 = blk0 + (int64_t)threadIdx.x * kPosPerThread;
+  unsigned flags = 0u;
+#pragma unroll
+  for (int k = 0; k < kPosPerThread; ++k) {
+    if (t0 + k < n && pidx[t0 + k] >= 0) flags |= 1u << k;   // pos_inds incl. ignored points (radet_head.py:245-247)
+  }
+  int total;
+  int pos = block_exclusive_scan(__popc(flags), s_scan, &total);
+  while (flags) {
+    const int k = __ffs((int)flags) - 1;
+    flags &= flags - 1u;
+    s_list[pos++] = threadIdx.x * kPosPerThread + k;
+  }
+  if (threadIdx.x == 0 && want_grad && total) s_base = atomicAdd(&ws->num_rec, (unsigned)total);
+  __syncthreads();
   float acc[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-  if (t < (int64_t)B * P) {
-    const int b = (int)(t / P), p = (int)(t - (int64_t)b * P);
+  for (int i = threadIdx.x; i < total; i += kPosThreads) {
+    const int64_t t = blk0 + s_list[i];
     const int64_t idx = pidx[t];
+    const int b = (int)(t / P), p = (int)(t - (int64_t)b * P);
     const int g0 = gt_offsets[b], G = gt_offsets[b + 1] - g0;
-    if (idx >= 0 && G > 0) {  // pos_inds: 0 <= label < C, includes ignored points (radet_head.py:245-247)
+    PosRec r;
+    r.lb = -1;                 // G == 0: radet_head.py:385-386, everything background -> empty record
+    r.q = 0;
+    r.g[0] = r.g[1] = r.g[2] = r.g[3] = r.g[4] = r.pad = 0.f;
+    if (G > 0) {
       const float w = pw[t];
       const int l = level_of(grid, p);
       const int q = p - grid.off[l];
@@ -197,22 +236,31 @@ loss_pos_kernel(GridDev grid, int B, MapsDev maps, const int* __restrict__ gt_of
       const float xi = maps.iou[l][(int64_t)b * hw + q];
       float tT, tB, tL, tR;
       point_target(idx, G, gt_bboxes + 4 * (int64_t)g0, cx, cy, tT, tB, tL, tR);
-      const BoxTerms bt = box_terms<false>(cx, cy, s, T, Bt, L, R, tT, tB, tL, tR, 1e-6f, cfg.eps);
+      const BoxTerms bt = box_terms<true>(cx, cy, s, T, Bt, L, R, tT, tB, tL, tR, 1e-6f, cfg.eps);
       const float wq = fmaxf(bt.iou, 1e-12f) * w;           // radet_head.py:272
-      acc[0] = w;
-      acc[1] = wq;
-      acc[2] = wq * (1.f - bt.giou);
-      acc[3] = w * bce_logits(xi, bt.iou);
-      acc[4] = (T + Bt) + (L + R);
-      acc[5] = xi;
+      acc[0] += w;
+      acc[1] += wq;
+      acc[2] += wq * (1.f - bt.giou);
+      acc[3] += w * bce_logits(xi, bt.iou);
+      acc[4] += (T + Bt) + (L + R);
+      acc[5] += xi;
+      r.lb = (l << 24) | b;
+      r.q = q;
+      r.g[0] = -wq * bt.d[0];                               // d(1 - giou) = -d giou
+      r.g[1] = -wq * bt.d[1];
+      r.g[2] = -wq * bt.d[2];
+      r.g[3] = -wq * bt.d[3];
+      r.g[4] = w * (sigmoidf_(xi) - bt.iou);
     }
+    if (want_grad) recs[s_base + i] = r;
   }
   __shared__ double s_part[kPosThreads / 32][6];
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const bool warp_any = __any_sync(kFull, threadIdx.x < total);   // most warps hold no positive: skip their shuffles
 #pragma unroll
   for (int k = 0; k < 6; ++k) {
-    const double v = warp_sum((double)acc[k]);
-    if (lane == 0) s_part[wid][k] = v;
+    const float v = warp_any ? warp_sum(acc[k]) : 0.f;
+    if (lane == 0) s_part[wid][k] = (double)v;
   }
   __syncthreads();
   __shared__ bool s_last;
@@ -264,48 +312,63 @@ struct DenseTable {
 
 // Sigmoid focal loss and its derivative for one logit (mmcv sigmoid_focal_loss semantics; restated from
 // focal_loss.py:10-41 because the mmcv op is not in the reference tree).  Tolerance parity (not bit parity), so the
-// transcendental part is kept short: one ex2, one rcp and a degree-8 polynomial
-//     log1p(e) = e * P(e),  P = near-minimax fit of log1p(t)/t on [0,1]  (relative error 2.5e-7 in fp32)
-// -> ~35 instructions per element, which keeps the kernel HBM-bound instead of ALU-bound at large batch.
+// transcendental part is kept to ~28 instructions per element (at 70+ the kernel is issue-bound, not HBM-bound):
+// one ex2.approx, one rcp.approx and a degree-7 polynomial
+//     log1p(e) = e * P(e),  P = near-minimax degree-7 fit of log1p(t)/t on [0,1]  (relative error 3.7e-7 in fp32).
+// The target case is folded into the non-target one by symmetry: with z = -x,
+//     FL_target(x) = alpha * sigmoid(z)^gamma * softplus(z),  dFL_target/dx = -d/dz[...],
+// so a single expression  m = coef * s^gamma,  loss = m * softplus(z),  dloss/dz = m * (s + gamma * (1-s) * softplus(z))
+// with s = sigmoid(z) serves both (coef = alpha for the target class, 1-alpha otherwise).
+__device__ __forceinline__ float ex2_approx(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float rcp_approx(float x) {
+  float y;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
 template <bool kGamma2>
 __device__ __forceinline__ void focal_elem(float x, bool is_t, float gamma, float alpha, float& loss, float& grad) {
-  const float e = __expf(-fabsf(x));        // in (0, 1]
-  float P = 0.00512610236f;
-  P = fmaf(P, e, -0.0290740654f);
-  P = fmaf(P, e, 0.0775160864f);
-  P = fmaf(P, e, -0.136022478f);
-  P = fmaf(P, e, 0.190768808f);
-  P = fmaf(P, e, -0.248353988f);
-  P = fmaf(P, e, 0.333181202f);
-  P = fmaf(P, e, -0.499994457f);
-  P = fmaf(P, e, 0.99999994f);
-  const float l1p = e * P;                  // log1p(exp(-|x|))
-  const float sp_x = fmaxf(x, 0.f) + l1p;   // softplus(x)  = -log(1-p)
-  const float sp_nx = sp_x - x;             // softplus(-x) = -log(p)
-  const float inv = __frcp_rn(1.0f + e);
-  const float p = x >= 0.f ? inv : e * inv;
-  const float q = x >= 0.f ? e * inv : inv;
-  if (is_t) {
-    const float m = kGamma2 ? q * q : __expf(-gamma * sp_x);      // (1-p)^gamma
-    loss = alpha * m * sp_nx;
-    grad = -alpha * m * (q + gamma * p * sp_nx);
-  } else {
-    const float m = kGamma2 ? p * p : __expf(-gamma * sp_nx);     // p^gamma
-    loss = (1.f - alpha) * m * sp_x;
-    grad = (1.f - alpha) * m * (p + gamma * q * sp_x);
-  }
+  const float z = is_t ? -x : x;
+  const float e = ex2_approx(fabsf(z) * -1.4426950408889634f);   // exp(-|z|) in (0, 1]
+  float P = -0.00837115292f;                                      // degree-7 fit: relative error 3.7e-7
+  P = fmaf(P, e, 0.0434939004f);
+  P = fmaf(P, e, -0.106850028f);
+  P = fmaf(P, e, 0.176874772f);
+  P = fmaf(P, e, -0.244747743f);
+  P = fmaf(P, e, 0.332719296f);
+  P = fmaf(P, e, -0.499971747f);
+  P = fmaf(P, e, 0.999999762f);
+  const float sp = fmaf(e, P, fmaxf(z, 0.f));     // softplus(z)
+  const float inv = rcp_approx(1.0f + e);
+  const float s = z >= 0.f ? inv : e * inv;       // sigmoid(z)
+  const float coef = is_t ? alpha : 1.f - alpha;
+  const float m = coef * (kGamma2 ? s * s : ex2_approx(gamma * -1.4426950408889634f * (sp - z)));   // s^gamma = exp(-gamma*softplus(-z))
+  loss = m * sp;
+  const float g = m * fmaf(kGamma2 ? fmaf(-2.f, s, 2.f) : gamma * (1.f - s), sp, s);
+  grad = is_t ? -g : g;
 }
 
+constexpr int kDG = 2;   // class planes per load group; the next group is prefetched while the current one computes
+
 template <bool kGamma2>
-__global__ void __launch_bounds__(kDenseThreads)
-loss_dense_kernel(GridDev grid, DenseTable tab, int B, int C, int cc /* classes per thread */, int nj, MapsDev maps,
+__global__ void __launch_bounds__(kDenseThreads, 3)
+loss_dense_kernel(GridDev grid, DenseTable tab, int B, int C, int cc /* channels per work item */, int nj, MapsDev maps,
                   GradsDev grads, const int* __restrict__ gt_offsets, const float* __restrict__ gt_bboxes,
                   const int64_t* __restrict__ gt_labels, const int64_t* __restrict__ pidx, const float* __restrict__ pw,
                   radet_loss_cfg_t cfg, const float* __restrict__ grad_scale, LossWs* __restrict__ ws,
-                  double* __restrict__ partials, float* __restrict__ losses) {
+                  double* __restrict__ partials, float* __restrict__ losses, const PosRec* __restrict__ recs) {
+  // One thread = one unit (4 consecutive points of one (image, level) plane) x the channel chunk blockIdx.y.
+  // Channels 0..C-1 are the class logits (focal loss + gradient); channels C..C+3 are the T,B,L,R gradient planes and
+  // C+4 the IoU-logit gradient plane (zero except at the sparse positives), so every output plane is written by the
+  // same streaming loop.  The per-point setup (index -> label, weight) is done once per thread and amortised over
+  // the whole chunk (all C+5 channels when the units alone fill the machine); 3 CTAs x 256 threads per SM with 4
+  // independent 128-bit loads in flight per thread keep ~48 KB outstanding per SM, enough for HBM latency x bandwidth.
   const int P = grid.off[grid.num_levels];
   const int U = tab.uoff[grid.num_levels];
-  const int64_t t = (int64_t)blockIdx.x * kDenseThreads + threadIdx.x;
+  const int CH = C + 5;
   const double num_pos = ws->norm[0], sum_wq = ws->norm[1];
   const bool has_pos = ws->norm[6] > 0.0;                                        // radet_head.py:261
   const float gs_cls = grad_scale ? grad_scale[0] : 1.f, gs_box = grad_scale ? grad_scale[1] : 1.f,
@@ -314,9 +377,17 @@ loss_dense_kernel(GridDev grid, DenseTable tab, int B, int C, int cc /* classes 
   const float k_box = has_pos ? gs_box * cfg.w_bbox / (float)sum_wq : gs_box;
   const float k_iou = has_pos ? gs_iou * cfg.w_iou / (float)num_pos : gs_iou;
   const bool want_grad = grads.cls[0] != nullptr;
+  const float gamma = cfg.gamma, alpha = cfg.alpha;
   float lsum = 0.f;
-  if (t < (int64_t)U * nj) {
-    const int j = (int)(t / U), u = (int)(t - (int64_t)j * U);
+  // Balanced mapping: the U x nj work items are cut into gridDim.x equal contiguous slices (gridDim.x is a multiple of
+  // the SM count), so every SM hosts the same number of equally loaded CTAs.
+  const int64_t items = (int64_t)U * nj;
+  const int64_t ipc = (items + gridDim.x - 1) / gridDim.x;
+  const int64_t w_end = min(items, (int64_t)(blockIdx.x + 1) * ipc);
+  for (int64_t wi = (int64_t)blockIdx.x * ipc + threadIdx.x; wi < w_end; wi += kDenseThreads) {
+    const int j = (int)(wi / U), u = (int)(wi - (int64_t)j * U);
+    const int c0 = j * cc, c1 = min(CH, c0 + cc);
+    const int cls_end = min(c1, C);
     int l = 0;
 #pragma unroll
     for (int k = 1; k < RADET_MAX_LEVELS; ++k) l += (k < grid.num_levels && u >= tab.uoff[k]) ? 1 : 0;
@@ -326,117 +397,90 @@ loss_dense_kernel(GridDev grid, DenseTable tab, int B, int C, int cc /* classes 
     const int hw = grid.h[l] * grid.w[l];
     const int nv = min(4, hw - q0);
     const bool vec = (hw & 3) == 0;
+    const float* src = maps.cls[l] + ((int64_t)b * C + c0) * hw + q0;
+    float* dst = want_grad ? grads.cls[l] + ((int64_t)b * C + c0) * hw + q0 : nullptr;
+    const int ncls = cls_end - c0;                  // class planes of this thread (<= 0: regression chunk only)
+    const int ngroups = vec ? (ncls + kDG - 1) / kDG : 0;
+    float4 cur[kDG];
+    if (ngroups > 0) {
+#pragma unroll
+      for (int k = 0; k < kDG; ++k)                 // in flight before the index -> label dependency chain
+        cur[k] = k < ncls ? ldg_stream4(src + (int64_t)k * hw) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
     const int g0 = gt_offsets[b], G = gt_offsets[b + 1] - g0;
     const int64_t pbase = (int64_t)b * P + grid.off[l] + q0;
-    const int c0 = j * cc, c1 = min(C, c0 + cc);
-    const float* cp = maps.cls[l] + ((int64_t)b * C) * hw + q0;
-    float* gp = want_grad ? grads.cls[l] + ((int64_t)b * C) * hw + q0 : nullptr;
-    // logits of the first class group go in flight BEFORE the index -> label dependency chain is resolved;
-    // afterwards the next group is prefetched while the current one is being computed (register double buffer)
-    constexpr int DG = 4;
-    float nx[DG][4];
-    auto load_group = [&](int cb) {
-#pragma unroll
-      for (int k = 0; k < DG; ++k) {
-        nx[k][0] = nx[k][1] = nx[k][2] = nx[k][3] = 0.f;
-        if (cb + k < c1) {
-          if (vec) {
-            const float4 v4 = ldg_stream4(cp + (int64_t)(cb + k) * hw);
-            nx[k][0] = v4.x; nx[k][1] = v4.y; nx[k][2] = v4.z; nx[k][3] = v4.w;
-          } else {
-            for (int i = 0; i < nv; ++i) nx[k][i] = cp[(int64_t)(cb + k) * hw + i];
-          }
-        }
-      }
-    };
-    load_group(c0);
-    int64_t idx[4];
-    float w[4];
+    int idx[4];   // 1-based GT index fits 32 bits (G <= RADET_MAX_GT_PER_IMAGE)
+    float w[4], kw[4];
     int lab[4];
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
       idx[i] = -1;
       w[i] = 0.f;
       if (i < nv) {
-        idx[i] = pidx[pbase + i];
+        const int64_t v = pidx[pbase + i];
+        idx[i] = v < 0 ? -1 : (int)(v > (int64_t)G ? (int64_t)G : v);
         w[i] = pw[pbase + i];
       }
     }
 #pragma unroll
-    for (int i = 0; i < 4; ++i) lab[i] = (int)label_of(idx[i], G, gt_labels + g0, C);
-    for (int cb = c0; cb < c1; cb += DG) {
-      float xv[DG][4];
+    for (int i = 0; i < 4; ++i) {
+      lab[i] = (int)label_of(idx[i], G, gt_labels + g0, C) - c0;   // relative to the chunk
+      kw[i] = k_cls * w[i];
+    }
+    for (int g = 0; g < ngroups; ++g) {
+      float4 nxt[kDG];
+      const bool more = g + 1 < ngroups;
+      if (more) {                                   // software pipeline: next group's loads fly during this compute
 #pragma unroll
-      for (int k = 0; k < DG; ++k)
+        for (int k = 0; k < kDG; ++k) {
+          const int cr = (g + 1) * kDG + k;
+          nxt[k] = cr < ncls ? ldg_stream4(src + (int64_t)cr * hw) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+      }
 #pragma unroll
-        for (int i = 0; i < 4; ++i) xv[k][i] = nx[k][i];
-      if (cb + DG < c1) load_group(cb + DG);
+      for (int k = 0; k < kDG; ++k) {
+        const int cr = g * kDG + k;
+        if (cr < ncls) {
+          const float4 xv = cur[k];
+          float lo_, gr_;
+          float4 gv;
+          focal_elem<kGamma2>(xv.x, lab[0] == cr, gamma, alpha, lo_, gr_); lsum = fmaf(w[0], lo_, lsum); gv.x = kw[0] * gr_;
+          focal_elem<kGamma2>(xv.y, lab[1] == cr, gamma, alpha, lo_, gr_); lsum = fmaf(w[1], lo_, lsum); gv.y = kw[1] * gr_;
+          focal_elem<kGamma2>(xv.z, lab[2] == cr, gamma, alpha, lo_, gr_); lsum = fmaf(w[2], lo_, lsum); gv.z = kw[2] * gr_;
+          focal_elem<kGamma2>(xv.w, lab[3] == cr, gamma, alpha, lo_, gr_); lsum = fmaf(w[3], lo_, lsum); gv.w = kw[3] * gr_;
+          if (dst) stg_stream4(dst + (int64_t)cr * hw, gv);
+        }
+      }
+      if (more) {
 #pragma unroll
-      for (int k = 0; k < DG; ++k) {
-        const int c = cb + k;
-        if (c < c1) {
-          float gv[4];
+        for (int k = 0; k < kDG; ++k) cur[k] = nxt[k];
+      }
+    }
+    if (!vec) {                                     // planes whose size is not a multiple of 4: scalar path
+      for (int cr = 0; cr < ncls; ++cr) {
 #pragma unroll
-          for (int i = 0; i < 4; ++i) {
+        for (int i = 0; i < 4; ++i) {                // static indices keep lab/w/kw in registers
+          if (i < nv) {
             float lo_, gr_;
-            focal_elem<kGamma2>(xv[k][i], lab[i] == c, cfg.gamma, cfg.alpha, lo_, gr_);
-            lsum += w[i] * lo_;          // w = 0 for padding lanes
-            gv[i] = k_cls * w[i] * gr_;
-          }
-          if (want_grad) {
-            if (vec) {
-              stg_stream4(gp + (int64_t)c * hw, make_float4(gv[0], gv[1], gv[2], gv[3]));
-            } else {
-              for (int i = 0; i < nv; ++i) gp[(int64_t)c * hw + i] = gv[i];
-            }
+            focal_elem<kGamma2>(src[(int64_t)cr * hw + i], lab[i] == cr, gamma, alpha, lo_, gr_);
+            lsum = fmaf(w[i], lo_, lsum);
+            if (dst) dst[(int64_t)cr * hw + i] = kw[i] * gr_;
           }
         }
       }
     }
-    if (j == 0 && want_grad) {
-      // bbox / iou gradients of these 4 points (zero for negatives)
-      float gb[4][4], gi[4];
-      const float st = (float)grid.stride[l];
-      const float s = grid.nrm * (grid.anchor_scale * st);
-      const float* bp = maps.bbox[l] + (int64_t)b * 4 * hw + q0;
-      const float* ip = maps.iou[l] + (int64_t)b * hw + q0;
+    // gradient planes of the regression / IoU branches (channels C .. C+4): zero fill; the sparse positives are
+    // scattered on top by the last CTA (below)
+    if (want_grad && c1 > C) {
+      for (int ch = max(c0, C); ch < c1; ++ch) {
+        const int kk = ch - C;  // 0..3: T,B,L,R ; 4: iou logit
+        float* o = kk < 4 ? grads.bbox[l] + ((int64_t)b * 4 + kk) * hw + q0 : grads.iou[l] + (int64_t)b * hw + q0;
+        if (vec) {
+          stg_stream4(o, make_float4(0.f, 0.f, 0.f, 0.f));
+        } else {
 #pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        gb[0][i] = gb[1][i] = gb[2][i] = gb[3][i] = 0.f;
-        gi[i] = 0.f;
-        if (i < nv && idx[i] >= 0 && G > 0) {
-          if (has_pos) {
-            const int q = q0 + i;
-            const int y = q / grid.w[l], x = q - y * grid.w[l];
-            const float cx = (float)x * st, cy = (float)y * st;
-            const float T = bp[i], Bt = bp[hw + i], L = bp[2 * hw + i], R = bp[3 * hw + i];
-            const float xi = ip[i];
-            float tT, tB, tL, tR;
-            point_target(idx[i], G, gt_bboxes + 4 * (int64_t)g0, cx, cy, tT, tB, tL, tR);
-            const BoxTerms bt = box_terms<true>(cx, cy, s, T, Bt, L, R, tT, tB, tL, tR, 1e-6f, cfg.eps);
-            const float wq = fmaxf(bt.iou, 1e-12f) * w[i];
-            const float kb = -k_box * wq;  // d(1-giou) = -dgiou
-#pragma unroll
-            for (int k = 0; k < 4; ++k) gb[k][i] = kb * bt.d[k];
-            gi[i] = k_iou * w[i] * (sigmoidf_(xi) - bt.iou);
-          } else {  // radet_head.py:280-281: loss = sum of the positive predictions
-#pragma unroll
-            for (int k = 0; k < 4; ++k) gb[k][i] = gs_box;
-            gi[i] = gs_iou;
-          }
-        }
-      }
-      float* gbp = grads.bbox[l] + (int64_t)b * 4 * hw + q0;
-      float* gip = grads.iou[l] + (int64_t)b * hw + q0;
-      if (vec) {
-#pragma unroll
-        for (int k = 0; k < 4; ++k) stg_stream4(gbp + (int64_t)k * hw, make_float4(gb[k][0], gb[k][1], gb[k][2], gb[k][3]));
-        stg_stream4(gip, make_float4(gi[0], gi[1], gi[2], gi[3]));
-      } else {
-        for (int i = 0; i < nv; ++i) {
-#pragma unroll
-          for (int k = 0; k < 4; ++k) gbp[(int64_t)k * hw + i] = gb[k][i];
-          gip[i] = gi[i];
+          for (int i = 0; i < 4; ++i)
+            if (i < nv) o[i] = 0.f;
         }
       }
     }
@@ -445,21 +489,23 @@ loss_dense_kernel(GridDev grid, DenseTable tab, int B, int C, int cc /* classes 
   __shared__ double s_part[kDenseThreads / 32];
   __shared__ bool s_last;
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const unsigned nblocks = gridDim.x, bid = blockIdx.x;
   const double v = warp_sum((double)lsum);
   if (lane == 0) s_part[wid] = v;
+  __threadfence();   // this thread's gradient stores are visible device-wide before the CTA signals completion
   __syncthreads();
   if (threadIdx.x == 0) {
     double s = 0.0;
     for (int w_ = 0; w_ < kDenseThreads / 32; ++w_) s += s_part[w_];
-    partials[blockIdx.x] = s;
+    partials[bid] = s;
     __threadfence();
-    s_last = (atomicAdd(&ws->counter_dense, 1u) == gridDim.x - 1);
+    s_last = (atomicAdd(&ws->counter_dense, 1u) == nblocks - 1);
   }
   __syncthreads();
   if (!s_last) return;
   __threadfence();
   double tot = 0.0;
-  for (int i = threadIdx.x; i < (int)gridDim.x; i += kDenseThreads) tot += partials[i];
+  for (int i = threadIdx.x; i < (int)nblocks; i += kDenseThreads) tot += partials[i];
   tot = warp_sum(tot);
   if (lane == 0) s_part[wid] = tot;
   __syncthreads();
@@ -472,6 +518,22 @@ loss_dense_kernel(GridDev grid, DenseTable tab, int B, int C, int cc /* classes 
     losses[3] = (float)num_pos;
     ws->counter_dense = 0u;
   }
+  // every other CTA has finished (and fenced) its zero fill: scatter the normalised gradients of the positives
+  if (want_grad) {
+    const unsigned nrec = ws->num_rec;
+    for (unsigned i = threadIdx.x; i < nrec; i += kDenseThreads) {
+      const PosRec r = recs[i];
+      if (r.lb < 0) continue;   // image without GT
+      const int l = r.lb >> 24, b = r.lb & 0xffffff;
+      const int hw = grid.h[l] * grid.w[l];
+      float* gb = grads.bbox[l] + (int64_t)b * 4 * hw + r.q;
+#pragma unroll
+      for (int k = 0; k < 4; ++k) gb[(int64_t)k * hw] = has_pos ? k_box * r.g[k] : gs_box;   // radet_head.py:280-281
+      grads.iou[l][(int64_t)b * hw + r.q] = has_pos ? k_iou * r.g[4] : gs_iou;
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) ws->num_rec = 0u;   // re-arm
 }
 
 struct ScaleTable {
@@ -549,7 +611,10 @@ extern "C" int radet_get_targets(const radet_grid_t* grid, int32_t batch, int32_
   return RADET_OK;
 }
 
-static int dense_plan(const GridDev& g, int B, int C, DenseTable* tab, int* cc, int* nj) {
+constexpr int kSMs = 148;
+constexpr int kDenseOcc = 3;   // resident CTAs per SM (launch bounds: 256 threads x <= 85 registers, no spills)
+
+static int dense_plan(const GridDev& g, int B, int C, DenseTable* tab, int* cc, int* nj, int* blocks) {
   int64_t u = 0;
   for (int l = 0; l < g.num_levels; ++l) {
     const int hw = g.h[l] * g.w[l];
@@ -560,14 +625,33 @@ static int dense_plan(const GridDev& g, int B, int C, DenseTable* tab, int* cc, 
   }
   for (int l = g.num_levels; l <= RADET_MAX_LEVELS; ++l) tab->uoff[l] = (int)u;
   for (int l = g.num_levels; l < RADET_MAX_LEVELS; ++l) tab->upl[l] = 1;
-  // classes per thread: every thread re-derives the labels of its 4 points, so a thread should own several classes
-  // (>= 4, one register-buffered load group); beyond that, keep >= ~2 CTAs of 256 threads per SM in flight
-  const int64_t target_threads = 148ll * 256 * 2;
-  int c = (int)((u * (int64_t)C + target_threads - 1) / target_threads);
-  if (c < 4) c = 4;
-  if (c > C) c = C;
-  *cc = c;
-  *nj = (C + c - 1) / c;
+  // Work items = units x channel chunks.  The grid is always a multiple of the SM count and the items are cut into
+  // equal slices, so there is no partially filled last wave.  One chunk per unit (all C+5 channels in one thread)
+  // amortises the per-point setup best; more chunks are used only to give every resident thread an item when the
+  // units alone cannot (small batches).  Cost model: rounds x (setup + channels).
+  const int CH = C + 5;
+  const double resident = (double)kSMs * kDenseOcc * kDenseThreads;
+  const int nmax = (CH + kDG - 1) / kDG;
+  double best = 1e30;
+  int best_c = CH;
+  for (int n = 1; n <= nmax; ++n) {
+    int c = (CH + n - 1) / n;
+    c = (c + kDG - 1) / kDG * kDG;                        // whole load groups
+    const int nn = (CH + c - 1) / c;
+    const double rounds = ceil((double)u * nn / resident);
+    const double t = rounds * (3.0 + c);
+    if (t < best - 1e-9) {
+      best = t;
+      best_c = c;
+    }
+  }
+  *cc = best_c;
+  *nj = (CH + best_c - 1) / best_c;
+  const int64_t items = u * *nj;
+  int64_t m = (items + (int64_t)kSMs * kDenseThreads - 1) / ((int64_t)kSMs * kDenseThreads);   // CTAs per SM needed
+  if (m < 1) m = 1;
+  if (m > kDenseOcc) m = kDenseOcc;
+  *blocks = (int)(kSMs * m);
   return RADET_OK;
 }
 
@@ -575,12 +659,13 @@ extern "C" size_t radet_loss_workspace_bytes(const radet_grid_t* grid, int32_t b
   GridDev g;
   if (make_grid_dev(grid, &g) != RADET_OK || batch <= 0 || num_classes <= 0) return 0;
   DenseTable tab;
-  int cc, nj;
-  if (dense_plan(g, batch, num_classes, &tab, &cc, &nj) != RADET_OK) return 0;
+  int cc, nj, dblk;
+  if (dense_plan(g, batch, num_classes, &tab, &cc, &nj, &dblk) != RADET_OK) return 0;
   const int64_t n = (int64_t)batch * g.off[g.num_levels];
-  const int64_t pos_blocks = (n + kPosThreads - 1) / kPosThreads;
-  const int64_t dense_blocks = ((int64_t)tab.uoff[g.num_levels] * num_classes + kDenseThreads - 1) / kDenseThreads;  // upper bound (cc=1)
-  return align_up(sizeof(LossWs), 256) + align_up((size_t)pos_blocks * 6 * 8, 256) + align_up((size_t)dense_blocks * 8, 256);
+  const int64_t pos_blocks = (n + kPosThreads * kPosPerThread - 1) / (kPosThreads * kPosPerThread);
+  const int64_t dense_blocks = dblk;
+  return align_up(sizeof(LossWs), 256) + align_up((size_t)pos_blocks * 6 * 8, 256) + align_up((size_t)dense_blocks * 8, 256) +
+         align_up((size_t)n * sizeof(PosRec), 256);
 }
 
 extern "C" int radet_loss_fwd_bwd(const radet_grid_t* grid, int32_t batch, int32_t num_classes, const radet_maps_t* maps,
@@ -615,32 +700,33 @@ extern "C" int radet_loss_fwd_bwd(const radet_grid_t* grid, int32_t batch, int32
     }
   }
   DenseTable tab;
-  int cc, nj;
-  rc = dense_plan(g, batch, num_classes, &tab, &cc, &nj);
+  int cc, nj, dblk;
+  rc = dense_plan(g, batch, num_classes, &tab, &cc, &nj, &dblk);
   if (rc != RADET_OK) return rc;
   unsigned char* wsb = static_cast<unsigned char*>(workspace);
   LossWs* ws = reinterpret_cast<LossWs*>(wsb);
   const int64_t n = (int64_t)batch * g.off[g.num_levels];
-  const int64_t pos_blocks = (n + kPosThreads - 1) / kPosThreads;
+  const int64_t pos_blocks = (n + kPosThreads * kPosPerThread - 1) / (kPosThreads * kPosPerThread);
   double* pos_part = reinterpret_cast<double*>(wsb + align_up(sizeof(LossWs), 256));
   double* dense_part = reinterpret_cast<double*>(wsb + align_up(sizeof(LossWs), 256) + align_up((size_t)pos_blocks * 6 * 8, 256));
+  PosRec* recs = reinterpret_cast<PosRec*>(wsb + align_up(sizeof(LossWs), 256) + align_up((size_t)pos_blocks * 6 * 8, 256) +
+                                           align_up((size_t)dblk * 8, 256));
   cudaStream_t st = (cudaStream_t)stream;
   if (phases & RADET_LOSS_PHASE_NORMALIZERS) {
     loss_pos_kernel<<<(unsigned)pos_blocks, kPosThreads, 0, st>>>(g, batch, md, gt_offsets, gt_bboxes, points_to_gt_index,
-                                                                  points_weight, *cfg, ws, pos_part);
+                                                                  points_weight, *cfg, ws, pos_part, recs, grads ? 1 : 0);
     RADET_LAUNCH_CHECK();
   }
   if (!(phases & RADET_LOSS_PHASE_DENSE)) return RADET_OK;
-  const int64_t dthreads = (int64_t)tab.uoff[g.num_levels] * nj;
-  const unsigned dblocks = (unsigned)((dthreads + kDenseThreads - 1) / kDenseThreads);
+  const unsigned dblocks = (unsigned)dblk;
   if (cfg->gamma == 2.0f)
     loss_dense_kernel<true><<<dblocks, kDenseThreads, 0, st>>>(g, tab, batch, num_classes, cc, nj, md, gd, gt_offsets, gt_bboxes,
                                                                gt_labels, points_to_gt_index, points_weight, *cfg, grad_scale,
-                                                               ws, dense_part, losses);
+                                                               ws, dense_part, losses, recs);
   else
     loss_dense_kernel<false><<<dblocks, kDenseThreads, 0, st>>>(g, tab, batch, num_classes, cc, nj, md, gd, gt_offsets, gt_bboxes,
                                                                 gt_labels, points_to_gt_index, points_weight, *cfg, grad_scale,
-                                                                ws, dense_part, losses);
+                                                                ws, dense_part, losses, recs);
   RADET_LAUNCH_CHECK();
   return RADET_OK;
 }
