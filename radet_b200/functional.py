@@ -226,12 +226,10 @@ def loss_fwd_bwd(geom: Geometry, num_classes: int, cls, bbox, iou, gt_counts, gt
     if sync_group is None:
         run(3)
     else:
-        import torch.distributed as dist
+        from .sharding import reduce_mean_
 
         run(1)
-        norm = ws[:16].view(torch.float64)          # num_pos, sum(wq): the two normalisers
-        norm /= dist.get_world_size(sync_group)     # reduce_mean (core/utils/dist_utils.py:63-69)
-        dist.all_reduce(norm, group=sync_group)
+        reduce_mean_(ws[:16].view(torch.float64), sync_group)   # num_pos, sum(wq): the two normalisers, over NCCL
         run(2)
     return losses, grads
 
