@@ -110,3 +110,30 @@ def test_image_sharding():
         sharding.image_range(4, 4, 8)
     t = torch.tensor([3.0, 5.0])
     assert sharding.reduce_mean_(t) is t and t.tolist() == [3.0, 5.0]      # no process group: identity
+
+
+@pytest.mark.skipif(not __import__("os").path.isdir("/root/reference/radet"), reason="reference tree only exists in the build container")
+def test_install_into_reference_registries():
+    """the B200 classes replace the reference's registry entries and radet.ops functions."""
+    from oracle import ref_shim
+
+    ref_shim.install()
+    import radet.ops as rops
+    from radet.datasets.builder import PIPELINES as R_PIPELINES
+    from radet.models.builder import HEADS as R_HEADS
+
+    ref_head = R_HEADS.get("RADetHead")
+    assert ref_head is not None and ref_head is not P.RADetHead
+    P.install_into_reference()
+    try:
+        assert R_HEADS.get("RADetHead") is P.RADetHead
+        assert R_PIPELINES.get("LabelAssignment") is P.LabelAssignment
+        assert rops.vote_nms is P.ops.vote_nms and rops.cluster_nms is P.ops.cluster_nms
+    finally:   # leave the reference as it was for the other tests of this process
+        from radet.datasets.pipelines.label_assignment import LabelAssignment as RefLA
+        from radet.ops.cluster import cluster_nms as c0
+        from radet.ops.vote import global_vote_nms as g0, vote_nms as v0
+
+        R_HEADS.register_module(name="RADetHead", force=True, module=ref_head)
+        R_PIPELINES.register_module(name="LabelAssignment", force=True, module=RefLA)
+        rops.vote_nms, rops.global_vote_nms, rops.cluster_nms = v0, g0, c0
