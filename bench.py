@@ -46,6 +46,8 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--profile", action="store_true", help="few eager steps, nothing else (for ncu)")
+    ap.add_argument("--serial", action="store_true", help="one stream: train and inference branches back to back")
+    ap.add_argument("--no-prefetch", action="store_true", help="assignment and loss of the same batch in sequence (no one-batch-ahead assignment)")
     ap.add_argument("--sets", type=int, default=0, help="rotating input sets (default: enough to exceed 2x L2)")
     ap.add_argument("--cpu-baseline-json", action="store_true", help=argparse.SUPPRESS)
     return ap.parse_args()
@@ -263,13 +265,64 @@ def main():
             host_sets.append((batch, ho))
     up_ones = torch.ones(3, dtype=torch.float32, device=dev)
 
-    def step(s, keep=None):
+    side = torch.cuda.Stream(device=dev)
+    side2 = torch.cuda.Stream(device=dev)
+    side3 = torch.cuda.Stream(device=dev)
+    for s in sets:   # assignment buffers of every input set (double-buffered hand-off, see step())
+        s["abuf"] = (torch.empty((B, Ppts), dtype=torch.int64, device=dev), torch.empty((B, Ppts), dtype=torch.float32, device=dev),
+                     torch.empty((B,), dtype=torch.int32, device=dev))
+
+    def do_assign(s, out=None, states=None):
         bits = F.pack_masks(s["grids"], 1, gh, gw)
-        idx, w, used = F.assign(geom, shapes, s["counts"], s["boxes"], bits, (gh, gw), seeds=s["seeds"], gt_offsets=s["off"])
+        if states is not None:
+            return F.assign(geom, shapes, s["counts"], s["boxes"], bits, (gh, gw), mt_states=states, gt_offsets=s["off"], out=out)
+        return F.assign(geom, shapes, s["counts"], s["boxes"], bits, (gh, gw), seeds=s["seeds"], gt_offsets=s["off"], out=out)
+
+    def do_loss(s, idx, w):
         losses, grads = F.loss_fwd_bwd(geom, wl.C, s["cls"], s["bbox"], s["iou"], s["counts"], s["boxes"], s["labels"], idx, w, lcfg,
                                        gt_offsets=s["off"])
         F.scale_grads(geom, wl.C, grads, up_ones)            # what autograd's backward of the three losses launches
-        dets, dl, num = F.get_bboxes(geom, wl.C, s["cls"], s["bbox"], s["iou"], s["shp"], s["sf"], dcfg, rescale=True)
+        return losses, grads
+
+    def do_detect(s):
+        return F.get_bboxes(geom, wl.C, s["cls"], s["bbox"], s["iou"], s["shp"], s["sf"], dcfg, rescale=True)
+
+    def step(s, keep=None, nxt=None):
+        """One step = assign + loss fwd/bwd + decode/vote-NMS, each over one batch of B images.
+
+        --serial: everything back to back on one stream.
+        --no-prefetch: the train branch (assign -> loss) and the inference branch (decode+NMS) of the SAME batch forked
+            onto two streams (two branches of one CUDA graph): the latency-bound kernels of one branch fill the SMs the
+            other leaves idle; np.random.seed()'s sequential state bring-up runs on a third stream.
+        default: additionally the assignment runs one batch AHEAD (assign(batch i+1) || loss(batch i) || detect(batch i)),
+            the way the reference runs LabelAssignment in DataLoader workers ahead of the trainer
+            (configs/base/datasets/bop_detection.py:19-32); the assignment is handed over through per-set buffers
+            written by the previous step.  Every step still executes all three stages for one full batch."""
+        main = torch.cuda.current_stream()
+        if args.serial:
+            idx, w, used = do_assign(s)
+            losses, grads = do_loss(s, idx, w)
+            dets, dl, num = do_detect(s)
+        else:
+            side.wait_stream(main)
+            side2.wait_stream(main)
+            with torch.cuda.stream(side2):      # np.random.seed() per image: sequential, depends on nothing
+                states = F.seed_states((nxt or s)["seeds"])
+            with torch.cuda.stream(side):
+                dets, dl, num = do_detect(s)
+            if nxt is None:                     # same-batch dependency: assign -> loss on the main stream
+                main.wait_stream(side2)
+                idx, w, used = do_assign(s, states=states)
+                losses, grads = do_loss(s, idx, w)
+            else:                               # assignment of the NEXT batch on its own branch
+                side3.wait_stream(main)
+                with torch.cuda.stream(side3):
+                    side3.wait_stream(side2)
+                    do_assign(nxt, out=nxt["abuf"], states=states)
+                idx, w, used = s["abuf"]
+                losses, grads = do_loss(s, idx, w)
+                main.wait_stream(side3)
+            main.wait_stream(side)
         if keep is not None:
             keep.append((idx, w, losses, grads, dets, dl, num))
         return losses, num
@@ -277,16 +330,19 @@ def main():
     torch.cuda.synchronize()
     if args.profile:
         for i in range(args.warmup + args.steps):
-            step(sets[i % R])
+            step(sets[i % R], nxt=None)
         torch.cuda.synchronize()
         return
 
-    # ---- launches per step, eager warm-up
+    # ---- launches per step, eager warm-up (also fills the hand-over buffers of every set)
+    prefetch = not (args.serial or args.no_prefetch)
+    for s in sets:
+        do_assign(s, out=s["abuf"])
     l0 = _lib.launch_count()
-    step(sets[0])
+    step(sets[0], nxt=sets[1 % R] if prefetch else None)
     launches_per_step = _lib.launch_count() - l0
     for i in range(max(3, min(args.warmup, 20))):
-        step(sets[i % R])
+        step(sets[i % R], nxt=sets[(i + 1) % R] if prefetch else None)
     torch.cuda.synchronize()
 
     # ---- CUDA graphs: one per input set (the C ABI only enqueues, so the whole step is capturable)
@@ -294,16 +350,16 @@ def main():
     graphs, outs = [], []
     if use_graph:
         pool = torch.cuda.graph_pool_handle()
-        for s in sets:
+        for r_, s in enumerate(sets):
             g = torch.cuda.CUDAGraph()
             keep = []
             with torch.cuda.graph(g, pool=pool):
-                step(s, keep)
+                step(s, keep, nxt=sets[(r_ + 1) % R] if prefetch else None)
             graphs.append(g)
             outs.append(keep)
         run = lambda i: graphs[i % R].replay()
     else:
-        run = lambda i: step(sets[i % R])
+        run = lambda i: step(sets[i % R], nxt=sets[(i + 1) % R] if prefetch else None)
 
     def barrier():
         if world > 1:
@@ -435,7 +491,11 @@ def main():
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": wl.name, "images_per_gpu": B, "points_per_image": Ppts, "classes": wl.C,
-                       "launch": "cuda_graph" if use_graph else "eager",
+                       "launch": ("cuda_graph" if use_graph else "eager") + (
+                           ", 1 stream" if args.serial else
+                           ", assign->loss and decode+NMS branches of one batch forked on streams" if args.no_prefetch else
+                           ", 3 branches per step: assign(batch i+1) || loss fwd+bwd(batch i) || decode+NMS(batch i) "
+                           "(assignment runs one batch ahead like the reference's DataLoader workers)"),
                        "l2": f"{R} rotating input sets, {R * per_set / 1e6:.0f} MB total > L2 ({L2_BYTES / 1e6:.0f} MB)",
                        "parallelism": f"images sharded over {world} rank(s), no data-path collective"},
             "point_gt_pairs_per_s": world * pairs / (stage_us["assign(pairs+resolve)"] * 1e-6),

@@ -93,6 +93,10 @@ int radet_pack_masks(const uint8_t* src, int64_t num_gt, int32_t src_h, int32_t 
  * Numpy-legacy MT19937 on the device: out[b][0..n) = what `np.random.seed(seeds[b]);
  * np.random.random_sample(n)` returns (53-bit doubles).  Used by tests and by the seeded mode below. */
 int radet_mt19937_uniforms(const uint32_t* seeds, int32_t batch, int32_t n, double* out, void* stream);
+/* mt_states[b] (625 words: key[624], pos) = the legacy state right after `np.random.seed(seeds[b])` (first block
+ * already regenerated, pos = 0).  The 624-step seeding recurrence is sequential but depends on nothing: enqueue it
+ * early / on a side stream and hand the states to radet_assign(mt_states=...). */
+int radet_mt19937_seed(const uint32_t* seeds, int32_t batch, uint32_t* mt_states, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Visibility-guided sample assignment for a batch of images.

@@ -48,6 +48,7 @@ _SIGS = {
     "radet_num_points": (c_int64, [POINTER(Grid)]),
     "radet_pack_masks": (c_int32, [c_void_p, c_int64, c_int32, c_int32, c_int32, c_int32, c_int32, c_void_p, c_void_p, c_void_p]),
     "radet_mt19937_uniforms": (c_int32, [c_void_p, c_int32, c_int32, c_void_p, c_void_p]),
+    "radet_mt19937_seed": (c_int32, [c_void_p, c_int32, c_void_p, c_void_p]),
     "radet_assign_workspace_bytes": (c_size_t, [POINTER(Grid), c_int32]),
     "radet_assign": (c_int32, [POINTER(Grid), c_int32, c_void_p, POINTER(c_int32), c_void_p, c_void_p, c_int32, c_int32, c_int32,
                                c_void_p, c_int32, c_void_p, c_void_p, c_int32, c_int32, c_void_p, c_void_p, c_void_p,

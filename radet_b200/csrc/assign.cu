@@ -122,6 +122,47 @@ struct MtWarp {
   }
 };
 
+// Pre-tempered view of the stream for the sampling loop: the 53-bit integers of all doubles left in the current
+// 624-word block are produced in one parallel sweep (all 32 lanes), so a choice() round fetches its uniforms with a
+// single shared-memory load instead of load + temper + combine on its critical path.  Requires an even word
+// position (always true for np.random.seed / random_sample streams); odd positions use MtWarp::draw53 directly.
+struct MtStream {
+  MtWarp mt;
+  unsigned long long* xbuf;   // [312]
+  int nx, xi;                 // doubles buffered / consumed
+  bool fast;
+
+  __device__ void fill(int lane) {
+    fast = (mt.pos & 1) == 0;
+    nx = fast ? (624 - mt.pos) >> 1 : 0;
+    xi = 0;
+    for (int i = lane; i < nx; i += 32) {
+      const uint32_t a = MtWarp::temper(mt.key[mt.pos + 2 * i]) >> 5, b = MtWarp::temper(mt.key[mt.pos + 2 * i + 1]) >> 6;
+      xbuf[i] = ((unsigned long long)a << 26) | (unsigned long long)b;
+    }
+    __syncwarp();
+  }
+  // word position of the underlying generator (for handing the state back)
+  __device__ int word_pos() const { return fast ? mt.pos + 2 * xi : mt.pos; }
+  __device__ unsigned long long draw53(int count, int lane) {
+    if (!fast) return mt.draw53(count, lane);
+    const int rem = nx - xi;
+    unsigned long long X = 0ull;
+    if (lane < count && lane < rem) X = xbuf[xi + lane];
+    if (count > rem) {           // block exhausted: regenerate, take the rest from the new block
+      __syncwarp();
+      mt.twist(lane);
+      mt.pos = 0;
+      fill(lane);
+      if (lane >= rem && lane < count) X = xbuf[lane - rem];
+      xi = count - rem;
+    } else {
+      xi += count;
+    }
+    return X;
+  }
+};
+
 __global__ void mt19937_uniforms_kernel(const uint32_t* __restrict__ seeds, int n, double* __restrict__ out) {
   __shared__ uint32_t key[624];
   const int lane = threadIdx.x;
@@ -133,6 +174,19 @@ __global__ void mt19937_uniforms_kernel(const uint32_t* __restrict__ seeds, int 
     const double u = mt.draw(cnt, lane);
     if (lane < cnt) o[base + lane] = u;
   }
+}
+
+// np.random.seed(seeds[b]) + first regeneration -> legacy state words [B][625] (pos = 0).  One warp per image; meant
+// to be enqueued early / on a side stream: the 624-step recurrence is sequential (~5 us) but depends on nothing.
+__global__ void mt19937_seed_kernel(const uint32_t* __restrict__ seeds, uint32_t* __restrict__ states) {
+  __shared__ uint32_t key[624];
+  const int lane = threadIdx.x;
+  MtWarp mt{key, 624};
+  mt.seed(seeds[blockIdx.x], lane);
+  mt.twist(lane);
+  uint32_t* st = states + (int64_t)blockIdx.x * RADET_MT_STATE_WORDS;
+  for (int i = lane; i < 624; i += 32) st[i] = key[i];
+  if (lane == 0) st[624] = 0u;
 }
 
 // ------------------------------------------------------------------------------------------------ pair tests
@@ -300,7 +354,6 @@ struct ResolveSmem {
   int M;
   int changed;
   int found[RADET_MAX_POSITIVE_NUM];
-  volatile int done;   // GTs (area ranks) whose selection is final: warps 1..31 write those outputs meanwhile
 };
 
 // warps 1..31 of the resolve CTA synchronise among themselves on named barrier 1 (warp 0 runs the RNG bring-up)
@@ -338,7 +391,7 @@ __device__ __forceinline__ int worker_exclusive_scan(int v, int* scratch, int* t
 __host__ __device__ inline size_t resolve_smem_bytes(int maxG, int K, bool list_in_smem) {
   size_t s = sizeof(ResolveSmem);
   s = (s + 15) & ~size_t(15);
-  s += 624 * 4;                             // MT key
+  s += 624 * 4 + 312 * 8;                   // MT key + pre-tempered 53-bit stream
   s += (size_t)maxG * 4 * 3;                // area, rank2gt, n_r
   s += (size_t)maxG * K * 4;                // sel_pos
   s += (size_t)maxG * K;                    // sel_cnt
@@ -366,6 +419,7 @@ assign_resolve_kernel(GridDev grid, const int* __restrict__ gt_offsets, const fl
 
   ResolveSmem* S = reinterpret_cast<ResolveSmem*>(smem_raw);
   unsigned char* cur = smem_raw + ((sizeof(ResolveSmem) + 15) & ~size_t(15));
+  unsigned long long* s_xbuf = reinterpret_cast<unsigned long long*>(cur); cur += 312 * 8;
   uint32_t* s_key = reinterpret_cast<uint32_t*>(cur); cur += 624 * 4;
   float* s_area = reinterpret_cast<float*>(cur); cur += (size_t)maxG * 4;
   int* s_rank2gt = reinterpret_cast<int*>(cur); cur += (size_t)maxG * 4;
@@ -402,7 +456,8 @@ assign_resolve_kernel(GridDev grid, const int* __restrict__ gt_offsets, const fl
 
   const uint32_t* bits = pair_bits + (int64_t)b * P * (2 * W32);
   const double* ub = uniforms ? uniforms + (int64_t)b * n_uniform : nullptr;
-  MtWarp mt{s_key, 624};
+  MtStream ms{MtWarp{s_key, 624}, s_xbuf, 0, 0, false};
+  MtWarp& mt = ms.mt;
   int M = 0;
   if (wid == 0) RESOLVE_DBG(0);
   if (wid == 0) {
@@ -426,6 +481,7 @@ assign_resolve_kernel(GridDev grid, const int* __restrict__ gt_offsets, const fl
         mt.twist(lane);
         mt.pos = 0;
       }
+      ms.fill(lane);
     }
     RESOLVE_DBG(1);
   } else {
@@ -527,10 +583,7 @@ assign_resolve_kernel(GridDev grid, const int* __restrict__ gt_offsets, const fl
         wt[p] = 1.0f;
       }
     }
-    if (wt_ == 0) {
-      S->M = M;
-      S->done = 0;
-    }
+    if (wt_ == 0) S->M = M;
     if (wid == 1) RESOLVE_DBG(2);
   }
   __syncthreads();
@@ -556,17 +609,13 @@ assign_resolve_kernel(GridDev grid, const int* __restrict__ gt_offsets, const fl
           if ((double)X != sc || !(ux >= 0.0 && ux < 1.0)) X = 1ull << 63;
         }
       } else {
-        X = mt.draw53(count, lane);
+        X = ms.draw53(count, lane);
       }
       used += count;
       return X;
     };
     auto search = [&](unsigned long long X, int m) -> int { return (X >> 63) ? cdf_search(ux, m) : cdf_search53(X, m); };
     for (int r = 0; r < G && !overflow; ++r) {
-      if (lane == 0 && r > 0) {
-        __threadfence_block();
-        S->done = r;                                                // selections of ranks < r are final
-      }
       const int n = s_nr[r];
       if (n == 0) continue;                                         // label_assignment.py:182-183: no RNG use
       int* selpos = s_selpos + r * K;
@@ -632,12 +681,7 @@ assign_resolve_kernel(GridDev grid, const int* __restrict__ gt_offsets, const fl
       }
       __syncwarp();
     }
-    __syncwarp();
-    if (lane == 0) {
-      __threadfence_block();
-      S->done = G;
-      consumed[b] = overflow ? -1 : used;
-    }
+    if (lane == 0) consumed[b] = overflow ? -1 : used;
     RESOLVE_DBG(4);
     if (dbg && lane == 0) {
       dbg[(int64_t)blockIdx.x * 16 + 8] = G;
@@ -647,15 +691,12 @@ assign_resolve_kernel(GridDev grid, const int* __restrict__ gt_offsets, const fl
     if (!ub && mt_states && state_writeback && used > 0) {  // hand the advanced generator back (untouched if nothing was drawn)
       uint32_t* st = mt_states + (int64_t)b * RADET_MT_STATE_WORDS;
       for (int i = lane; i < 624; i += 32) st[i] = s_key[i];
-      if (lane == 0) st[624] = (uint32_t)mt.pos;
+      if (lane == 0) st[624] = (uint32_t)ms.word_pos();
     }
   }
-  // 5. (warps 1..31, overlapped with the sampling of later GTs) one warp per GT: walk its members in ascending point
-  //    order, selected -> positive, others -> ignore
-  if (wid > 0)
-  for (int r = wid - 1; r < G; r += kResolveThreads / 32 - 1) {
-    while (S->done <= r) __nanosleep(20);
-    __threadfence_block();
+  __syncthreads();
+  // 5. one warp per GT: walk its members in ascending point order, selected -> positive, others -> ignore
+  for (int r = wid; r < G; r += kResolveThreads / 32) {
     if (s_nr[r] == 0) continue;
     const int gt1 = s_rank2gt[r] + 1;
     const int nsel = s_nsel[r];
@@ -705,6 +746,14 @@ extern "C" int radet_mt19937_uniforms(const uint32_t* seeds, int32_t batch, int3
   if (batch == 0 || n == 0) return RADET_OK;
   if (!seeds || !out || batch < 0 || n < 0) return RADET_E_BADARG;
   mt19937_uniforms_kernel<<<batch, 32, 0, (cudaStream_t)stream>>>(seeds, n, out);
+  RADET_LAUNCH_CHECK();
+  return RADET_OK;
+}
+
+extern "C" int radet_mt19937_seed(const uint32_t* seeds, int32_t batch, uint32_t* mt_states, void* stream) {
+  if (batch == 0) return RADET_OK;
+  if (!seeds || !mt_states || batch < 0) return RADET_E_BADARG;
+  mt19937_seed_kernel<<<batch, 32, 0, (cudaStream_t)stream>>>(seeds, mt_states);
   RADET_LAUNCH_CHECK();
   return RADET_OK;
 }

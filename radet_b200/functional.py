@@ -101,22 +101,38 @@ def mt19937_uniforms(seeds: torch.Tensor, n: int) -> torch.Tensor:
     return out
 
 
+def seed_states(seeds: torch.Tensor) -> torch.Tensor:
+    """[B,625] legacy MT19937 states of np.random.seed(seeds[b]) (enqueue early / on a side stream)."""
+    _require_cuda(seeds, "seeds")
+    if seeds.dtype != torch.int32:
+        seeds = seeds.to(torch.int32)
+    st = torch.empty((seeds.numel(), _lib.MT_STATE_WORDS), dtype=torch.int32, device=seeds.device)
+    check(_lib.load().radet_mt19937_seed(_ptr(seeds), seeds.numel(), _ptr(st), _stream()), "radet_mt19937_seed")
+    return st
+
+
 # ------------------------------------------------------------------------------------------------ assignment
 def assign(geom: Geometry, level_shapes, gt_counts: Sequence[int], gt_bboxes: torch.Tensor, mask_bits: torch.Tensor,
            mask_hw: Tuple[int, int], *, uniforms: Optional[torch.Tensor] = None, seeds: Optional[torch.Tensor] = None,
            mt_states: Optional[torch.Tensor] = None, positive_num: int = 10, balance_sample: bool = True,
-           gt_offsets: Optional[Tuple[np.ndarray, torch.Tensor]] = None):
+           gt_offsets: Optional[Tuple[np.ndarray, torch.Tensor]] = None, out=None):
     """Batched LabelAssignment (label_assignment.py:136-201).  Returns points_to_gt_index int64 [B,P],
-    points_weight f32 [B,P], consumed int32 [B]."""
+    points_weight f32 [B,P], consumed int32 [B] (written into `out` = (idx, w, consumed) when given)."""
     _require_cuda(gt_bboxes, "gt_bboxes")
     dev = gt_bboxes.device
     B = len(gt_counts)
     grid = geom.grid(level_shapes)
     P = geom.num_points(level_shapes)
     off_h, off_d = gt_offsets if gt_offsets is not None else offsets_of(gt_counts, dev)
-    idx = torch.empty((B, P), dtype=torch.int64, device=dev)
-    w = torch.empty((B, P), dtype=torch.float32, device=dev)
-    consumed = torch.empty((B,), dtype=torch.int32, device=dev)
+    if out is not None:
+        idx, w, consumed = out
+        if tuple(idx.shape) != (B, P) or idx.dtype != torch.int64 or tuple(w.shape) != (B, P) or w.dtype != torch.float32 \
+                or consumed.numel() != B or consumed.dtype != torch.int32 or not (idx.is_contiguous() and w.is_contiguous()):
+            raise RadetError("assign(out=...): need contiguous idx int64 [B,P], w float32 [B,P], consumed int32 [B]")
+    else:
+        idx = torch.empty((B, P), dtype=torch.int64, device=dev)
+        w = torch.empty((B, P), dtype=torch.float32, device=dev)
+        consumed = torch.empty((B,), dtype=torch.int32, device=dev)
     lib = _lib.load()
     nws = lib.radet_assign_workspace_bytes(ctypes.byref(grid), B)
     ws = _workspace(("assign", B, P), nws, dev)
