@@ -120,10 +120,10 @@ def assign(geom: Geometry, level_shapes, gt_counts: Sequence[int], gt_bboxes: to
     points_weight f32 [B,P], consumed int32 [B] (written into `out` = (idx, w, consumed) when given)."""
     _require_cuda(gt_bboxes, "gt_bboxes")
     dev = gt_bboxes.device
-    B = len(gt_counts)
+    off_h, off_d = gt_offsets if gt_offsets is not None else offsets_of(gt_counts, dev)
+    B = int(off_h.shape[0]) - 1
     grid = geom.grid(level_shapes)
     P = geom.num_points(level_shapes)
-    off_h, off_d = gt_offsets if gt_offsets is not None else offsets_of(gt_counts, dev)
     if out is not None:
         idx, w, consumed = out
         if tuple(idx.shape) != (B, P) or idx.dtype != torch.int64 or tuple(w.shape) != (B, P) or w.dtype != torch.float32 \

@@ -5,13 +5,14 @@ configs/bop/*.py build unchanged; the work is done by libradet_b200.so through r
 """
 from . import ops
 from .coders import AnchorGenerator, TBLRBBoxCoder
+from .graphed import GraphedHotPath
 from .head import RADetHead
 from .losses import CrossEntropyLoss, FocalLoss, GIoULoss
 from .pipelines import LabelAssignment
 from .registry import (ANCHOR_GENERATORS, BBOX_CODERS, HEADS, LOSSES, PIPELINES, ConfigDict, Registry, build_anchor_generator,
                        build_bbox_coder, build_from_cfg, build_head, build_loss)
 
-__all__ = ['RADetHead', 'LabelAssignment', 'TBLRBBoxCoder', 'AnchorGenerator', 'FocalLoss', 'GIoULoss', 'CrossEntropyLoss',
+__all__ = ['RADetHead', 'LabelAssignment', 'GraphedHotPath', 'TBLRBBoxCoder', 'AnchorGenerator', 'FocalLoss', 'GIoULoss', 'CrossEntropyLoss',
            'ops', 'HEADS', 'LOSSES', 'BBOX_CODERS', 'ANCHOR_GENERATORS', 'PIPELINES', 'Registry', 'build_from_cfg', 'build_head',
            'build_loss', 'build_bbox_coder', 'build_anchor_generator', 'ConfigDict', 'install_into_reference']
 

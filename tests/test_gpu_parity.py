@@ -424,3 +424,33 @@ def test_nms_properties_full_size():
         assert bool((d[:-1, 4] >= d[1:, 4]).all())                                  # sorted by score
         d2, keep = P.ops.batched_nms(d[:, :4], d[:, 4], l, dict(type="nms", iou_threshold=0.65))
         assert d2.shape[0] == k and np.array_equal(keep.cpu().numpy(), np.arange(k))  # NMS of a kept set keeps everything
+
+
+def test_graphed_hot_path_matches_eager_calls():
+    """plugin.GraphedHotPath (pinned arena -> H2D -> one CUDA graph -> D2H) gives exactly what the call-by-call API gives."""
+    wl, batch, idx_l, w_l, ho = _head_inputs("cfg1")
+    la = P.LabelAssignment(anchor_generator_cfg=dict(type="AnchorGenerator", ratios=[1.0], octave_base_scale=8, scales_per_octave=1,
+                                                     strides=[8, 16, 32, 64, 128]),
+                           neg_threshold=0.2, positive_num=10, adapt_positive_num=False, balance_sample=True)
+    head = P.build_head(dict(type="RADetHead", num_classes=wl.C, in_channels=8, feat_channels=8, stacked_convs=1,
+                             norm_cfg=dict(type="GN", num_groups=4, requires_grad=True),
+                             test_cfg=dict(nms_pre=1000, score_thr=0.05, nms=dict(type="vote", **NMS_CFG), max_per_img=100)))
+    g = P.GraphedHotPath(head, la, len(batch), (wl.H, wl.W), max_gt_per_image=32).capture()
+    buf, views = g.new_host_arena()
+    for rep in range(2):      # replay twice: the kernels re-arm their counters
+        g.fill(views, [im.gt_bboxes for im in batch], [im.gt_labels for im in batch], [syn.sample_grid(im.masks) for im in batch],
+               [im.seed for im in batch], ho.cls, ho.bbox, ho.iou)
+        res = g.run(buf)
+        o32 = orc.head_loss(ho.cls, ho.bbox, ho.iou, [b.gt_bboxes for b in batch], [b.gt_labels for b in batch], idx_l, w_l, wl.C, wl.H, wl.W)
+        for i, k in enumerate(("loss_cls", "loss_bbox", "loss_iou")):
+            assert abs(float(res["losses"][i]) - o32[k]) <= 1e-5 * abs(o32[k]), (rep, k)
+        _check_grads(g.grads[0], o32["grad_cls"], 1e-4, 1e-6)
+        _check_grads(g.grads[1], o32["grad_bbox"], 1e-4, 1e-6)
+        for b, im in enumerate(batch):
+            od, ol = orc.get_bboxes_image([m[b] for m in ho.cls], [m[b] for m in ho.bbox], [m[b] for m in ho.iou], (im.H, im.W, 3),
+                                          np.ones(4, np.float32), score_thr=0.05, nms_cfg=dict(type="vote", **NMS_CFG))
+            k = int(res["num"][b])
+            assert k == od.shape[0]
+            assert np.array_equal(res["dets"][b, :k].numpy().view(np.uint32), od.view(np.uint32))
+            assert np.array_equal(res["labels"][b, :k].numpy(), ol)
+            assert int(res["consumed"][b]) == orc.assign_image_seeded(im.gt_bboxes, im.masks, im.H, im.W, im.seed)[2]
