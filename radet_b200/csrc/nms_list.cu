@@ -238,7 +238,9 @@ nms_list_kernel(NmsParams p) {
     const int s0 = seg_start[sg], s1 = (sg + 1 < nseg) ? seg_start[sg + 1] : n;
     for (int a = s0; a < s1; ++a) {
       const int ia = (int)A.perm[a];
-      if ((int)A.owner[ia] != -1) continue;                 // warp-uniform
+      const int ow = (int)A.owner[ia];
+      __syncwarp();                                         // every lane has read owner[ia] before lane 0 rewrites it
+      if (ow != -1) continue;                               // warp-uniform
       if (p.mode == RADET_NMS_GLOBAL_VOTE && a != s0) {     // vote_ext.cpp:257-263: label already emitted
         if (lane == 0) A.owner[ia] = (IdxT)-2;
         __syncwarp();
