@@ -170,30 +170,21 @@ constexpr int kNormSlots = 8;   // S0 num_pos, S1 sum wq, S2 sum wq(1-giou), S3 
 struct LossWs {
   double norm[kNormSlots];
   unsigned int counter_pos, counter_dense;
-  unsigned int num_rec;   // positives recorded by loss_pos_kernel (consumed + re-armed by loss_dense_kernel)
-  unsigned int pad;
-};
-
-// One record per positive (idx >= 0) point: where its 5 gradient values go and their un-normalised values.
-struct __align__(16) PosRec {
-  int lb;        // level << 24 | image
-  int q;         // cell inside the (image, level) plane
-  float g[5];    // -wq * d giou/d(T,B,L,R),  w * (sigmoid(iou_logit) - iou_target)
-  float pad;
+  unsigned int pad[2];
 };
 
 __global__ void __launch_bounds__(kPosThreads)
 loss_pos_kernel(GridDev grid, int B, MapsDev maps, const int* __restrict__ gt_offsets,
                 const float* __restrict__ gt_bboxes, const int64_t* __restrict__ pidx, const float* __restrict__ pw,
-                radet_loss_cfg_t cfg, LossWs* __restrict__ ws, double* __restrict__ partials, PosRec* __restrict__ recs,
-                int want_grad) {
+                radet_loss_cfg_t cfg, LossWs* __restrict__ ws, double* __restrict__ partials, GradsDev grads) {
   // Phase 1: every thread scans kPosPerThread consecutive points and the CTA compacts the (sparse, spatially
   // clustered) positives into shared memory.  Phase 2: one positive per thread -- IoU target, GIoU and BCE terms and
-  // their gradients, evaluated ONCE here and parked in `recs` (one global atomic per CTA); the dense kernel writes
-  // the zero-filled gradient planes and its last CTA scatters the normalised records on top.
+  // their gradients, evaluated ONCE here.  The un-normalised gradient values are parked in the gradient planes
+  // themselves at the positives' cells; the dense kernel (next in the stream) rescales those cells while it
+  // zero-fills the rest of the regression / IoU planes.
   __shared__ int s_scan[34];
   __shared__ int s_list[kPosThreads * kPosPerThread];
-  __shared__ unsigned s_base;
+  const bool want_grad = grads.bbox[0] != nullptr;
   const int P = grid.off[grid.num_levels];
   const int64_t n = (int64_t)B * P;
   const int64_t blk0 = (int64_t)blockIdx.x * kPosThreads * kPosPerThread;
@@ -210,7 +201,6 @@ loss_pos_kernel(GridDev grid, int B, MapsDev maps, const int* __restrict__ gt_of
     flags &= flags - 1u;
     s_list[pos++] = threadIdx.x * kPosPerThread + k;
   }
-  if (threadIdx.x == 0 && want_grad && total) s_base = atomicAdd(&ws->num_rec, (unsigned)total);
   __syncthreads();
   float acc[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
   for (int i = threadIdx.x; i < total; i += kPosThreads) {
@@ -218,10 +208,6 @@ loss_pos_kernel(GridDev grid, int B, MapsDev maps, const int* __restrict__ gt_of
     const int64_t idx = pidx[t];
     const int b = (int)(t / P), p = (int)(t - (int64_t)b * P);
     const int g0 = gt_offsets[b], G = gt_offsets[b + 1] - g0;
-    PosRec r;
-    r.lb = -1;                 // G == 0: radet_head.py:385-386, everything background -> empty record
-    r.q = 0;
-    r.g[0] = r.g[1] = r.g[2] = r.g[3] = r.g[4] = r.pad = 0.f;
     if (G > 0) {
       const float w = pw[t];
       const int l = level_of(grid, p);
@@ -244,15 +230,15 @@ loss_pos_kernel(GridDev grid, int B, MapsDev maps, const int* __restrict__ gt_of
       acc[3] += w * bce_logits(xi, bt.iou);
       acc[4] += (T + Bt) + (L + R);
       acc[5] += xi;
-      r.lb = (l << 24) | b;
-      r.q = q;
-      r.g[0] = -wq * bt.d[0];                               // d(1 - giou) = -d giou
-      r.g[1] = -wq * bt.d[1];
-      r.g[2] = -wq * bt.d[2];
-      r.g[3] = -wq * bt.d[3];
-      r.g[4] = w * (sigmoidf_(xi) - bt.iou);
+      if (want_grad) {
+        float* gb = grads.bbox[l] + (int64_t)b * 4 * hw + q;
+        gb[0] = -wq * bt.d[0];                              // d(1 - giou) = -d giou
+        gb[hw] = -wq * bt.d[1];
+        gb[2 * hw] = -wq * bt.d[2];
+        gb[3 * hw] = -wq * bt.d[3];
+        grads.iou[l][(int64_t)b * hw + q] = w * (sigmoidf_(xi) - bt.iou);
+      }
     }
-    if (want_grad) recs[s_base + i] = r;
   }
   __shared__ double s_part[kPosThreads / 32][6];
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
@@ -351,7 +337,7 @@ __device__ __forceinline__ void focal_elem(float x, bool is_t, float gamma, floa
   grad = is_t ? -g : g;
 }
 
-constexpr int kDG = 2;   // class planes per load group; the next group is prefetched while the current one computes
+constexpr int kDG = 2;   // class planes per load group (pairs ping-pong between two register sets)
 
 template <bool kGamma2>
 __global__ void __launch_bounds__(kDenseThreads, 3)
@@ -359,7 +345,7 @@ loss_dense_kernel(GridDev grid, DenseTable tab, int B, int C, int cc /* channels
                   GradsDev grads, const int* __restrict__ gt_offsets, const float* __restrict__ gt_bboxes,
                   const int64_t* __restrict__ gt_labels, const int64_t* __restrict__ pidx, const float* __restrict__ pw,
                   radet_loss_cfg_t cfg, const float* __restrict__ grad_scale, LossWs* __restrict__ ws,
-                  double* __restrict__ partials, float* __restrict__ losses, const PosRec* __restrict__ recs) {
+                  double* __restrict__ partials, float* __restrict__ losses) {
   // One thread = one unit (4 consecutive points of one (image, level) plane) x the channel chunk blockIdx.y.
   // Channels 0..C-1 are the class logits (focal loss + gradient); channels C..C+3 are the T,B,L,R gradient planes and
   // C+4 the IoU-logit gradient plane (zero except at the sparse positives), so every output plane is written by the
@@ -400,12 +386,15 @@ loss_dense_kernel(GridDev grid, DenseTable tab, int B, int C, int cc /* channels
     const float* src = maps.cls[l] + ((int64_t)b * C + c0) * hw + q0;
     float* dst = want_grad ? grads.cls[l] + ((int64_t)b * C + c0) * hw + q0 : nullptr;
     const int ncls = cls_end - c0;                  // class planes of this thread (<= 0: regression chunk only)
-    const int ngroups = vec ? (ncls + kDG - 1) / kDG : 0;
-    float4 cur[kDG];
-    if (ngroups > 0) {
-#pragma unroll
-      for (int k = 0; k < kDG; ++k)                 // in flight before the index -> label dependency chain
-        cur[k] = k < ncls ? ldg_stream4(src + (int64_t)k * hw) : make_float4(0.f, 0.f, 0.f, 0.f);
+    const int64_t pstride = hw;                     // plane stride in floats
+    // Software pipeline over pairs of planes with two register sets (A, B) that ping-pong: no copies, no per-plane
+    // predicates in the steady state, plane addresses advance by pointer increments.
+    const int npairs = vec ? ncls / 2 : 0;          // full pairs; an odd last plane is handled after the loop
+    float4 a0, a1, b0, b1;
+    a0 = a1 = b0 = b1 = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (npairs > 0) {                               // in flight before the index -> label dependency chain
+      a0 = ldg_stream4(src);
+      a1 = ldg_stream4(src + pstride);
     }
     const int g0 = gt_offsets[b], G = gt_offsets[b + 1] - g0;
     const int64_t pbase = (int64_t)b * P + grid.off[l] + q0;
@@ -427,34 +416,44 @@ loss_dense_kernel(GridDev grid, DenseTable tab, int B, int C, int cc /* channels
       lab[i] = (int)label_of(idx[i], G, gt_labels + g0, C) - c0;   // relative to the chunk
       kw[i] = k_cls * w[i];
     }
-    for (int g = 0; g < ngroups; ++g) {
-      float4 nxt[kDG];
-      const bool more = g + 1 < ngroups;
-      if (more) {                                   // software pipeline: next group's loads fly during this compute
-#pragma unroll
-        for (int k = 0; k < kDG; ++k) {
-          const int cr = (g + 1) * kDG + k;
-          nxt[k] = cr < ncls ? ldg_stream4(src + (int64_t)cr * hw) : make_float4(0.f, 0.f, 0.f, 0.f);
+    auto plane = [&](const float4& xv, int cr, float* out) {
+      float lo_, gr_;
+      float4 gv;
+      focal_elem<kGamma2>(xv.x, lab[0] == cr, gamma, alpha, lo_, gr_); lsum = fmaf(w[0], lo_, lsum); gv.x = kw[0] * gr_;
+      focal_elem<kGamma2>(xv.y, lab[1] == cr, gamma, alpha, lo_, gr_); lsum = fmaf(w[1], lo_, lsum); gv.y = kw[1] * gr_;
+      focal_elem<kGamma2>(xv.z, lab[2] == cr, gamma, alpha, lo_, gr_); lsum = fmaf(w[2], lo_, lsum); gv.z = kw[2] * gr_;
+      focal_elem<kGamma2>(xv.w, lab[3] == cr, gamma, alpha, lo_, gr_); lsum = fmaf(w[3], lo_, lsum); gv.w = kw[3] * gr_;
+      if (out) stg_stream4(out, gv);
+    };
+    {
+      const float* sp_ = src + 2 * pstride;         // next pair to load
+      float* dp_ = dst;                             // next pair to store
+      int cr = 0;
+      int left = npairs;
+      while (left >= 2) {                           // two pairs per trip: compute A while B loads, then B while A loads
+        b0 = ldg_stream4(sp_);
+        b1 = ldg_stream4(sp_ + pstride);
+        plane(a0, cr, dp_);
+        plane(a1, cr + 1, dp_ ? dp_ + pstride : nullptr);
+        if (left > 2) {
+          a0 = ldg_stream4(sp_ + 2 * pstride);
+          a1 = ldg_stream4(sp_ + 3 * pstride);
         }
+        plane(b0, cr + 2, dp_ ? dp_ + 2 * pstride : nullptr);
+        plane(b1, cr + 3, dp_ ? dp_ + 3 * pstride : nullptr);
+        sp_ += 4 * pstride;
+        if (dp_) dp_ += 4 * pstride;
+        cr += 4;
+        left -= 2;
       }
-#pragma unroll
-      for (int k = 0; k < kDG; ++k) {
-        const int cr = g * kDG + k;
-        if (cr < ncls) {
-          const float4 xv = cur[k];
-          float lo_, gr_;
-          float4 gv;
-          focal_elem<kGamma2>(xv.x, lab[0] == cr, gamma, alpha, lo_, gr_); lsum = fmaf(w[0], lo_, lsum); gv.x = kw[0] * gr_;
-          focal_elem<kGamma2>(xv.y, lab[1] == cr, gamma, alpha, lo_, gr_); lsum = fmaf(w[1], lo_, lsum); gv.y = kw[1] * gr_;
-          focal_elem<kGamma2>(xv.z, lab[2] == cr, gamma, alpha, lo_, gr_); lsum = fmaf(w[2], lo_, lsum); gv.z = kw[2] * gr_;
-          focal_elem<kGamma2>(xv.w, lab[3] == cr, gamma, alpha, lo_, gr_); lsum = fmaf(w[3], lo_, lsum); gv.w = kw[3] * gr_;
-          if (dst) stg_stream4(dst + (int64_t)cr * hw, gv);
-        }
+      if (left == 1) {                              // one full pair left (already in A)
+        plane(a0, cr, dp_);
+        plane(a1, cr + 1, dp_ ? dp_ + pstride : nullptr);
+        if (dp_) dp_ += 2 * pstride;
+        cr += 2;
       }
-      if (more) {
-#pragma unroll
-        for (int k = 0; k < kDG; ++k) cur[k] = nxt[k];
-      }
+      if (vec && cr < ncls)                         // odd last plane
+        plane(ldg_stream4(src + (int64_t)cr * pstride), cr, dst ? dst + (int64_t)cr * pstride : nullptr);
     }
     if (!vec) {                                     // planes whose size is not a multiple of 4: scalar path
       for (int cr = 0; cr < ncls; ++cr) {
@@ -469,18 +468,26 @@ loss_dense_kernel(GridDev grid, DenseTable tab, int B, int C, int cc /* channels
         }
       }
     }
-    // gradient planes of the regression / IoU branches (channels C .. C+4): zero fill; the sparse positives are
-    // scattered on top by the last CTA (below)
+    // gradient planes of the regression / IoU branches (channels C .. C+4): zero everywhere except at the positives,
+    // whose un-normalised values loss_pos_kernel parked in these planes: rescale those cells in place
     if (want_grad && c1 > C) {
+      const bool anypos = G > 0 && (idx[0] >= 0 || idx[1] >= 0 || idx[2] >= 0 || idx[3] >= 0);
       for (int ch = max(c0, C); ch < c1; ++ch) {
         const int kk = ch - C;  // 0..3: T,B,L,R ; 4: iou logit
         float* o = kk < 4 ? grads.bbox[l] + ((int64_t)b * 4 + kk) * hw + q0 : grads.iou[l] + (int64_t)b * hw + q0;
+        const float kn = kk < 4 ? k_box : k_iou, gs = kk < 4 ? gs_box : gs_iou;
+        float gv[4] = {0.f, 0.f, 0.f, 0.f};
+        if (anypos) {
+#pragma unroll
+          for (int i = 0; i < 4; ++i)
+            if (i < nv && idx[i] >= 0) gv[i] = has_pos ? kn * o[i] : gs;        // radet_head.py:280-281 when num_pos == 0
+        }
         if (vec) {
-          stg_stream4(o, make_float4(0.f, 0.f, 0.f, 0.f));
+          stg_stream4(o, make_float4(gv[0], gv[1], gv[2], gv[3]));
         } else {
 #pragma unroll
           for (int i = 0; i < 4; ++i)
-            if (i < nv) o[i] = 0.f;
+            if (i < nv) o[i] = gv[i];
         }
       }
     }
@@ -492,7 +499,6 @@ loss_dense_kernel(GridDev grid, DenseTable tab, int B, int C, int cc /* channels
   const unsigned nblocks = gridDim.x, bid = blockIdx.x;
   const double v = warp_sum((double)lsum);
   if (lane == 0) s_part[wid] = v;
-  __threadfence();   // this thread's gradient stores are visible device-wide before the CTA signals completion
   __syncthreads();
   if (threadIdx.x == 0) {
     double s = 0.0;
@@ -518,22 +524,6 @@ loss_dense_kernel(GridDev grid, DenseTable tab, int B, int C, int cc /* channels
     losses[3] = (float)num_pos;
     ws->counter_dense = 0u;
   }
-  // every other CTA has finished (and fenced) its zero fill: scatter the normalised gradients of the positives
-  if (want_grad) {
-    const unsigned nrec = ws->num_rec;
-    for (unsigned i = threadIdx.x; i < nrec; i += kDenseThreads) {
-      const PosRec r = recs[i];
-      if (r.lb < 0) continue;   // image without GT
-      const int l = r.lb >> 24, b = r.lb & 0xffffff;
-      const int hw = grid.h[l] * grid.w[l];
-      float* gb = grads.bbox[l] + (int64_t)b * 4 * hw + r.q;
-#pragma unroll
-      for (int k = 0; k < 4; ++k) gb[(int64_t)k * hw] = has_pos ? k_box * r.g[k] : gs_box;   // radet_head.py:280-281
-      grads.iou[l][(int64_t)b * hw + r.q] = has_pos ? k_iou * r.g[4] : gs_iou;
-    }
-  }
-  __syncthreads();
-  if (threadIdx.x == 0) ws->num_rec = 0u;   // re-arm
 }
 
 struct ScaleTable {
@@ -664,8 +654,7 @@ extern "C" size_t radet_loss_workspace_bytes(const radet_grid_t* grid, int32_t b
   const int64_t n = (int64_t)batch * g.off[g.num_levels];
   const int64_t pos_blocks = (n + kPosThreads * kPosPerThread - 1) / (kPosThreads * kPosPerThread);
   const int64_t dense_blocks = dblk;
-  return align_up(sizeof(LossWs), 256) + align_up((size_t)pos_blocks * 6 * 8, 256) + align_up((size_t)dense_blocks * 8, 256) +
-         align_up((size_t)n * sizeof(PosRec), 256);
+  return align_up(sizeof(LossWs), 256) + align_up((size_t)pos_blocks * 6 * 8, 256) + align_up((size_t)dense_blocks * 8, 256);
 }
 
 extern "C" int radet_loss_fwd_bwd(const radet_grid_t* grid, int32_t batch, int32_t num_classes, const radet_maps_t* maps,
@@ -709,12 +698,10 @@ extern "C" int radet_loss_fwd_bwd(const radet_grid_t* grid, int32_t batch, int32
   const int64_t pos_blocks = (n + kPosThreads * kPosPerThread - 1) / (kPosThreads * kPosPerThread);
   double* pos_part = reinterpret_cast<double*>(wsb + align_up(sizeof(LossWs), 256));
   double* dense_part = reinterpret_cast<double*>(wsb + align_up(sizeof(LossWs), 256) + align_up((size_t)pos_blocks * 6 * 8, 256));
-  PosRec* recs = reinterpret_cast<PosRec*>(wsb + align_up(sizeof(LossWs), 256) + align_up((size_t)pos_blocks * 6 * 8, 256) +
-                                           align_up((size_t)dblk * 8, 256));
   cudaStream_t st = (cudaStream_t)stream;
   if (phases & RADET_LOSS_PHASE_NORMALIZERS) {
     loss_pos_kernel<<<(unsigned)pos_blocks, kPosThreads, 0, st>>>(g, batch, md, gt_offsets, gt_bboxes, points_to_gt_index,
-                                                                  points_weight, *cfg, ws, pos_part, recs, grads ? 1 : 0);
+                                                                  points_weight, *cfg, ws, pos_part, gd);
     RADET_LAUNCH_CHECK();
   }
   if (!(phases & RADET_LOSS_PHASE_DENSE)) return RADET_OK;
@@ -722,11 +709,11 @@ extern "C" int radet_loss_fwd_bwd(const radet_grid_t* grid, int32_t batch, int32
   if (cfg->gamma == 2.0f)
     loss_dense_kernel<true><<<dblocks, kDenseThreads, 0, st>>>(g, tab, batch, num_classes, cc, nj, md, gd, gt_offsets, gt_bboxes,
                                                                gt_labels, points_to_gt_index, points_weight, *cfg, grad_scale,
-                                                               ws, dense_part, losses, recs);
+                                                               ws, dense_part, losses);
   else
     loss_dense_kernel<false><<<dblocks, kDenseThreads, 0, st>>>(g, tab, batch, num_classes, cc, nj, md, gd, gt_offsets, gt_bboxes,
                                                                 gt_labels, points_to_gt_index, points_weight, *cfg, grad_scale,
-                                                                ws, dense_part, losses, recs);
+                                                                ws, dense_part, losses);
   RADET_LAUNCH_CHECK();
   return RADET_OK;
 }
