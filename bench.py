@@ -47,6 +47,8 @@ def parse():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--profile", action="store_true", help="few eager steps, nothing else (for ncu)")
     ap.add_argument("--serial", action="store_true", help="one stream: train and inference branches back to back")
+    ap.add_argument("--inflight", type=int, default=8, help="steps in flight: step graphs are replayed round-robin on this many "
+                    "streams, the assignment running this many batches ahead (1 = one step at a time)")
     ap.add_argument("--no-prefetch", action="store_true", help="assignment and loss of the same batch in sequence (no one-batch-ahead assignment)")
     ap.add_argument("--sets", type=int, default=0, help="rotating input sets (default: enough to exceed 2x L2)")
     ap.add_argument("--cpu-baseline-json", action="store_true", help=argparse.SUPPRESS)
@@ -237,6 +239,8 @@ def main():
     R = args.sets or max(2, int(np.ceil(2.2 * L2_BYTES / per_set)))
     if args.profile:
         R = 2
+    U = 1 if (args.profile or args.no_graph) else max(1, args.inflight)
+    R = (R + U - 1) // U * U            # set r always replays on stream r % U
     sets = []
     host_sets = []
 
@@ -265,9 +269,8 @@ def main():
             host_sets.append((batch, ho))
     up_ones = torch.ones(3, dtype=torch.float32, device=dev)
 
-    side = torch.cuda.Stream(device=dev)
-    side2 = torch.cuda.Stream(device=dev)
-    side3 = torch.cuda.Stream(device=dev)
+    lanes = [dict(main=torch.cuda.Stream(device=dev), side=torch.cuda.Stream(device=dev), side2=torch.cuda.Stream(device=dev),
+                  side3=torch.cuda.Stream(device=dev)) for _ in range(U)]
     for s in sets:   # assignment buffers of every input set (double-buffered hand-off, see step())
         s["abuf"] = (torch.empty((B, Ppts), dtype=torch.int64, device=dev), torch.empty((B, Ppts), dtype=torch.float32, device=dev),
                      torch.empty((B,), dtype=torch.int32, device=dev))
@@ -287,18 +290,21 @@ def main():
     def do_detect(s):
         return F.get_bboxes(geom, wl.C, s["cls"], s["bbox"], s["iou"], s["shp"], s["sf"], dcfg, rescale=True)
 
-    def step(s, keep=None, nxt=None):
+    def step(s, keep=None, nxt=None, lane=0):
         """One step = assign + loss fwd/bwd + decode/vote-NMS, each over one batch of B images.
 
         --serial: everything back to back on one stream.
         --no-prefetch: the train branch (assign -> loss) and the inference branch (decode+NMS) of the SAME batch forked
             onto two streams (two branches of one CUDA graph): the latency-bound kernels of one branch fill the SMs the
             other leaves idle; np.random.seed()'s sequential state bring-up runs on a third stream.
-        default: additionally the assignment runs one batch AHEAD (assign(batch i+1) || loss(batch i) || detect(batch i)),
+        default: additionally the assignment runs AHEAD (assign(batch i+U) || loss(batch i) || detect(batch i)),
             the way the reference runs LabelAssignment in DataLoader workers ahead of the trainer
             (configs/base/datasets/bop_detection.py:19-32); the assignment is handed over through per-set buffers
-            written by the previous step.  Every step still executes all three stages for one full batch."""
+            written by an earlier step on the same stream.  Every step still executes all three stages for one full
+            batch.  U = --inflight step graphs are in flight at a time (round-robin over U streams, each with its
+            own workspaces), so the narrow latency-bound kernels of neighbouring steps share the 148 SMs."""
         main = torch.cuda.current_stream()
+        side, side2, side3 = lanes[lane]["side"], lanes[lane]["side2"], lanes[lane]["side3"]
         if args.serial:
             idx, w, used = do_assign(s)
             losses, grads = do_loss(s, idx, w)
@@ -338,28 +344,39 @@ def main():
     prefetch = not (args.serial or args.no_prefetch)
     for s in sets:
         do_assign(s, out=s["abuf"])
-    l0 = _lib.launch_count()
-    step(sets[0], nxt=sets[1 % R] if prefetch else None)
-    launches_per_step = _lib.launch_count() - l0
-    for i in range(max(3, min(args.warmup, 20))):
-        step(sets[i % R], nxt=sets[(i + 1) % R] if prefetch else None)
     torch.cuda.synchronize()
+    nxt_of = lambda r: sets[(r + U) % R] if prefetch else None
+    l0 = _lib.launch_count()
+    with torch.cuda.stream(lanes[0]["main"]):
+        step(sets[0], nxt=nxt_of(0), lane=0)
+    launches_per_step = _lib.launch_count() - l0
+    for i in range(max(3, min(args.warmup, 20), U)):      # eager warm-up on every lane's streams (allocates its workspaces)
+        with torch.cuda.stream(lanes[i % U]["main"]):
+            step(sets[i % R], nxt=nxt_of(i % R), lane=i % U)
+        torch.cuda.synchronize()
 
     # ---- CUDA graphs: one per input set (the C ABI only enqueues, so the whole step is capturable)
     use_graph = not args.no_graph
     graphs, outs = [], []
     if use_graph:
-        pool = torch.cuda.graph_pool_handle()
+        # one memory pool per lane: graphs of one lane replay back to back on its stream and may share intermediates,
+        # graphs of different lanes run concurrently and must not
+        lane_pools = [torch.cuda.graph_pool_handle() for _ in range(U)]
         for r_, s in enumerate(sets):
             g = torch.cuda.CUDAGraph()
             keep = []
-            with torch.cuda.graph(g, pool=pool):
-                step(s, keep, nxt=sets[(r_ + 1) % R] if prefetch else None)
+            with torch.cuda.graph(g, pool=lane_pools[r_ % U], stream=lanes[r_ % U]["main"]):
+                step(s, keep, nxt=nxt_of(r_), lane=r_ % U)
             graphs.append(g)
             outs.append(keep)
-        run = lambda i: graphs[i % R].replay()
+
+        def run(i, one_lane=False):
+            with torch.cuda.stream(lanes[0 if one_lane else i % U]["main"]):
+                graphs[i % R].replay()
     else:
-        run = lambda i: step(sets[i % R], nxt=sets[(i + 1) % R] if prefetch else None)
+        def run(i, one_lane=False):
+            with torch.cuda.stream(lanes[0]["main"]):
+                step(sets[i % R], nxt=nxt_of(i % R))
 
     def barrier():
         if world > 1:
@@ -377,19 +394,48 @@ def main():
         i += 1
         if i % 256 == 0:
             torch.cuda.synchronize()
-    barrier()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    def timed(n, one_lane=False):
+        """ms for n steps: events on the current stream, every lane's stream forked from / joined into it."""
+        barrier()
+        cur = torch.cuda.current_stream()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for ln in lanes:
+            ln["main"].wait_stream(cur)
+        for i in range(n):
+            run(i, one_lane)
+        for ln in lanes:
+            cur.wait_stream(ln["main"])
+        e1.record()
+        barrier()
+        ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms.item())
+
+    one_lane_ms = timed(min(args.steps, 500), one_lane=True) / min(args.steps, 500) if U > 1 else None
     t_clk0 = time.perf_counter()
-    e0.record()
-    for i in range(args.steps):
-        run(i)
-    e1.record()
-    barrier()
+    ms_total = timed(args.steps)
     t_clk1 = time.perf_counter()
-    ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
-    ms_total = float(ms.item())
+
+    # overlapped replays must leave exactly what one-at-a-time replays leave (no scratch shared between lanes)
+    overlap_check = None
+    if use_graph and U > 1:
+        flat = lambda keep: [t.clone() for t in (keep[0][0], keep[0][1], keep[0][2], *keep[0][3][0], *keep[0][3][1], *keep[0][3][2],
+                                                 keep[0][4], keep[0][5], keep[0][6])]
+        for i in range(2 * R):
+            run(i)
+        torch.cuda.synchronize()
+        got = [flat(k) for k in outs]
+        for i in range(R):
+            run(i, one_lane=True)
+            torch.cuda.synchronize()
+            want = flat(outs[i])
+            for a, b in zip(got[i], want):
+                if not torch.equal(a, b):
+                    raise RuntimeError(f"overlapped replay of input set {i} differs from its serial replay")
+        overlap_check = f"outputs of {R} sets after overlapped replays bit-identical to one-at-a-time replays"
+        del got
     ms_per_step = ms_total / args.steps
     value = world * B * args.steps / (ms_total * 1e-3)
 
@@ -402,9 +448,10 @@ def main():
         torch.cuda.synchronize()
         gs, keepalive = [], []
         if use_graph:
+            stage_pool = torch.cuda.graph_pool_handle()
             for s in sets:
                 g = torch.cuda.CUDAGraph()
-                with torch.cuda.graph(g, pool=pool):
+                with torch.cuda.graph(g, pool=stage_pool):
                     keepalive.append(fn(s))
                 gs.append(g)
             call = lambda i: gs[i % R].replay()
@@ -494,8 +541,10 @@ def main():
                        "launch": ("cuda_graph" if use_graph else "eager") + (
                            ", 1 stream" if args.serial else
                            ", assign->loss and decode+NMS branches of one batch forked on streams" if args.no_prefetch else
-                           ", 3 branches per step: assign(batch i+1) || loss fwd+bwd(batch i) || decode+NMS(batch i) "
-                           "(assignment runs one batch ahead like the reference's DataLoader workers)"),
+                           f", 3 branches per step: assign(batch i+{U}) || loss fwd+bwd(batch i) || decode+NMS(batch i) "
+                           f"(assignment runs ahead like the reference's DataLoader workers); {U} step graphs in flight "
+                           f"(round-robin over {U} streams)"),
+                       "steps_in_flight": U, "ms_per_step_one_in_flight": one_lane_ms, "overlap_check": overlap_check,
                        "l2": f"{R} rotating input sets, {R * per_set / 1e6:.0f} MB total > L2 ({L2_BYTES / 1e6:.0f} MB)",
                        "parallelism": f"images sharded over {world} rank(s), no data-path collective"},
             "point_gt_pairs_per_s": world * pairs / (stage_us["assign(pairs+resolve)"] * 1e-6),
@@ -601,7 +650,8 @@ def run_e2e(args, wl, B, host_sets, dev, P, F, world):
 
     # ---------------- graphed path
     gmax = max(int(im.gt_bboxes.shape[0]) for batch, _ in host_sets for im in batch)
-    pipes = [P.GraphedHotPath(head, la, B, (wl.H, wl.W), max_gt_per_image=max(32, gmax), device=dev).capture() for _ in range(2)]
+    NP = 3   # instances in flight: the H2D copy of batch i+1/i+2 overlaps the kernels and the D2H of batch i
+    pipes = [P.GraphedHotPath(head, la, B, (wl.H, wl.W), max_gt_per_image=max(32, gmax), device=dev).capture() for _ in range(NP)]
     arenas = []
     for batch, ho in host_sets:
         buf, views = pipes[0].new_host_arena()
@@ -610,25 +660,28 @@ def run_e2e(args, wl, B, host_sets, dev, P, F, world):
         arenas.append(buf)
     n = max(10, min(args.steps, 1000))
     sink = 0.0
-    for i in range(6):
-        sink += float(pipes[i % 2].run(arenas[i % len(arenas)])["losses"][0])
+    for i in range(2 * NP):
+        sink += float(pipes[i % NP].run(arenas[i % len(arenas)])["losses"][0])
     if world > 1:
         dist.barrier()
     torch.cuda.synchronize()
     t0 = time.perf_counter()
-    pipes[0].launch(arenas[0])
-    for i in range(1, n + 1):
+    for i in range(n + NP - 1):
         if i < n:
-            pipes[i % 2].launch(arenas[i % len(arenas)])          # copy + graph of batch i overlap batch i-1
-        res = pipes[(i - 1) % 2].wait()                            # results of batch i-1 are on the host now
-        sink += float(res["losses"][0]) + float(res["num"][0])
+            pipes[i % NP].launch(arenas[i % len(arenas)])         # copy + graph of batch i overlap the batches before it
+        j = i - (NP - 1)
+        if j >= 0:
+            res = pipes[j % NP].wait()                             # results of batch j are on the host now
+            sink += float(res["losses"][0]) + float(res["num"][0])
     torch.cuda.synchronize()
     dt = sync_max(time.perf_counter() - t0)
     out = {"value": world * B * n / dt, "unit": "images/s", "h2d_bytes_per_step": int(pipes[0].h2d_bytes),
            "d2h_bytes_per_step": int(pipes[0].d2h_bytes), "steps": n, "ms_per_step": 1e3 * dt / n,
+           "h2d_GBps_per_gpu": pipes[0].h2d_bytes * n / dt / 1e9,
            "timing": "host wall clock between device synchronisations (max over ranks)",
            "api": "plugin.GraphedHotPath.launch/wait: pinned host arena -> H2D -> CUDA graph (seed | pack+assign+loss fwd/bwd | "
-                  "decode+vote-NMS) -> D2H of losses/detections; two instances ping-pong"}
+                  f"decode+vote-NMS) -> D2H of losses/detections; {NP} instances in flight; the step is bound by the "
+                  "host->device copy of the head outputs (h2d_GBps_per_gpu against the PCIe link)"}
 
     # ---------------- eager plugin calls
     pin = lambda a: torch.from_numpy(np.ascontiguousarray(a)).pin_memory()

@@ -51,4 +51,4 @@ lib.radet_debug_set_buffer(None)
 d = dbg2.cpu().numpy()
 print("assign_resolve per image: G, uniforms used, candidate points M, then cycles: seed+twist | workers phases 1-3 | join | sampling | tail(phase 5)")
 for r in d:
-    print(f"  G={r[8]:3d} used={r[9]:4d} M={r[10]:5d}  seed={r[1]-r[0]:7d} workers={r[2]-r[0]:7d} join={r[3]-r[0]:7d} sampling={r[4]-r[3]:7d} tail={r[5]-r[4]:7d} total={r[5]-r[0]:7d}   first GT: draw={r[12]-r[11]} search={r[13]-r[12]} dedupe={r[14]-r[13]} round_end={r[15]-r[14]}")
+    print(f"  G={r[8]:3d} used={r[9]:4d} M={r[10]:5d}  state={r[1]-r[0]:6d} | compaction={r[11]-r[0]:6d} claiming={r[12]-r[11]:6d} owners={r[2]-r[12]:6d} | join={r[3]-r[0]:6d} sampling={r[4]-r[3]:6d} tail={r[5]-r[4]:6d} total={r[5]-r[0]:6d}")

@@ -488,37 +488,63 @@ assign_resolve_kernel(GridDev grid, const int* __restrict__ gt_offsets, const fl
     // ---- warps 1..31 (992 worker threads, named barrier 1)
     const int wt_ = tid - 32;
     // 1. ordered compaction of points that are a candidate of at least one GT; everything else keeps the defaults.
-    //    Each worker owns `per` consecutive points (one block scan per tile of kWorkers*per points).
-    const int per = min(32, (P + kWorkers - 1) / kWorkers);
-    for (int base = 0; base < P; base += kWorkers * per) {
-      const int p0 = base + wt_ * per;
-      unsigned fl = 0u;
-      for (int k = 0; k < per; ++k) {
-        const int p = p0 + k;
-        if (p < P) {
-          uint32_t any = 0;
+    //    Worker warp ww owns a contiguous chunk of the points and walks it 32 points at a time (coalesced loads and
+    //    default stores, independent iterations); lane `it` keeps the ballot word of iteration `it`, so one tile
+    //    covers up to 31 * 1024 points with a single cross-warp scan.
+    const int ww = wid - 1;
+    constexpr int kWW = kWorkers / 32;
+    for (int base = 0; base < P; base += kWW * 1024) {
+      const int span = min(P - base, kWW * 1024);
+      const int chunk = (((span + kWW - 1) / kWW) + 31) & ~31;     // points per warp, multiple of 32, <= 1024
+      const int c0 = base + ww * chunk;
+      const int nit = max(0, min(chunk, base + span - c0) + 31) >> 5;
+      uint32_t myword = 0u;
+      for (int it0 = 0; it0 < nit; it0 += 8) {                      // 8 iterations' loads in flight
+        uint32_t any[8];
 #pragma unroll
-          for (int w = 0; w < W32; ++w) any |= bits[(int64_t)p * (2 * W32) + w];
-          if (any) fl |= 1u << k;
+        for (int u = 0; u < 8; ++u) {
+          const int p = c0 + (it0 + u) * 32 + lane;
+          any[u] = 0u;
+          if (it0 + u < nit && p < base + span) {
+#pragma unroll
+            for (int w = 0; w < W32; ++w) any[u] |= bits[(int64_t)p * (2 * W32) + w];
+          }
+        }
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+          const int p = c0 + (it0 + u) * 32 + lane;
+          if (it0 + u < nit && p < base + span && !any[u]) {
+            idx[p] = -1;
+            wt[p] = 1.0f;
+          }
+          const uint32_t bal = __ballot_sync(kFull, any[u] != 0u);
+          if (lane == it0 + u) myword = bal;
         }
       }
-      for (int k = 0; k < per; ++k) {
-        const int p = p0 + k;
-        if (p < P && !((fl >> k) & 1u)) {
-          idx[p] = -1;
-          wt[p] = 1.0f;
-        }
+      // exclusive prefix of the per-iteration counts inside the warp, then across the worker warps
+      const int cnt = __popc(myword);
+      int inc = cnt;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const int t = __shfl_up_sync(kFull, inc, o);
+        if (lane >= o) inc += t;
       }
-      int total;
-      int pos = M + worker_exclusive_scan(__popc(fl), S->scan, &total);
-      while (fl) {
-        const int k = __ffs((int)fl) - 1;
-        fl &= fl - 1u;
-        list[pos++] = (uint32_t)(p0 + k);
+      worker_barrier();                                             // S->scan reuse across tiles
+      if (lane == 31) S->scan[ww] = inc;
+      worker_barrier();
+      const int wtot = lane < kWW ? S->scan[lane] : 0;
+      const int before = __reduce_add_sync(kFull, lane < ww ? wtot : 0);
+      const int total = __reduce_add_sync(kFull, wtot);
+      const int ex = M + before + inc - cnt;
+      for (int it = 0; it < nit; ++it) {
+        const uint32_t bal = __shfl_sync(kFull, myword, it);
+        const int off = __shfl_sync(kFull, ex, it);
+        if ((bal >> lane) & 1u) list[off + __popc(bal & ((1u << lane) - 1u))] = (uint32_t)(c0 + it * 32 + lane);
       }
       M += total;
     }
     worker_barrier();
+    if (wid == 1) RESOLVE_DBG(11);
 
     // 2. fixed point over the fallback set F
     for (int round = 0; round <= G; ++round) {
@@ -562,6 +588,7 @@ assign_resolve_kernel(GridDev grid, const int* __restrict__ gt_offsets, const fl
       if (!changed) break;
     }
 
+    if (wid == 1) RESOLVE_DBG(12);
     // 3. owners, member counts; unclaimed candidate points keep the defaults
     for (int e = wt_; e < M; e += kWorkers) {
       const int p = (int)list[e];
@@ -638,43 +665,34 @@ assign_resolve_kernel(GridDev grid, const int* __restrict__ gt_offsets, const fl
         }
         if (lane == 0) s_nsel[r] = __popc(fm);
       } else {                                                      // :119 choice(n, K, p, replace=False)
-        int n_uniq = 0;
-        const bool stamp = dbg && dbg[(int64_t)blockIdx.x * 16 + 11] == 0;
-        if (stamp) RESOLVE_DBG(11);
-        while (n_uniq < K) {
+        // Lane j < n_uniq keeps, in registers, the j-th kept position f (draw order) and g = f - #{kept < f}, the
+        // number of not-yet-kept entries below it.  A draw of rank t among the not-yet-kept entries then lands on
+        // position t + #{j : g_j <= t} — one pass of shuffles, no fixed-point iteration over found[].
+        int n_uniq = 0, f = 0x7fffffff, g = 0x7fffffff;
+        while (true) {
           const int d = K - n_uniq, m = n - n_uniq;
           const unsigned long long x = draw(d);
-          if (stamp && n_uniq == 0) RESOLVE_DBG(12);
           if (overflow) break;
-          int pos = -1;
-          if (lane < d) {
-            // rank among the not-yet-found entries, then skip over the found ones:
-            // pos = t + #{f in found : f <= pos}, iterated to its fixed point (found[] is tiny)
-            const int t = search(x, m);
-            int cur = t;
-            while (true) {
-              int le = 0;
-              for (int j = 0; j < n_uniq; ++j) le += (s_found[j] <= cur) ? 1 : 0;
-              if (t + le == cur) break;
-              cur = t + le;
-            }
-            pos = cur;
-          }
-          if (stamp && n_uniq == 0) RESOLVE_DBG(13);
+          const int t = search(x, m);                               // idle lanes hold x = 0: harmless, result unused
+          int c = 0;
+          for (int j = 0; j < n_uniq; ++j) c += (__shfl_sync(kFull, g, j) <= t) ? 1 : 0;
+          const int pos = lane < d ? t + c : -1;
           // keep the first occurrence of each value, in draw order (np.unique(return_index) + sort in choice())
           const unsigned peers = __match_any_sync(kFull, pos);      // idle lanes all hold -1: at most d+1 distinct values
           const bool first = lane < d && lane == __ffs((int)peers) - 1;
           const unsigned fm = __ballot_sync(kFull, first);
-          __syncwarp();
           if (first) s_found[n_uniq + __popc(fm & ((1u << lane) - 1u))] = pos;
           __syncwarp();
-          if (stamp && n_uniq == 0) RESOLVE_DBG(14);
           n_uniq += __popc(fm);
+          if (lane < n_uniq) f = s_found[lane];
+          if (n_uniq >= K) break;
+          int rk = 0;
+          for (int j = 0; j < n_uniq; ++j) rk += (__shfl_sync(kFull, f, j) < f) ? 1 : 0;
+          g = lane < n_uniq ? f - rk : 0x7fffffff;
         }
         if (overflow) break;
-        if (stamp) RESOLVE_DBG(15);
         if (lane < K) {
-          selpos[lane] = s_found[lane];
+          selpos[lane] = f;
           selcnt[lane] = 1;
         }
         if (lane == 0) s_nsel[r] = K;

@@ -58,8 +58,9 @@ _WS = {}
 
 
 def _workspace(key, nbytes, device):
-    """Zero-initialised, cached per configuration (the kernels re-arm their counters)."""
-    k = (key, str(device))
+    """Zero-initialised, cached per configuration AND per stream (the kernels re-arm their counters; calls on the same
+    stream are ordered, calls enqueued on different streams may overlap and must not share scratch memory)."""
+    k = (key, str(device), torch.cuda.current_stream(device).cuda_stream)
     t = _WS.get(k)
     if t is None or t.numel() < nbytes:
         t = torch.zeros(max(int(nbytes), 256), dtype=torch.uint8, device=device)
