@@ -47,6 +47,7 @@ def parse():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--profile", action="store_true", help="few eager steps, nothing else (for ncu)")
     ap.add_argument("--serial", action="store_true", help="one stream: train and inference branches back to back")
+    ap.add_argument("--stages", default="assign,loss,detect", help="development aid: run only these stages of the step")
     ap.add_argument("--inflight", type=int, default=8, help="steps in flight: step graphs are replayed round-robin on this many "
                     "streams, the assignment running this many batches ahead (1 = one step at a time)")
     ap.add_argument("--no-prefetch", action="store_true", help="assignment and loss of the same batch in sequence (no one-batch-ahead assignment)")
@@ -290,6 +291,8 @@ def main():
     def do_detect(s):
         return F.get_bboxes(geom, wl.C, s["cls"], s["bbox"], s["iou"], s["shp"], s["sf"], dcfg, rescale=True)
 
+    stages = set(args.stages.split(","))
+
     def step(s, keep=None, nxt=None, lane=0):
         """One step = assign + loss fwd/bwd + decode/vote-NMS, each over one batch of B images.
 
@@ -312,6 +315,21 @@ def main():
         else:
             side.wait_stream(main)
             side2.wait_stream(main)
+            if stages != {"assign", "loss", "detect"}:          # development aid: a subset of the step
+                idx, w, used = s["abuf"]
+                losses = grads = dets = dl = num = None
+                if "assign" in stages:
+                    with torch.cuda.stream(side2):
+                        states = F.seed_states((nxt or s)["seeds"])
+                        do_assign(nxt or s, out=(nxt or s)["abuf"], states=states)
+                if "detect" in stages:
+                    with torch.cuda.stream(side):
+                        dets, dl, num = do_detect(s)
+                if "loss" in stages:
+                    losses, grads = do_loss(s, idx, w)
+                main.wait_stream(side2)
+                main.wait_stream(side)
+                return losses, num
             with torch.cuda.stream(side2):      # np.random.seed() per image: sequential, depends on nothing
                 states = F.seed_states((nxt or s)["seeds"])
             with torch.cuda.stream(side):
@@ -394,6 +412,8 @@ def main():
         i += 1
         if i % 256 == 0:
             torch.cuda.synchronize()
+    host_enqueue_us = [0.0]
+
     def timed(n, one_lane=False):
         """ms for n steps: events on the current stream, every lane's stream forked from / joined into it."""
         barrier()
@@ -402,8 +422,10 @@ def main():
         e0.record()
         for ln in lanes:
             ln["main"].wait_stream(cur)
+        th0 = time.perf_counter()
         for i in range(n):
             run(i, one_lane)
+        host_enqueue_us[0] = (time.perf_counter() - th0) * 1e6 / n
         for ln in lanes:
             cur.wait_stream(ln["main"])
         e1.record()
@@ -420,7 +442,7 @@ def main():
 
     # overlapped replays must leave exactly what one-at-a-time replays leave (no scratch shared between lanes)
     overlap_check = None
-    if use_graph and U > 1:
+    if use_graph and U > 1 and len(stages) == 3:
         flat = lambda keep: [t.clone() for t in (keep[0][0], keep[0][1], keep[0][2], *keep[0][3][0], *keep[0][3][1], *keep[0][3][2],
                                                  keep[0][4], keep[0][5], keep[0][6])]
         for i in range(2 * R):
@@ -545,6 +567,7 @@ def main():
                            f"(assignment runs ahead like the reference's DataLoader workers); {U} step graphs in flight "
                            f"(round-robin over {U} streams)"),
                        "steps_in_flight": U, "ms_per_step_one_in_flight": one_lane_ms, "overlap_check": overlap_check,
+                       "host_enqueue_us_per_step": host_enqueue_us[0],
                        "l2": f"{R} rotating input sets, {R * per_set / 1e6:.0f} MB total > L2 ({L2_BYTES / 1e6:.0f} MB)",
                        "parallelism": f"images sharded over {world} rank(s), no data-path collective"},
             "point_gt_pairs_per_s": world * pairs / (stage_us["assign(pairs+resolve)"] * 1e-6),
@@ -675,9 +698,10 @@ def run_e2e(args, wl, B, host_sets, dev, P, F, world):
             sink += float(res["losses"][0]) + float(res["num"][0])
     torch.cuda.synchronize()
     dt = sync_max(time.perf_counter() - t0)
-    out = {"value": world * B * n / dt, "unit": "images/s", "h2d_bytes_per_step": int(pipes[0].h2d_bytes),
+    h2d_mean = float(np.mean([pipes[0].used_bytes(a) for a in arenas]))
+    out = {"value": world * B * n / dt, "unit": "images/s", "h2d_bytes_per_step": int(h2d_mean),
            "d2h_bytes_per_step": int(pipes[0].d2h_bytes), "steps": n, "ms_per_step": 1e3 * dt / n,
-           "h2d_GBps_per_gpu": pipes[0].h2d_bytes * n / dt / 1e9,
+           "h2d_GBps_per_gpu": h2d_mean * n / dt / 1e9,
            "timing": "host wall clock between device synchronisations (max over ranks)",
            "api": "plugin.GraphedHotPath.launch/wait: pinned host arena -> H2D -> CUDA graph (seed | pack+assign+loss fwd/bwd | "
                   f"decode+vote-NMS) -> D2H of losses/detections; {NP} instances in flight; the step is bound by the "

@@ -265,8 +265,33 @@ __device__ __forceinline__ bool iou_gt(const float4& bi, float area_i, const flo
   return __fdiv_rn(inter, __fsub_rn(__fadd_rn(area_j, area_i), inter)) > thr;
 }
 
-// decode one sorted key into box / cluster score / vote score (radet_head.py:123-143, tblr_bbox_coder.py:154-171)
-__device__ __forceinline__ void decode_item(const ClsParams& p, int b, int cls, u64 key, float4& bx, float& cs, float& vs) {
+// The same decision, branch-free, with the division replaced by rcp.approx + one multiply: |q - iou| <= ~2 ulp, so
+// outside the band [lo, hi] = thr * (1 -+ 1e-6) (8 ulp on each side) the quotient is clearly on one side of thr.  Inside
+// the band, for NaN and for a (near-)denormal union the result is flagged ambiguous and the caller falls back to the
+// exact division (iou_gt).  Requires thr > 0; area_j is the precomputed box_area_rn of bj.
+__device__ __forceinline__ bool iou_gt_fast(const float4& bi, float area_i, const float4& bj, float area_j, float lo, float hi,
+                                            bool& ambiguous) {
+  const float xl = fmaxf(bj.x, bi.x), yt = fmaxf(bj.y, bi.y), xr = fminf(bj.z, bi.z), yb = fminf(bj.w, bi.w);
+  const float iw = fmaxf(0.f, __fsub_rn(xr, xl)), ih = fmaxf(0.f, __fsub_rn(yb, yt));
+  const float inter = __fmul_rn(iw, ih);
+  const float uni = __fsub_rn(__fadd_rn(area_j, area_i), inter);
+  float r;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(uni));
+  const float q = __fmul_rn(inter, r);
+  const bool pos = inter != 0.f;                                     // inter == 0: iou is 0 or NaN, never > thr
+  const bool ok = uni > 1e-30f;
+  const bool yes = q > hi && ok, no = q < lo && ok;
+  ambiguous = pos && !yes && !no;
+  return pos && yes;
+}
+
+// decode one key into box / cluster score / vote score (radet_head.py:123-143, tblr_bbox_coder.py:154-171); split
+// into the global loads and the arithmetic so a caller can put independent work between the two
+struct DecodeRaw {
+  float t, b, l, r, cls, iou, H, W, cx, cy, side;
+  float4 sf;
+};
+__device__ __forceinline__ DecodeRaw decode_load(const ClsParams& p, int b, int cls, u64 key) {
   const GridDev& g = p.grid;
   const unsigned ord = 0xffffffffu - (unsigned)(key & 0xffffffffull);
   const int l = (int)(ord >> kOrdLevelShift);
@@ -275,25 +300,41 @@ __device__ __forceinline__ void decode_item(const ClsParams& p, int b, int cls, 
   const int hw = g.h[l] * g.w[l];
   const int y = q / g.w[l], x = q - y * g.w[l];
   const float st = (float)g.stride[l];
-  const float cx = (float)x * st, cy = (float)y * st;
-  const float side = __fmul_rn(g.anchor_scale, st);
+  DecodeRaw d;
+  d.cx = (float)x * st;
+  d.cy = (float)y * st;
+  d.side = __fmul_rn(g.anchor_scale, st);
   const float* bp = p.maps.bbox[l] + (int64_t)b * 4 * hw + q;
-  const float T = __fmul_rn(__fmul_rn(bp[0], g.nrm), side), Bt = __fmul_rn(__fmul_rn(bp[hw], g.nrm), side);
-  const float L = __fmul_rn(__fmul_rn(bp[2 * hw], g.nrm), side), R = __fmul_rn(__fmul_rn(bp[3 * hw], g.nrm), side);
-  const float H = (float)p.img_shapes[2 * b], W = (float)p.img_shapes[2 * b + 1];
-  bx.x = fminf(fmaxf(__fsub_rn(cx, L), 0.f), W);
-  bx.y = fminf(fmaxf(__fsub_rn(cy, T), 0.f), H);
-  bx.z = fminf(fmaxf(__fadd_rn(cx, R), 0.f), W);
-  bx.w = fminf(fmaxf(__fadd_rn(cy, Bt), 0.f), H);
+  d.t = bp[0];
+  d.b = bp[hw];
+  d.l = bp[2 * hw];
+  d.r = bp[3 * hw];
+  d.cls = p.maps.cls[l][((int64_t)b * p.C + cls) * hw + q];
+  d.iou = p.maps.iou[l][(int64_t)b * hw + q];
+  d.H = (float)p.img_shapes[2 * b];
+  d.W = (float)p.img_shapes[2 * b + 1];
+  d.sf = p.rescale ? *reinterpret_cast<const float4*>(p.scale_factors + 4 * b) : make_float4(1.f, 1.f, 1.f, 1.f);
+  return d;
+}
+__device__ __forceinline__ void decode_finish(const ClsParams& p, const DecodeRaw& d, float4& bx, float& cs, float& vs) {
+  const float nrm = p.grid.nrm;
+  const float T = __fmul_rn(__fmul_rn(d.t, nrm), d.side), Bt = __fmul_rn(__fmul_rn(d.b, nrm), d.side);
+  const float L = __fmul_rn(__fmul_rn(d.l, nrm), d.side), R = __fmul_rn(__fmul_rn(d.r, nrm), d.side);
+  bx.x = fminf(fmaxf(__fsub_rn(d.cx, L), 0.f), d.W);
+  bx.y = fminf(fmaxf(__fsub_rn(d.cy, T), 0.f), d.H);
+  bx.z = fminf(fmaxf(__fadd_rn(d.cx, R), 0.f), d.W);
+  bx.w = fminf(fmaxf(__fadd_rn(d.cy, Bt), 0.f), d.H);
   if (p.rescale) {                                                    // radet_head.py:141-143
-    const float4 sf = *reinterpret_cast<const float4*>(p.scale_factors + 4 * b);
-    bx.x = __fdiv_rn(bx.x, sf.x); bx.y = __fdiv_rn(bx.y, sf.y);
-    bx.z = __fdiv_rn(bx.z, sf.z); bx.w = __fdiv_rn(bx.w, sf.w);
+    bx.x = __fdiv_rn(bx.x, d.sf.x); bx.y = __fdiv_rn(bx.y, d.sf.y);
+    bx.z = __fdiv_rn(bx.z, d.sf.z); bx.w = __fdiv_rn(bx.w, d.sf.w);
   }
-  const float S = sigmoid_rn(p.maps.cls[l][((int64_t)b * p.C + cls) * hw + q]);
-  const float ctr = sigmoid_rn(p.maps.iou[l][(int64_t)b * hw + q]);
+  const float S = sigmoid_rn(d.cls);
+  const float ctr = sigmoid_rn(d.iou);
   cs = p.cs_mode == 0 ? __fmul_rn(S, ctr) : (p.cs_mode == 1 ? S : ctr);
   vs = p.vs_mode == 0 ? __fmul_rn(S, ctr) : (p.vs_mode == 1 ? S : ctr);
+}
+__device__ __forceinline__ void decode_item(const ClsParams& p, int b, int cls, u64 key, float4& bx, float& cs, float& vs) {
+  decode_finish(p, decode_load(p, b, cls, key), bx, cs, vs);
 }
 
 // vote_single_dim (vote_ext.cpp:8-35) over a member list given as "seed + set bits of `mem` words" (ascending index =
@@ -357,7 +398,7 @@ __device__ float vote_axis_members(const unsigned* words, int nw, int seed, GetS
   return __fdiv_rn(fx, fs);
 }
 
-__global__ void __launch_bounds__(kClsThreads)
+__global__ void __launch_bounds__(kClsThreads, 3)
 class_nms_kernel(ClsParams p) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   __shared__ int s_nseed, s_base;
@@ -377,43 +418,40 @@ class_nms_kernel(ClsParams p) {
     float* cs = vs + kMaskItems;                                                    // [512]
     unsigned* mask = reinterpret_cast<unsigned*>(cs + kMaskItems);                  // [512][W]
     short* seeds = reinterpret_cast<short*>(mask + kMaskItems * kMaskWords);        // [512]
-    int npad = 32;
-    while (npad < m) npad <<= 1;
+    float* area = reinterpret_cast<float*>(seeds + kMaskItems) + 2 * kMaskWords;    // [512] (after nzrow, seedbits)
     const int W = (m + 31) >> 5;
-    for (int i = tid; i < npad; i += kClsThreads) keys[i] = i < m ? gkeys[i] : 0ull;
+    // One thread per item (m <= 512 = kClsThreads).  Sort by counting: rank_i = #{j : key_j > key_i} (keys are unique),
+    // m broadcast reads of shared memory per thread, no barriers inside.  The item's global loads (4 regression planes,
+    // class and IoU logits) are issued first and land while the rank loop runs.
+    u64* ukeys = reinterpret_cast<u64*>(mask);                     // unsorted keys; the mask area is free until later
+    u64 mykey = 0ull;
+    DecodeRaw raw;
+    if (tid < m) {
+      mykey = gkeys[tid];
+      ukeys[tid] = mykey;
+      raw = decode_load(p, b, c, mykey);
+    }
+    if (tid == m && (m & 1)) ukeys[m] = 0ull;                      // pad to an even count for the 128-bit reads
     __syncthreads();
     RADET_DBG(1);
-    {
-      // bitonic sort by the first npad/2 threads only, synchronised on a named barrier of just those warps
-      const int nsort = max(32, npad >> 1);
-      if (tid < nsort) {
-        for (int k = 2; k <= npad; k <<= 1) {
-          for (int j = k >> 1; j > 0; j >>= 1) {
-            if (tid < (npad >> 1)) {
-              const int i = ((tid & ~(j - 1)) << 1) | (tid & (j - 1));
-              const int ixj = i | j;
-              const bool desc = (i & k) == 0;
-              const u64 a = keys[i], b2 = keys[ixj];
-              if ((a < b2) == desc) {
-                keys[i] = b2;
-                keys[ixj] = a;
-              }
-            }
-            if (nsort > 32) asm volatile("bar.sync 2, %0;" ::"r"(nsort) : "memory");
-            else __syncwarp();
-          }
-        }
+    if (tid < m) {
+      int rank = 0;
+      const ulonglong2* uk2 = reinterpret_cast<const ulonglong2*>(ukeys);
+      const int n2 = (m + 1) >> 1;
+#pragma unroll 4
+      for (int j = 0; j < n2; ++j) {
+        const ulonglong2 k2 = uk2[j];
+        rank += (k2.x > mykey ? 1 : 0) + (k2.y > mykey ? 1 : 0);
       }
-      __syncthreads();
-    }
-    RADET_DBG(2);
-    for (int i = tid; i < m; i += kClsThreads) {
+      RADET_DBG(2);
       float4 bx;
       float c_, v_;
-      decode_item(p, b, c, keys[i], bx, c_, v_);
-      box[i] = bx;
-      cs[i] = c_;
-      vs[i] = v_;
+      decode_finish(p, raw, bx, c_, v_);
+      keys[rank] = mykey;
+      box[rank] = bx;
+      area[rank] = box_area_rn(bx);
+      cs[rank] = c_;
+      vs[rank] = v_;
     }
     __syncthreads();
     RADET_DBG(3);
@@ -423,20 +461,52 @@ class_nms_kernel(ClsParams p) {
     unsigned* seedbits = nzrow + kMaskWords;                                        // [W]
     if (tid < kMaskWords) nzrow[tid] = 0u;
     __syncthreads();
-    for (int i = wid; i < m; i += kClsThreads / 32) {
-      const float4 bi = box[i];
-      const float area_i = box_area_rn(bi);
-      unsigned any = 0u;
-      if (lane < (i >> 5)) mask[i * W + lane] = 0u;                 // words below the diagonal
-#pragma unroll 4
-      for (int wj = i >> 5; wj < W; ++wj) {
-        const int j = wj * 32 + lane;
-        const bool hit = (j > i && j < m) && iou_gt(bi, area_i, box[j], p.thr);     // vote_ext.cpp:169
-        const unsigned word = __ballot_sync(kFull, hit);
-        if (lane == 0) mask[i * W + wj] = word;
-        any |= word;
+    // Two adjacent rows per warp trip (iA, iA + 1 share the column loads and the diagonal word); lanes = columns.
+    constexpr int kNW = kClsThreads / 32;
+    const bool fast_ok = p.thr >= 1e-30f;                           // rcp-filtered decision (iou_gt_fast) needs thr > 0
+    const float thr_lo = p.thr * (1.f - 1e-6f), thr_hi = p.thr * (1.f + 1e-6f);
+    for (int iA = 2 * wid; iA < m; iA += 2 * kNW) {
+      const int iB = iA + 1;
+      const bool hasB = iB < m;
+      const float4 bA = box[iA], bB = box[hasB ? iB : iA];
+      const float areaA = area[iA], areaB = area[hasB ? iB : iA];
+      unsigned anyA = 0u, anyB = 0u;
+      const int w0 = iA >> 5;                                       // == iB >> 5 (iA is even)
+      if (lane < w0) {                                              // words below the diagonal
+        mask[iA * W + lane] = 0u;
+        if (hasB) mask[iB * W + lane] = 0u;
       }
-      if (lane == 0 && any) atomicOr(&nzrow[i >> 5], 1u << (i & 31));
+#pragma unroll 2
+      for (int wj = w0; wj < W; ++wj) {
+        const int j = wj * 32 + lane;
+        const bool in = j < m;
+        const float4 bj = box[in ? j : 0];
+        const float aj = area[in ? j : 0];
+        bool hitA, hitB;
+        if (fast_ok) {                                              // warp-uniform
+          bool ambA, ambB;
+          hitA = iou_gt_fast(bA, areaA, bj, aj, thr_lo, thr_hi, ambA);                     // vote_ext.cpp:169
+          hitB = iou_gt_fast(bB, areaB, bj, aj, thr_lo, thr_hi, ambB);
+          if (__any_sync(kFull, ambA || ambB)) {                    // a quotient within 8 ulp of thr: exact division
+            if (ambA) hitA = iou_gt(bA, areaA, bj, p.thr);
+            if (ambB) hitB = iou_gt(bB, areaB, bj, p.thr);
+          }
+          hitA = hitA && in && j > iA;
+          hitB = hitB && in && hasB && j > iB;
+        } else {
+          hitA = in && j > iA && iou_gt(bA, areaA, bj, p.thr);
+          hitB = in && hasB && j > iB && iou_gt(bB, areaB, bj, p.thr);
+        }
+        const unsigned wordA = __ballot_sync(kFull, hitA), wordB = __ballot_sync(kFull, hitB);
+        if (lane == 0) {
+          mask[iA * W + wj] = wordA;
+          if (hasB) mask[iB * W + wj] = wordB;
+        }
+        anyA |= wordA;
+        anyB |= wordB;
+      }
+      if (lane == 0 && anyA) atomicOr(&nzrow[iA >> 5], 1u << (iA & 31));
+      if (lane == 0 && anyB) atomicOr(&nzrow[iB >> 5], 1u << (iB & 31));
     }
     __syncthreads();
     RADET_DBG(4);
@@ -908,7 +978,7 @@ extern "C" int radet_get_bboxes(const radet_grid_t* grid, int32_t batch, int32_t
   cp.g_box = w.g_box;
   cp.g_vs = w.g_vs;
   cp.g_owner = w.g_owner;
-  const size_t cls_smem = (size_t)kMaskItems * (8 + 16 + 4 + 4 + kMaskWords * 4 + 2) + 2 * kMaskWords * 4;
+  const size_t cls_smem = (size_t)kMaskItems * (8 + 16 + 4 + 4 + kMaskWords * 4 + 2 + 4) + 2 * kMaskWords * 4;
   cudaFuncSetAttribute(class_nms_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cls_smem);
   cudaFuncSetAttribute(class_nms_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
   class_nms_kernel<<<dim3(num_classes, batch), kClsThreads, cls_smem, st>>>(cp);

@@ -615,33 +615,29 @@ static int dense_plan(const GridDev& g, int B, int C, DenseTable* tab, int* cc, 
   }
   for (int l = g.num_levels; l <= RADET_MAX_LEVELS; ++l) tab->uoff[l] = (int)u;
   for (int l = g.num_levels; l < RADET_MAX_LEVELS; ++l) tab->upl[l] = 1;
-  // Work items = units x channel chunks.  The grid is always a multiple of the SM count and the items are cut into
-  // equal slices, so there is no partially filled last wave.  One chunk per unit (all C+5 channels in one thread)
-  // amortises the per-point setup best; more chunks are used only to give every resident thread an item when the
-  // units alone cannot (small batches).  Cost model: rounds x (setup + channels).
+  // Work items = units x channel chunks.  When the units alone fill the machine, one chunk per unit (all C+5 channels
+  // in one thread) amortises the per-point setup best and the grid is a multiple of the SM count cut into equal
+  // slices (no partially filled last wave).  Small batches stay at one item per thread in ceil(items / 256) full
+  // CTAs: the kernel is latency-bound there, and the fewest resident CTAs x time leaves the other SMs to whatever
+  // else is in flight (neighbouring steps, the decode branch); the chunk is only split to keep a thread's serial
+  // plane loop at <= kMaxChunk channels.
   const int CH = C + 5;
-  const double resident = (double)kSMs * kDenseOcc * kDenseThreads;
-  const int nmax = (CH + kDG - 1) / kDG;
-  double best = 1e30;
+  constexpr int kMaxChunk = 48;
+  const int64_t resident = (int64_t)kSMs * kDenseOcc * kDenseThreads;
   int best_c = CH;
-  for (int n = 1; n <= nmax; ++n) {
-    int c = (CH + n - 1) / n;
-    c = (c + kDG - 1) / kDG * kDG;                        // whole load groups
-    const int nn = (CH + c - 1) / c;
-    const double rounds = ceil((double)u * nn / resident);
-    const double t = rounds * (3.0 + c);
-    if (t < best - 1e-9) {
-      best = t;
-      best_c = c;
-    }
+  if (u < resident && CH > kMaxChunk) {
+    const int n = (CH + kMaxChunk - 1) / kMaxChunk;
+    best_c = ((CH + n - 1) / n + kDG - 1) / kDG * kDG;
   }
   *cc = best_c;
   *nj = (CH + best_c - 1) / best_c;
   const int64_t items = u * *nj;
-  int64_t m = (items + (int64_t)kSMs * kDenseThreads - 1) / ((int64_t)kSMs * kDenseThreads);   // CTAs per SM needed
-  if (m < 1) m = 1;
-  if (m > kDenseOcc) m = kDenseOcc;
-  *blocks = (int)(kSMs * m);
+  if (items <= resident) {
+    *blocks = (int)((items + kDenseThreads - 1) / kDenseThreads);
+    if (*blocks < 1) *blocks = 1;
+  } else {
+    *blocks = (int)(kSMs * kDenseOcc);
+  }
   return RADET_OK;
 }
 

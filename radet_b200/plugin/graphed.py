@@ -50,10 +50,12 @@ class GraphedHotPath:
         B, cap, C = self.B, self.cap, self.C
         # ---- arena layout (bytes); every field 256-byte aligned
         fields = [("gt_bboxes", (B * cap, 4), np.float32), ("gt_labels", (B * cap,), np.int64), ("gt_offsets", (B + 1,), np.int32),
-                  ("mask_grids", (B * cap, self.gh, self.gw), np.uint8), ("seeds", (B,), np.int32),
-                  ("img_shapes", (B, 2), np.int32), ("scale_factors", (B, 4), np.float32)]
+                  ("seeds", (B,), np.int32), ("img_shapes", (B, 2), np.int32), ("scale_factors", (B, 4), np.float32)]
         for l, (h, w) in enumerate(self.shapes):
             fields += [(f"cls{l}", (B, C, h, w), np.float32), (f"bbox{l}", (B, 4, h, w), np.float32), (f"iou{l}", (B, 1, h, w), np.float32)]
+        # the only field whose used size varies from batch to batch goes last: `launch` copies the arena only up to
+        # the last GT's mask grid (the padding up to max_gt_per_image never crosses the bus)
+        fields += [("mask_grids", (B * cap, self.gh, self.gw), np.uint8)]
         self._layout, off = {}, 0
         for name, shape, dt in fields:
             nbytes = int(np.prod(shape)) * np.dtype(dt).itemsize
@@ -169,14 +171,23 @@ class GraphedHotPath:
         return self
 
     # ------------------------------------------------------------------ run
+    def used_bytes(self, host_arena: torch.Tensor) -> int:
+        """Bytes of the arena that carry data for the batch it holds (everything up to the last GT's mask grid)."""
+        off, shape, _ = self._layout["gt_offsets"]
+        n_gt = int(host_arena[off:off + 4 * (self.B + 1)].view(torch.int32)[self.B])
+        moff = self._layout["mask_grids"][0]
+        return min(self.arena_bytes, _align(moff + n_gt * self.gh * self.gw))
+
     def launch(self, host_arena: torch.Tensor):
-        """Enqueue: H2D of the arena, the graph, D2H of the results.  Returns immediately."""
+        """Enqueue: H2D of the used part of the arena, the graph, D2H of the results.  Returns immediately."""
         if self._graph is None:
             self.capture()
+        n = self.used_bytes(host_arena)
         with torch.cuda.stream(self._stream):
-            self._dev_arena.copy_(host_arena, non_blocking=True)
+            self._dev_arena[:n].copy_(host_arena[:n], non_blocking=True)
             self._graph.replay()
             self._done.record(self._stream)
+        self.last_h2d_bytes = n
 
     def wait(self):
         """Block until the last launch has finished; returns the pinned result block (valid until the next launch)
