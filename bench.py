@@ -529,10 +529,14 @@ def main():
         peaks = json.load(open(pk))
     peak_gbs = float(peaks.get("hbm_gbs", 6650.0))
     peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650 GB/s"
+    traffic = None   # dram bytes per launch of the same kernel from the committed `ncu --set full` capture, if it matches this shape
+    tj = os.path.join(ROOT, "profiles", "r1_traffic.json")
+    if os.path.exists(tj) and wl.name.startswith("cfg2") and B == 8:
+        traffic = json.load(open(tj)).get("loss_dense_kernel@cfg2_B8")
     loss_bytes = B * Ppts * (8 * wl.C + 52)
     ach = loss_bytes / (stage_us["loss_dense_kernel"] * 1e-6) / 1e9
     roofline = {"bound": "hbm", "kernel": "loss_dense_kernel", "achieved": ach, "peak": peak_gbs, "unit": "GB/s", "frac": ach / peak_gbs,
-                "traffic": None, "peak_source": peak_src, "algorithmic_bytes_per_launch": loss_bytes,
+                "traffic": traffic, "peak_source": peak_src, "algorithmic_bytes_per_launch": loss_bytes,
                 "us_per_launch": stage_us["loss_dense_kernel"],
                 "note": f"(8C+52) B/point x {B * Ppts} points; at this batch the launch moves {loss_bytes / 1e6:.1f} MB "
                         "(latency-bound regime, SURVEY 8d); see roofline_large for the bandwidth-bound regime"}
