@@ -24,14 +24,24 @@ namespace radet {
 __global__ void pack_masks_kernel(const uint8_t* __restrict__ src, int64_t num_gt, int src_h, int src_w, int step,
                                   int grid_h, int grid_w, int pitch, uint32_t* __restrict__ bits,
                                   int* __restrict__ status) {
-  // one warp per output word: lane i tests sample gx = word*32 + i
+  // one warp per output word: lane i tests sample gx = word*32 + i (general form: any step, any source size)
   const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   const int64_t total = num_gt * grid_h * pitch;
   if (warp >= total) return;
-  const int wx = (int)(warp % pitch);
-  const int gy = (int)((warp / pitch) % grid_h);
-  const int64_t g = warp / ((int64_t)pitch * grid_h);
+  int wx, gy;
+  int64_t g;
+  if (total < (1ll << 31)) {                                         // 32-bit index arithmetic (the usual case)
+    const unsigned w32 = (unsigned)warp, row = w32 / (unsigned)pitch;
+    wx = (int)(w32 - row * (unsigned)pitch);
+    const unsigned gg = row / (unsigned)grid_h;
+    gy = (int)(row - gg * (unsigned)grid_h);
+    g = gg;
+  } else {
+    wx = (int)(warp % pitch);
+    gy = (int)((warp / pitch) % grid_h);
+    g = warp / ((int64_t)pitch * grid_h);
+  }
   const int gx = wx * 32 + lane;
   int v = 0;
   if (gx < grid_w) {
@@ -45,6 +55,35 @@ __global__ void pack_masks_kernel(const uint8_t* __restrict__ src, int64_t num_g
   if (lane == 0) {
     bits[warp] = word;
     if (status && word && vmin != vmax) atomicOr(status, 1);
+  }
+}
+
+// Pre-sampled grids (step 1, source = grid, width a multiple of 4): one THREAD per output word, eight 32-bit loads,
+// byte-wise SIMD compares.  ~45 instructions per 32 samples instead of a warp's worth.
+__global__ void pack_grid_kernel(const uint32_t* __restrict__ src4, unsigned total, int grid_h, int grid_w, int pitch,
+                                 uint32_t* __restrict__ bits, int* __restrict__ status) {
+  const unsigned t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= total) return;
+  const unsigned row = t / (unsigned)pitch, wx = t - row * (unsigned)pitch;   // row = g * grid_h + gy
+  const int n4 = min(8, (grid_w - (int)wx * 32) >> 2);                       // 32-bit groups of this word
+  const uint32_t* p = src4 + ((size_t)row * grid_w >> 2) + wx * 8;
+  uint32_t v[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) v[k] = k < n4 ? p[k] : 0u;
+  uint32_t word = 0u, mx = 0u, mn = 0xffffffffu;
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    const uint32_t nz = __vcmpne4(v[k], 0u);                                  // 0xff per non-zero byte
+    const uint32_t x = nz & 0x01010101u;
+    word |= ((x | (x >> 7) | (x >> 14) | (x >> 21)) & 0xfu) << (4 * k);
+    mx = __vmaxu4(mx, v[k]);
+    mn = __vminu4(mn, v[k] | ~nz);                                            // zero bytes count as 255
+  }
+  bits[t] = word;
+  if (status && word) {                                                       // same per-word binary-mask check
+    const uint32_t hi = max(max(mx & 0xffu, (mx >> 8) & 0xffu), max((mx >> 16) & 0xffu, mx >> 24));
+    const uint32_t lo = min(min(mn & 0xffu, (mn >> 8) & 0xffu), min((mn >> 16) & 0xffu, mn >> 24));
+    if (lo != hi) atomicOr(status, 1);
   }
 }
 
@@ -753,6 +792,13 @@ extern "C" int radet_pack_masks(const uint8_t* src, int64_t num_gt, int32_t src_
   const int pitch = (grid_w + 31) / 32;
   const int64_t warps = num_gt * grid_h * pitch;
   const int threads = 256;
+  if (step == 1 && src_h == grid_h && src_w == grid_w && (grid_w & 3) == 0 && warps < (1ll << 31) &&
+      (reinterpret_cast<uintptr_t>(src) & 3) == 0) {
+    pack_grid_kernel<<<(unsigned)((warps + threads - 1) / threads), threads, 0, (cudaStream_t)stream>>>(
+        reinterpret_cast<const uint32_t*>(src), (unsigned)warps, grid_h, grid_w, pitch, bits, status);
+    RADET_LAUNCH_CHECK();
+    return RADET_OK;
+  }
   const int64_t blocks = (warps * 32 + threads - 1) / threads;
   pack_masks_kernel<<<(unsigned)blocks, threads, 0, (cudaStream_t)stream>>>(src, num_gt, src_h, src_w, step, grid_h, grid_w,
                                                                            pitch, bits, status);

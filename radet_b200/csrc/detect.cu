@@ -54,14 +54,14 @@ struct SelPlan {
 __global__ void __launch_bounds__(kSelThreads)
 detect_select_kernel(GridDev grid, SelPlan plan, int C, MapsDev maps, float thr, float x_lo, u64* __restrict__ cand,
                      int* __restrict__ counts) {
-  __shared__ u64 s_keys[kSelThreads * 4 * kSelChunk];
-  __shared__ int s_cnt, s_base;
-  const int b = blockIdx.y, j = blockIdx.z;
+  __shared__ u64 s_buf[kSelThreads * 4 * kSelChunk];   // staged (logit, flat) entries, overwritten in place by the keys
+  __shared__ int s_cnt, s_keep, s_base;
+  const int b = blockIdx.y, j = blockIdx.z, tid = threadIdx.x, lane = tid & 31;
   int l = 0;
 #pragma unroll
   for (int k = 1; k < RADET_MAX_LEVELS; ++k) l += (k < grid.num_levels && (int)blockIdx.x >= plan.boff[k]) ? 1 : 0;
   const int hw = grid.h[l] * grid.w[l];
-  const int q0 = 4 * (((int)blockIdx.x - plan.boff[l]) * kSelThreads + (int)threadIdx.x);
+  const int q0 = 4 * (((int)blockIdx.x - plan.boff[l]) * kSelThreads + tid);
   const int nv = min(4, hw - q0);  // <= 0: idle thread
   const bool vec = (hw & 3) == 0;
   const float* cp = maps.cls[l] + ((int64_t)b * C) * hw + q0;
@@ -69,7 +69,10 @@ detect_select_kernel(GridDev grid, SelPlan plan, int C, MapsDev maps, float thr,
   int* cnt = counts + b * RADET_MAX_LEVELS + l;
   const int c0 = j * plan.cc, c1 = min(C, c0 + plan.cc);
   for (int cb = c0; cb < c1; cb += kSelChunk) {
-    if (threadIdx.x == 0) s_cnt = 0;
+    if (tid == 0) {
+      s_cnt = 0;
+      s_keep = 0;
+    }
     __syncthreads();
     const int ce = min(c1, cb + kSelChunk);
     float xv[kSelChunk][4];
@@ -85,24 +88,43 @@ detect_select_kernel(GridDev grid, SelPlan plan, int C, MapsDev maps, float thr,
         }
       }
     }
+    // A. conservative prefilter on the raw logit: the few survivors are staged so that the sigmoid below runs on
+    //    dense warps instead of inside a branch that one lane in 32 takes
 #pragma unroll
     for (int k = 0; k < kSelChunk; ++k) {
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
-        if (i < nv && xv[k][i] > x_lo) {            // conservative prefilter on the logit
-          const float s = sigmoid_rn(xv[k][i]);
-          if (s > thr) {                            // radet_head.py:111 (strict)
-            const unsigned flat = (unsigned)(q0 + i) * (unsigned)C + (unsigned)(cb + k);
-            s_keys[atomicAdd(&s_cnt, 1)] = ((u64)__float_as_uint(s) << 32) | (u64)(0xffffffffu - flat);
-          }
+        if (i < nv && xv[k][i] > x_lo) {
+          const unsigned flat = (unsigned)(q0 + i) * (unsigned)C + (unsigned)(cb + k);
+          s_buf[atomicAdd(&s_cnt, 1)] = ((u64)__float_as_uint(xv[k][i]) << 32) | (u64)flat;
         }
       }
     }
     __syncthreads();
     const int n = s_cnt;
-    if (threadIdx.x == 0 && n) s_base = atomicAdd(cnt, n);
+    // B. exact test on the staged entries; kept keys are compacted in place (a tile's writes land below its reads)
+    for (int base = 0; base < n; base += kSelThreads) {
+      const int i = base + tid;
+      bool keep = false;
+      u64 key = 0ull;
+      if (i < n) {
+        const u64 e = s_buf[i];
+        const float sc = sigmoid_rn(__uint_as_float((unsigned)(e >> 32)));
+        keep = sc > thr;                              // radet_head.py:111 (strict)
+        key = ((u64)__float_as_uint(sc) << 32) | (u64)(0xffffffffu - (unsigned)(e & 0xffffffffull));
+      }
+      const unsigned bal = __ballot_sync(kFull, keep);
+      int wbase = 0;
+      if (lane == 0 && bal) wbase = atomicAdd(&s_keep, __popc(bal));
+      wbase = __shfl_sync(kFull, wbase, 0);
+      __syncthreads();
+      if (keep) s_buf[wbase + __popc(bal & ((1u << lane) - 1u))] = key;
+    }
     __syncthreads();
-    for (int i = threadIdx.x; i < n; i += kSelThreads) out[s_base + i] = s_keys[i];
+    const int nk = s_keep;
+    if (tid == 0 && nk) s_base = atomicAdd(cnt, nk);
+    __syncthreads();
+    for (int i = tid; i < nk; i += kSelThreads) out[s_base + i] = s_buf[i];
     __syncthreads();
   }
 }
