@@ -184,6 +184,23 @@ int radet_tblr_decode(const float* priors, const float* tblr, int64_t n, float n
                       float max_w, float* out, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
+ * Standalone element-wise losses (the LOSSES registry entries called outside the fused head).  Each call writes the
+ * un-reduced, un-weighted loss and, when dloss_dpred != NULL, its derivative w.r.t. pred in the same launch; weighting
+ * and reduction (losses/utils.py:26-52 weight_reduce_loss) stay with the caller.
+ *   radet_sigmoid_focal_loss  FocalLoss -> sigmoid_focal_loss (models/losses/focal_loss.py:44-87): mmcv.ops
+ *       sigmoid_focal_loss(pred [n,C], target int64 [n], gamma, alpha, None, 'none'); a target outside [0,C) is an
+ *       all-negative row.  loss / dloss_dpred: [n,C].
+ *   radet_giou_loss           GIoULoss -> giou_loss (models/losses/iou_loss.py:82-98): 1 - bbox_overlaps(pred, target,
+ *       mode='giou', is_aligned=True, eps) on (x1,y1,x2,y2) rows.  loss [n], dloss_dpred [n,4].
+ *   radet_bce_with_logits     CrossEntropyLoss(use_sigmoid=True) -> binary_cross_entropy
+ *       (models/losses/cross_entropy_loss.py:58-91) with pred.dim() == label.dim():
+ *       F.binary_cross_entropy_with_logits(pred, label.float(), reduction='none').  loss / dloss_dpred: [n]. */
+int radet_sigmoid_focal_loss(const float* pred, const int64_t* target, int64_t n, int32_t num_classes, float gamma, float alpha,
+                             float* loss, float* dloss_dpred, void* stream);
+int radet_giou_loss(const float* pred, const float* target, int64_t n, float eps, float* loss, float* dloss_dpred, void* stream);
+int radet_bce_with_logits(const float* pred, const float* target, int64_t n, float* loss, float* dloss_dpred, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
  * Vote-NMS family on explicit box lists.  Replaces the pybind modules
  *   vote_ext.vote_nms / vote_ext.global_vote_nms (ops/vote/vote_ext.cpp:70-207, 210-353, 358-361) and
  *   cluster_ext.cluster_nms (ops/cluster/cluster_ext.cpp:4-87, 90-92),

@@ -333,6 +333,74 @@ def head_loss(cls_maps, bbox_maps, iou_maps, gt_bboxes_list, gt_labels_list, idx
     return out
 
 
+# --------------------------------------------------------------------------- standalone LOSSES modules
+def weight_reduce(loss, weight=None, reduction="mean", avg_factor=None):
+    """losses/utils.py:26-52."""
+    if weight is not None:
+        loss = loss * weight
+    if avg_factor is None:
+        return loss.mean() if reduction == "mean" else loss.sum() if reduction == "sum" else loss
+    if reduction == "mean":
+        return loss.sum() / avg_factor
+    if reduction != "none":
+        raise ValueError('avg_factor can not be used with reduction="sum"')
+    return loss
+
+
+def standalone_loss(kind, pred, target, weight=None, reduction="mean", avg_factor=None, loss_weight=1.0, gamma=2.0, alpha=0.25,
+                    eps=1e-6, dtype="float64"):
+    """FocalLoss (focal_loss.py:10-41 py version + :72-86 weight reshape), GIoULoss (iou_loss.py:82-98, 327-354) and
+    CrossEntropyLoss(use_sigmoid=True) (cross_entropy_loss.py:40-91) called on their own.  numpy in, (loss, grad of
+    loss.sum() w.r.t. pred) out; evaluated in `dtype` (float64 gives the tolerance-free reference value)."""
+    import torch
+    import torch.nn.functional as F
+
+    td = getattr(torch, dtype)
+    x = torch.tensor(np.asarray(pred), dtype=td, requires_grad=True)
+    w = None if weight is None else torch.tensor(np.asarray(weight), dtype=td)
+    if kind == "focal":
+        C = x.shape[1]
+        onehot = F.one_hot(torch.from_numpy(np.asarray(target, np.int64)), C + 1)[:, :C].to(td)
+        ps = x.sigmoid()
+        pt = (1 - ps) * onehot + ps * (1 - onehot)
+        loss = F.binary_cross_entropy_with_logits(x, onehot, reduction="none") * (alpha * onehot + (1 - alpha) * (1 - onehot)) * pt.pow(gamma)
+        if w is not None and w.shape != loss.shape:
+            w = w.view(-1, 1) if w.shape[0] == loss.shape[0] else w.view(loss.shape[0], -1)
+    elif kind == "giou":
+        t = torch.tensor(np.asarray(target), dtype=td)
+        if w is not None and not bool((w > 0).any()):
+            out = (x * w).sum()
+            out.backward()
+            return out.detach().numpy(), x.grad.numpy()
+        if w is not None and w.dim() > 1:
+            w = w.mean(-1)
+        a1 = (x[:, 2] - x[:, 0]) * (x[:, 3] - x[:, 1])
+        a2 = (t[:, 2] - t[:, 0]) * (t[:, 3] - t[:, 1])
+        wh = (torch.min(x[:, 2:], t[:, 2:]) - torch.max(x[:, :2], t[:, :2])).clamp(min=0)
+        ov = wh[:, 0] * wh[:, 1]
+        e = a1.new_tensor([eps])
+        union = torch.max(a1 + a2 - ov, e)
+        ewh = (torch.max(x[:, 2:], t[:, 2:]) - torch.min(x[:, :2], t[:, :2])).clamp(min=0)
+        ea = torch.max(ewh[:, 0] * ewh[:, 1], e)
+        loss = 1 - (ov / union - (ea - union) / ea)
+    elif kind == "bce":
+        t = torch.from_numpy(np.asarray(target))
+        if x.dim() != t.dim():
+            C = x.shape[-1]
+            onehot = torch.zeros((t.shape[0], C), dtype=td)
+            rows = ((t >= 0) & (t < C)).nonzero().reshape(-1)
+            onehot[rows, t[rows]] = 1
+            t = onehot
+            if w is not None:
+                w = w.view(-1, 1).expand(w.shape[0], C)
+        loss = F.binary_cross_entropy_with_logits(x, t.to(td), reduction="none")
+    else:
+        raise ValueError(kind)
+    out = loss_weight * weight_reduce(loss, w, reduction, avg_factor)
+    out.sum().backward()
+    return out.detach().numpy(), x.grad.numpy()
+
+
 # --------------------------------------------------------------------------- decode + candidate selection
 def _sigmoid_f32(x):
     """``Tensor.sigmoid()`` of radet_head.py:106-109.

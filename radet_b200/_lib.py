@@ -61,6 +61,9 @@ _SIGS = {
     "radet_scale_grads": (c_int32, [POINTER(Grid), c_int32, c_int32, POINTER(Maps), c_void_p, c_void_p]),
     "radet_tblr_encode": (c_int32, [c_void_p, c_void_p, c_int64, c_float, c_void_p, c_void_p]),
     "radet_tblr_decode": (c_int32, [c_void_p, c_void_p, c_int64, c_float, c_int32, c_float, c_float, c_void_p, c_void_p]),
+    "radet_sigmoid_focal_loss": (c_int32, [c_void_p, c_void_p, c_int64, c_int32, c_float, c_float, c_void_p, c_void_p, c_void_p]),
+    "radet_giou_loss": (c_int32, [c_void_p, c_void_p, c_int64, c_float, c_void_p, c_void_p, c_void_p]),
+    "radet_bce_with_logits": (c_int32, [c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_void_p]),
     "radet_vote_nms_workspace_bytes": (c_size_t, [c_int32, c_int64, c_int64]),
     "radet_vote_nms": (c_int32, [c_int32, POINTER(c_int32), c_void_p, c_void_p, c_void_p, c_void_p, c_float, c_int32, c_float,
                                  c_int32, c_int32, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,

@@ -578,6 +578,56 @@ __global__ void tblr_decode_kernel(const float4* __restrict__ priors, const floa
   out[i] = o;
 }
 
+// ------------------------------------------------------------------------------------------------ standalone losses
+// mmcv 1.3.x sigmoid_focal_loss forward / backward arithmetic (source not in the reference tree):
+//   p = 1/(1+exp(-x));  target class: -alpha (1-p)^g log(max(p,FLT_MIN));  other: -(1-alpha) p^g log(max(1-p,FLT_MIN))
+__global__ void focal_loss_kernel(const float* __restrict__ pred, const int64_t* __restrict__ target, int64_t total, int C,
+                                  float gamma, float alpha, float* __restrict__ loss, float* __restrict__ dpred) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const int64_t n = i / C;
+  const int c = (int)(i - n * C);
+  const float x = pred[i];
+  const bool is_t = target[n] == (int64_t)c;
+  const float p = 1.f / (1.f + expf(-x));
+  const float kMin = 1.17549435e-38f;
+  if (is_t) {
+    const float lg = logf(fmaxf(p, kMin)), m = powf(1.f - p, gamma);
+    if (loss) loss[i] = -alpha * m * lg;
+    if (dpred) dpred[i] = -alpha * m * (1.f - p - gamma * p * lg);
+  } else {
+    const float lg = logf(fmaxf(1.f - p, kMin)), m = powf(p, gamma);
+    if (loss) loss[i] = -(1.f - alpha) * m * lg;
+    if (dpred) dpred[i] = -(1.f - alpha) * m * (gamma * (1.f - p) * lg - p);
+  }
+}
+
+__global__ void giou_loss_kernel(const float4* __restrict__ pred, const float4* __restrict__ target, int64_t n, float eps,
+                                 float* __restrict__ loss, float4* __restrict__ dpred) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float4 p = pred[i], t = target[i];
+  // box_terms takes (centre, T, B, L, R): with centre 0 and scale 1, x1 = -L, y1 = -T, x2 = R, y2 = B (negation is exact)
+  if (dpred) {
+    const BoxTerms bt = box_terms<true>(0.f, 0.f, 1.f, -p.y, p.w, -p.x, p.z, -t.y, t.w, -t.x, t.z, eps, eps);
+    loss[i] = 1.f - bt.giou;
+    // d(1-giou)/d(x1,y1,x2,y2) from d giou / d(T,B,L,R)
+    dpred[i] = make_float4(bt.d[2], bt.d[0], -bt.d[3], -bt.d[1]);
+  } else {
+    const BoxTerms bt = box_terms<false>(0.f, 0.f, 1.f, -p.y, p.w, -p.x, p.z, -t.y, t.w, -t.x, t.z, eps, eps);
+    loss[i] = 1.f - bt.giou;
+  }
+}
+
+__global__ void bce_logits_kernel(const float* __restrict__ pred, const float* __restrict__ target, int64_t n,
+                                  float* __restrict__ loss, float* __restrict__ dpred) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float x = pred[i], z = target[i];
+  if (loss) loss[i] = bce_logits(x, z);
+  if (dpred) dpred[i] = sigmoidf_(x) - z;
+}
+
 }  // namespace radet
 
 // ================================================================================================ C ABI
@@ -758,6 +808,39 @@ extern "C" int radet_tblr_decode(const float* priors, const float* tblr, int64_t
   tblr_decode_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
       reinterpret_cast<const float4*>(priors), reinterpret_cast<const float4*>(tblr), n, normalizer, clip, max_h, max_w,
       reinterpret_cast<float4*>(out));
+  RADET_LAUNCH_CHECK();
+  return RADET_OK;
+}
+
+extern "C" int radet_sigmoid_focal_loss(const float* pred, const int64_t* target, int64_t n, int32_t num_classes, float gamma,
+                                        float alpha, float* loss, float* dloss_dpred, void* stream) {
+  if (n == 0) return RADET_OK;
+  if (n < 0 || num_classes <= 0 || !pred || !target || (!loss && !dloss_dpred)) return RADET_E_BADARG;
+  const int64_t total = n * num_classes;
+  focal_loss_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(pred, target, total, num_classes, gamma, alpha,
+                                                                                      loss, dloss_dpred);
+  RADET_LAUNCH_CHECK();
+  return RADET_OK;
+}
+
+extern "C" int radet_giou_loss(const float* pred, const float* target, int64_t n, float eps, float* loss, float* dloss_dpred,
+                               void* stream) {
+  if (n == 0) return RADET_OK;
+  if (n < 0 || !pred || !target || !loss) return RADET_E_BADARG;
+  if ((reinterpret_cast<uintptr_t>(pred) | reinterpret_cast<uintptr_t>(target) | reinterpret_cast<uintptr_t>(dloss_dpred)) & 15)
+    return RADET_E_BADARG;
+  giou_loss_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+      reinterpret_cast<const float4*>(pred), reinterpret_cast<const float4*>(target), n, eps, loss,
+      reinterpret_cast<float4*>(dloss_dpred));
+  RADET_LAUNCH_CHECK();
+  return RADET_OK;
+}
+
+extern "C" int radet_bce_with_logits(const float* pred, const float* target, int64_t n, float* loss, float* dloss_dpred,
+                                     void* stream) {
+  if (n == 0) return RADET_OK;
+  if (n < 0 || !pred || !target || (!loss && !dloss_dpred)) return RADET_E_BADARG;
+  bce_logits_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(pred, target, n, loss, dloss_dpred);
   RADET_LAUNCH_CHECK();
   return RADET_OK;
 }

@@ -311,6 +311,65 @@ def tblr_decode(priors: torch.Tensor, tblr: torch.Tensor, normalizer: float, max
     return out
 
 
+# ------------------------------------------------------------------------------------------------ standalone losses
+class _ElementwiseLoss(torch.autograd.Function):
+    """loss = kernel(pred, target) element-wise; the same launch writes d loss / d pred, backward is one multiply."""
+
+    @staticmethod
+    def forward(ctx, pred, target, kind, a, b):
+        _require_cuda(pred, "pred")
+        p = pred.detach().contiguous().float()
+        lib = _lib.load()
+        want = pred.requires_grad
+        if kind == "focal":
+            t = target.detach().contiguous().to(torch.int64)
+            loss = torch.empty_like(p)
+            d = torch.empty_like(p) if want else None
+            check(lib.radet_sigmoid_focal_loss(_ptr(p), _ptr(t), p.shape[0], p.shape[1], float(a), float(b), _ptr(loss), _ptr(d),
+                                               _stream()), "radet_sigmoid_focal_loss")
+        elif kind == "giou":
+            t = target.detach().contiguous().float()
+            loss = torch.empty(p.shape[0], dtype=torch.float32, device=p.device)
+            d = torch.empty_like(p) if want else None
+            check(lib.radet_giou_loss(_ptr(p), _ptr(t), p.shape[0], float(a), _ptr(loss), _ptr(d), _stream()), "radet_giou_loss")
+        else:
+            t = target.detach().contiguous().float()
+            loss = torch.empty_like(p)
+            d = torch.empty_like(p) if want else None
+            check(lib.radet_bce_with_logits(_ptr(p), _ptr(t), p.numel(), _ptr(loss), _ptr(d), _stream()), "radet_bce_with_logits")
+        ctx.save_for_backward(d)
+        ctx.kind = kind
+        return loss
+
+    @staticmethod
+    def backward(ctx, g):
+        (d,) = ctx.saved_tensors
+        if ctx.kind == "giou":
+            g = g.unsqueeze(-1)
+        return g * d, None, None, None, None
+
+
+def sigmoid_focal_loss_elementwise(pred: torch.Tensor, target: torch.Tensor, gamma: float, alpha: float) -> torch.Tensor:
+    """[N,C] un-reduced sigmoid focal loss (mmcv.ops.sigmoid_focal_loss(..., 'none'), focal_loss.py:70-71)."""
+    if pred.dim() != 2 or target.dim() != 1 or target.shape[0] != pred.shape[0]:
+        raise RadetError("sigmoid_focal_loss expects pred [N,C] and target [N]")
+    return _ElementwiseLoss.apply(pred, target, "focal", gamma, alpha)
+
+
+def giou_loss_elementwise(pred: torch.Tensor, target: torch.Tensor, eps: float) -> torch.Tensor:
+    """[n] un-reduced 1 - GIoU of aligned (x1,y1,x2,y2) rows (iou_loss.py:82-98)."""
+    if pred.dim() != 2 or pred.shape[1] != 4 or target.shape != pred.shape:
+        raise RadetError("giou_loss expects pred and target of shape [n,4]")
+    return _ElementwiseLoss.apply(pred, target, "giou", eps, 0.0)
+
+
+def bce_with_logits_elementwise(pred: torch.Tensor, target: torch.Tensor) -> torch.Tensor:
+    """Un-reduced binary cross entropy with logits, same shape as pred (cross_entropy_loss.py:83-85)."""
+    if target.shape != pred.shape:
+        raise RadetError("binary_cross_entropy expects label of the same shape as pred")
+    return _ElementwiseLoss.apply(pred, target, "bce", 0.0, 0.0)
+
+
 # ------------------------------------------------------------------------------------------------ NMS family
 _SCORE_MODE = {"cls": 1, "iou": 2}
 

@@ -1,17 +1,36 @@
 """LOSSES mirrors named by the configs (configs/bop/r50_ycbv_pbr.py:46-55).
 
 Inside RADetHead.loss the three modules are folded into one fused kernel pair (csrc/loss.cu); the modules carry the
-hyper-parameters (gamma, alpha, eps, loss_weight) exactly as the reference's do:
+hyper-parameters (gamma, alpha, eps, loss_weight) exactly as the reference's do.  Called on their own they run the
+element-wise CUDA kernels (radet_sigmoid_focal_loss / radet_giou_loss / radet_bce_with_logits: loss and derivative in
+one launch) and weight / reduce the way losses/utils.py does:
   FocalLoss        models/losses/focal_loss.py:91-157
   GIoULoss         models/losses/iou_loss.py:319-354
   CrossEntropyLoss models/losses/cross_entropy_loss.py:128-201 (use_sigmoid=True only)
 """
+import torch
 import torch.nn as nn
 
+from .. import functional as F
 from .registry import LOSSES
 
-_STANDALONE = ("standalone {0}.forward is not part of the accelerated path in this round: RADetHead.loss runs the fused "
-               "CUDA kernel (radet_loss_fwd_bwd); there is no PyTorch fallback")
+
+def weight_reduce_loss(loss, weight=None, reduction='mean', avg_factor=None):
+    """losses/utils.py:26-52 (element-wise weight, then mean / sum / sum-over-avg_factor)."""
+    if weight is not None:
+        loss = loss * weight
+    if avg_factor is None:
+        if reduction == 'mean':
+            loss = loss.mean()
+        elif reduction == 'sum':
+            loss = loss.sum()
+        elif reduction != 'none':
+            raise ValueError(f"{reduction} is not a valid value for reduction")
+    elif reduction == 'mean':
+        loss = loss.sum() / avg_factor
+    elif reduction != 'none':
+        raise ValueError('avg_factor can not be used with reduction="sum"')
+    return loss
 
 
 @LOSSES.register_module()
@@ -26,7 +45,19 @@ class FocalLoss(nn.Module):
         self.loss_weight = loss_weight
 
     def forward(self, pred, target, weight=None, avg_factor=None, reduction_override=None):
-        raise NotImplementedError(_STANDALONE.format("FocalLoss"))
+        """focal_loss.py:122-157 -> sigmoid_focal_loss :44-87 (standalone use; RADetHead.loss runs the fused kernel)."""
+        assert reduction_override in (None, 'none', 'mean', 'sum')
+        reduction = reduction_override if reduction_override else self.reduction
+        loss = F.sigmoid_focal_loss_elementwise(pred, target, self.gamma, self.alpha)
+        if weight is not None:
+            if weight.shape != loss.shape:
+                if weight.size(0) == loss.size(0):
+                    weight = weight.view(-1, 1)
+                else:
+                    assert weight.numel() == loss.numel()
+                    weight = weight.view(loss.size(0), -1)
+            assert weight.ndim == loss.ndim
+        return self.loss_weight * weight_reduce_loss(loss, weight, reduction, avg_factor)
 
 
 @LOSSES.register_module()
@@ -38,7 +69,16 @@ class GIoULoss(nn.Module):
         self.loss_weight = loss_weight
 
     def forward(self, pred, target, weight=None, avg_factor=None, reduction_override=None, **kwargs):
-        raise NotImplementedError(_STANDALONE.format("GIoULoss"))
+        """iou_loss.py:327-354 -> giou_loss :82-98."""
+        if weight is not None and not torch.any(weight > 0):
+            return (pred * weight).sum()  # 0
+        assert reduction_override in (None, 'none', 'mean', 'sum')
+        reduction = reduction_override if reduction_override else self.reduction
+        if weight is not None and weight.dim() > 1:
+            assert weight.shape == pred.shape
+            weight = weight.mean(-1)
+        loss = F.giou_loss_elementwise(pred, target, self.eps)
+        return self.loss_weight * weight_reduce_loss(loss, weight, reduction, avg_factor)
 
 
 @LOSSES.register_module()
@@ -56,4 +96,20 @@ class CrossEntropyLoss(nn.Module):
         self.class_weight = class_weight
 
     def forward(self, cls_score, label, weight=None, avg_factor=None, reduction_override=None, **kwargs):
-        raise NotImplementedError(_STANDALONE.format("CrossEntropyLoss"))
+        """cross_entropy_loss.py:163-201 -> binary_cross_entropy :58-91."""
+        assert reduction_override in (None, 'none', 'mean', 'sum')
+        reduction = reduction_override if reduction_override else self.reduction
+        if cls_score.dim() != label.dim():      # _expand_onehot_labels, cross_entropy_loss.py:40-55
+            C = cls_score.size(-1)
+            valid = (label >= 0) & (label < C)
+            onehot = torch.zeros((label.size(0), C), dtype=cls_score.dtype, device=cls_score.device)
+            rows = torch.nonzero(valid, as_tuple=False).squeeze(1)
+            if rows.numel() > 0:
+                onehot[rows, label[rows]] = 1
+            if weight is not None:
+                weight = weight.view(-1, 1).expand(weight.size(0), C)
+            label = onehot
+        if weight is not None:
+            weight = weight.float()
+        loss = F.bce_with_logits_elementwise(cls_score, label.float())
+        return self.loss_weight * weight_reduce_loss(loss, weight, reduction=reduction, avg_factor=avg_factor)

@@ -454,3 +454,45 @@ def test_graphed_hot_path_matches_eager_calls():
             assert np.array_equal(res["dets"][b, :k].numpy().view(np.uint32), od.view(np.uint32))
             assert np.array_equal(res["labels"][b, :k].numpy(), ol)
             assert int(res["consumed"][b]) == orc.assign_image_seeded(im.gt_bboxes, im.masks, im.H, im.W, im.seed)[2]
+
+
+# ------------------------------------------------------------------------------------------------ standalone LOSSES
+from tests.test_oracle_golden import _LOSS_CASES, loss_case_inputs  # noqa: E402
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("kind,tag,kw", _LOSS_CASES)
+def test_standalone_loss_modules(kind, tag, kw):
+    """plugin FocalLoss / GIoULoss / CrossEntropyLoss called on their own (models/losses/*.py): value and autograd
+    gradient against the reference's golden output (fp32) and the float64 oracle.  Tolerances: loss 1e-5 relative,
+    gradient rtol 1e-4 + 1e-6 max|g| (the head's)."""
+    g = hp.load("losses.npz")
+    pred, target, weight, red, af, lw = loss_case_inputs(g, kind, kw)
+    mod = {"focal": lambda: P.FocalLoss(use_sigmoid=True, gamma=2.0, alpha=0.25), "giou": lambda: P.GIoULoss(eps=1e-6, loss_weight=2.0),
+           "bce": lambda: P.CrossEntropyLoss(use_sigmoid=True)}[kind]()
+    x = torch.from_numpy(pred).to(DEV).requires_grad_()
+    t = torch.from_numpy(target).to(DEV)
+    w = None if weight is None else torch.from_numpy(weight).to(DEV)
+    out = mod(x, t, weight=w, avg_factor=af, reduction_override=red if tag != "zero_w4" else None)
+    out.sum().backward()
+    want64, grad64 = orc.standalone_loss(kind, pred, target, weight, red, af, loss_weight=lw, dtype="float64")
+    for want, gw in ((g[f"{kind}/{tag}/loss"], g[f"{kind}/{tag}/grad"]), (want64, grad64)):
+        np.testing.assert_allclose(out.detach().cpu().numpy(), want, rtol=1e-5, atol=1e-6)
+        np.testing.assert_allclose(x.grad.cpu().numpy(), gw, rtol=1e-4, atol=1e-6 * max(1e-30, float(np.abs(gw).max())))
+
+
+@pytest.mark.gpu
+def test_standalone_bce_class_index_labels():
+    g = hp.load("losses.npz")
+    x = torch.from_numpy(g["focal/pred"]).to(DEV).requires_grad_()
+    out = P.CrossEntropyLoss(use_sigmoid=True)(x, torch.from_numpy(g["focal/target"].astype(np.int64)).to(DEV),
+                                               weight=torch.from_numpy(g["focal/weight"]).to(DEV), avg_factor=11.0)
+    out.backward()
+    np.testing.assert_allclose(out.item(), g["bce/onehot/loss"], rtol=1e-5)
+    np.testing.assert_allclose(x.grad.cpu().numpy(), g["bce/onehot/grad"], rtol=1e-4, atol=1e-8)
+
+
+@pytest.mark.gpu
+def test_standalone_losses_refuse_cpu_tensors():
+    with pytest.raises(Exception):
+        P.FocalLoss()(torch.zeros(4, 3), torch.zeros(4, dtype=torch.int64))

@@ -123,3 +123,45 @@ def test_anchor_docstring_kat():
     # anchor_generator.py:40-55 known answers, with this config's scale (8) instead of 9 checked structurally
     a = orc.grid_anchors(32, 32, strides=(16,), octave_base_scale=9)
     assert np.array_equal(a, np.array([[-72, -72, 72, 72], [-56, -72, 88, 72], [-72, -56, 72, 88], [-56, -56, 88, 88]], np.float32))
+
+
+_LOSS_CASES = [("focal", "mean_avg", dict(reduction="mean", avg_factor=37.5, use_w=True)), ("focal", "none", dict(reduction="none")),
+               ("focal", "sum_w", dict(reduction="sum", use_w=True)), ("focal", "mean", dict(reduction="mean")),
+               ("giou", "mean_avg", dict(reduction="mean", avg_factor="sum_w", use_w=True, loss_weight=2.0)),
+               ("giou", "none", dict(reduction="none", loss_weight=2.0)), ("giou", "zero_w4", dict(zero_w4=True, loss_weight=2.0)),
+               ("giou", "w4", dict(reduction="sum", w4=True, loss_weight=2.0)),
+               ("bce", "mean_avg", dict(reduction="mean", avg_factor="sum_w", use_w=True)), ("bce", "none", dict(reduction="none"))]
+
+
+def loss_case_inputs(g, kind, kw):
+    """(pred, target, weight, reduction, avg_factor, loss_weight) of one losses.npz record."""
+    pred = g[f"{kind}/pred"]
+    target = g["focal/target"].astype(np.int64) if kind == "focal" else g["giou/target"] if kind == "giou" else g["bce/label"]
+    w = g[f"{kind}/weight"]
+    weight = w if kw.get("use_w") else None
+    if kw.get("zero_w4"):
+        weight = np.zeros((pred.shape[0], 4), np.float32)
+    if kw.get("w4"):
+        weight = np.repeat(w[:, None], 4, 1)
+    af = kw.get("avg_factor")
+    if af == "sum_w":
+        af = float(w.sum())
+    return pred, target, weight, kw.get("reduction", "mean"), af, kw.get("loss_weight", 1.0)
+
+
+@pytest.mark.parametrize("kind,tag,kw", _LOSS_CASES)
+def test_standalone_losses_match_reference(kind, tag, kw):
+    """oracle restatement of FocalLoss / GIoULoss / CrossEntropyLoss vs the reference modules (fp32 autograd golden)."""
+    g = hp.load("losses.npz")
+    pred, target, weight, red, af, lw = loss_case_inputs(g, kind, kw)
+    loss, grad = orc.standalone_loss(kind, pred, target, weight, red, af, loss_weight=lw, dtype="float32")
+    np.testing.assert_allclose(loss, g[f"{kind}/{tag}/loss"], rtol=2e-6, atol=1e-7)
+    np.testing.assert_allclose(grad, g[f"{kind}/{tag}/grad"], rtol=2e-5, atol=1e-7)
+
+
+def test_standalone_bce_onehot_matches_reference():
+    g = hp.load("losses.npz")
+    loss, grad = orc.standalone_loss("bce", g["focal/pred"], g["focal/target"].astype(np.int64), g["focal/weight"], "mean", 11.0,
+                                     dtype="float32")
+    np.testing.assert_allclose(loss, g["bce/onehot/loss"], rtol=2e-6)
+    np.testing.assert_allclose(grad, g["bce/onehot/grad"], rtol=2e-5, atol=1e-8)
