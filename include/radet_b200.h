@@ -249,6 +249,17 @@ int radet_get_bboxes(const radet_grid_t* grid, int32_t batch, int32_t num_classe
                      float* dets, int64_t* labels, int32_t* num_dets, void* workspace, size_t workspace_bytes,
                      void* stream);
 
+/* with_nms=False branch of _get_bboxes_single (radet_head.py:165-169): every candidate that passed score_thr and the
+ * per-level top-k, un-suppressed.  rows f32 [batch][cap][9] = decoded box (clamped to img_shape, divided by
+ * scale_factor when cfg->rescale), score * centerness, prior box (same rescale); labels int64 [batch][cap];
+ * num_rows int32 [batch].  cap = radet_candidates_capacity(); rows of one image are ordered by class, then by
+ * descending score * centerness (the reference's order inside a level is topk(sorted=False)'s).
+ * Workspace: radet_get_bboxes_workspace_bytes().  nms_* fields of cfg are ignored. */
+int64_t radet_candidates_capacity(const radet_grid_t* grid, int32_t num_classes, int32_t nms_pre);
+int radet_get_candidates(const radet_grid_t* grid, int32_t batch, int32_t num_classes, const radet_maps_t* maps,
+                         const int32_t* img_shapes, const float* scale_factors, const radet_detect_cfg_t* cfg, float* rows,
+                         int64_t* labels, int32_t* num_rows, void* workspace, size_t workspace_bytes, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

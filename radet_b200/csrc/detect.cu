@@ -237,6 +237,7 @@ struct ClsParams {
   const int* img_shapes;
   const float* scale_factors;
   const int* class_counts;
+  int* class_counts_rw; // same array (detect_emit_kernel re-arms it)
   u64* bins;           // sorted in place
   int img_cap;         // seeds per image <= candidates per image
   float* seed_out;     // [B][img_cap][5]  voted box + score of every cluster of the image (any order)
@@ -868,6 +869,78 @@ static int sel_plan(const GridDev& g, int B, int C, SelPlan* plan) {
   return RADET_OK;
 }
 
+// ------------------------------------------------------------------------------------------------ with_nms=False
+// radet_head.py:165-169: every candidate that survived score_thr and the per-level top-k, un-suppressed, as rows
+// [x1,y1,x2,y2 (decoded, clamped, rescaled), score*centerness, anchor x1,y1,x2,y2 (rescaled)] + its class.
+// One CTA per (image, class) bin; rows are written class-major and by descending score*centerness inside a class
+// (the reference's own order inside a level is whatever topk(sorted=False) returns).
+struct EmitParams {
+  ClsParams cls;      // grid, maps, C, class_cap, rescale, img_shapes, scale_factors, class_counts, bins (cs_mode = 0)
+  float* rows;        // [B][img_cap][9]
+  int64_t* labels;    // [B][img_cap]
+  int* num;           // [B]
+  int* done;          // [B] CTAs finished (re-armed here, like class_counts)
+};
+
+__global__ void __launch_bounds__(kClsThreads)
+detect_emit_kernel(EmitParams e) {
+  const ClsParams& p = e.cls;
+  __shared__ int s_base, s_total;
+  const int c = blockIdx.x, b = blockIdx.y, tid = threadIdx.x;
+  if (tid < 32) {                                  // exclusive prefix of the class counts of this image
+    int before = 0, total = 0;
+    for (int k = tid; k < p.C; k += 32) {
+      const int n = min(p.class_counts[b * p.C + k], p.class_cap);
+      total += n;
+      if (k < c) before += n;
+    }
+    before = __reduce_add_sync(kFull, before);
+    total = __reduce_add_sync(kFull, total);
+    if (tid == 0) {
+      s_base = before;
+      s_total = total;
+    }
+  }
+  __syncthreads();
+  const int m = min(p.class_counts[b * p.C + c], p.class_cap);
+  const u64* keys = p.bins + ((int64_t)b * p.C + c) * p.class_cap;
+  const GridDev& g = p.grid;
+  for (int i = tid; i < m; i += kClsThreads) {
+    const u64 key = keys[i];
+    int rank = 0;
+    for (int j = 0; j < m; ++j) rank += keys[j] > key ? 1 : 0;
+    float4 bx;
+    float cs, vs;
+    decode_item(p, b, c, key, bx, cs, vs);
+    const unsigned ord = 0xffffffffu - (unsigned)(key & 0xffffffffull);
+    const int l = (int)(ord >> kOrdLevelShift);
+    const int q = (int)((ord & ((1u << kOrdLevelShift) - 1u)) / (unsigned)p.C);
+    const int y = q / g.w[l], x = q - y * g.w[l];
+    const float st = (float)g.stride[l], half = __fmul_rn(0.5f, __fmul_rn(g.anchor_scale, st));   // anchor_generator.py:142-185
+    float4 an = make_float4(__fsub_rn((float)x * st, half), __fsub_rn((float)y * st, half), __fadd_rn((float)x * st, half),
+                            __fadd_rn((float)y * st, half));
+    if (p.rescale) {                                // radet_head.py:141-143
+      const float4 sf = *reinterpret_cast<const float4*>(p.scale_factors + 4 * b);
+      an = make_float4(__fdiv_rn(an.x, sf.x), __fdiv_rn(an.y, sf.y), __fdiv_rn(an.z, sf.z), __fdiv_rn(an.w, sf.w));
+    }
+    const int64_t row = (int64_t)b * p.img_cap + s_base + rank;
+    float* o = e.rows + row * 9;
+    o[0] = bx.x; o[1] = bx.y; o[2] = bx.z; o[3] = bx.w;
+    o[4] = cs;
+    o[5] = an.x; o[6] = an.y; o[7] = an.z; o[8] = an.w;
+    e.labels[row] = c;
+  }
+  __syncthreads();
+  if (tid == 0) {
+    if (c == 0) e.num[b] = s_total;
+    __threadfence();
+    if (atomicAdd(&e.done[b], 1) == p.C - 1) {     // last class CTA of the image: re-arm the counters
+      for (int k = 0; k < p.C; ++k) p.class_counts_rw[b * p.C + k] = 0;
+      e.done[b] = 0;
+    }
+  }
+}
+
 struct DetWs {
   int* counts;        // [B][8]
   int* class_counts;  // [B][C]
@@ -1021,4 +1094,86 @@ extern "C" int radet_get_bboxes(const radet_grid_t* grid, int32_t batch, int32_t
   detect_rank_kernel<<<batch, kRankThreads, rank_smem, st>>>(rp);
   RADET_LAUNCH_CHECK();
   return RADET_OK;
+}
+
+// radet_head.py:165-169 (with_nms=False): select -> per-level top-k / class bins -> emit
+extern "C" int radet_get_candidates(const radet_grid_t* grid, int32_t batch, int32_t num_classes, const radet_maps_t* maps,
+                                    const int32_t* img_shapes, const float* scale_factors, const radet_detect_cfg_t* cfg,
+                                    float* rows, int64_t* labels, int32_t* num_rows, void* workspace, size_t workspace_bytes,
+                                    void* stream) {
+  GridDev g;
+  int rc = make_grid_dev(grid, &g);
+  if (rc != RADET_OK) return rc;
+  if (batch <= 0 || num_classes <= 0 || !maps || !img_shapes || !cfg || !rows || !labels || !num_rows || !workspace) return RADET_E_BADARG;
+  if (cfg->rescale && !scale_factors) return RADET_E_BADARG;
+  if (batch > 65535 || num_classes > 65535) return RADET_E_UNSUPPORTED;
+  if (workspace_bytes < radet_get_bboxes_workspace_bytes(grid, batch, num_classes, cfg) || (reinterpret_cast<uintptr_t>(workspace) & 255))
+    return RADET_E_WORKSPACE;
+  MapsDev md;
+  for (int l = 0; l < RADET_MAX_LEVELS; ++l) {
+    const bool on = l < g.num_levels;
+    md.cls[l] = on ? maps->cls[l] : nullptr;
+    md.bbox[l] = on ? maps->bbox[l] : nullptr;
+    md.iou[l] = on ? maps->iou[l] : nullptr;
+    if (on && (!md.cls[l] || !md.bbox[l] || !md.iou[l])) return RADET_E_BADARG;
+    if (on && ((g.h[l] * g.w[l]) & 3) == 0 && (reinterpret_cast<uintptr_t>(md.cls[l]) & 15)) return RADET_E_BADARG;
+  }
+  SelPlan plan;
+  rc = sel_plan(g, batch, num_classes, &plan);
+  if (rc != RADET_OK) return rc;
+  const int cap = class_cap_of(g, cfg->nms_pre);
+  const int img_cap = img_cap_of(g, num_classes, cfg->nms_pre);
+  DetWs w = det_ws_layout(static_cast<unsigned char*>(workspace), g, batch, num_classes, cap, img_cap);
+  cudaStream_t st = (cudaStream_t)stream;
+  float x_lo = -INFINITY;
+  const double thr = (double)cfg->score_thr;
+  if (thr >= 1.0) x_lo = INFINITY;
+  else if (thr > 0.0) {
+    const double lg = log(thr / (1.0 - thr));
+    x_lo = (float)(lg - 1e-3 * (1.0 + fabs(lg)));
+  }
+  detect_select_kernel<<<dim3(plan.boff[g.num_levels], batch, plan.nj), kSelThreads, 0, st>>>(g, plan, num_classes, md, cfg->score_thr,
+                                                                                              x_lo, w.cand, w.counts);
+  RADET_LAUNCH_CHECK();
+  BinParams bp{};
+  bp.grid = g;
+  bp.maps = md;
+  for (int l = 0; l <= RADET_MAX_LEVELS; ++l) bp.coff[l] = plan.coff[l];
+  bp.C = num_classes;
+  bp.nms_pre = cfg->nms_pre;
+  bp.cs_mode = 0;                 // bins keyed by score * centerness
+  bp.class_cap = cap;
+  bp.cand = w.cand;
+  bp.counts = w.counts;
+  bp.bins = w.bins;
+  bp.class_counts = w.class_counts;
+  detect_bin_kernel<<<dim3(g.num_levels, batch), kBinThreads, 0, st>>>(bp);
+  RADET_LAUNCH_CHECK();
+  EmitParams ep{};
+  ep.cls.grid = g;
+  ep.cls.maps = md;
+  ep.cls.C = num_classes;
+  ep.cls.class_cap = cap;
+  ep.cls.rescale = cfg->rescale;
+  ep.cls.cs_mode = 0;
+  ep.cls.vs_mode = 0;
+  ep.cls.img_shapes = img_shapes;
+  ep.cls.scale_factors = scale_factors;
+  ep.cls.class_counts = w.class_counts;
+  ep.cls.class_counts_rw = w.class_counts;
+  ep.cls.bins = w.bins;
+  ep.cls.img_cap = img_cap;
+  ep.rows = rows;
+  ep.labels = labels;
+  ep.num = num_rows;
+  ep.done = w.img_seed_count;
+  detect_emit_kernel<<<dim3(num_classes, batch), kClsThreads, 0, st>>>(ep);
+  RADET_LAUNCH_CHECK();
+  return RADET_OK;
+}
+
+extern "C" int64_t radet_candidates_capacity(const radet_grid_t* grid, int32_t num_classes, int32_t nms_pre) {
+  GridDev g;
+  if (make_grid_dev(grid, &g) != RADET_OK || num_classes <= 0) return 0;
+  return img_cap_of(g, num_classes, nms_pre);
 }

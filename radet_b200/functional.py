@@ -468,3 +468,30 @@ def get_bboxes(geom: Geometry, num_classes: int, cls, bbox, iou, img_shapes: tor
                                ctypes.byref(ccfg), _ptr(dets), _ptr(labels), _ptr(num), _ptr(ws), ws.numel(), _stream()),
           "radet_get_bboxes")
     return dets, labels, num
+
+
+def get_candidates(geom: Geometry, num_classes: int, cls, bbox, iou, img_shapes: torch.Tensor, scale_factors: torch.Tensor,
+                   cfg: DetectConfig, rescale=False):
+    """with_nms=False branch (radet_head.py:165-169), batched: rows [B,cap,9] = (decoded box, score*centerness, prior box),
+    labels [B,cap], num [B]; rows of an image ordered by class, then by descending score*centerness."""
+    B = cls[0].shape[0]
+    level_shapes = tuple(tuple(t.shape[-2:]) for t in cls)
+    _check_maps(cls, bbox, iou, level_shapes, B, num_classes)
+    dev = cls[0].device
+    cls = [t.contiguous() for t in cls]
+    bbox = [t.contiguous() for t in bbox]
+    iou = [t.contiguous() for t in iou]
+    grid = geom.grid(level_shapes)
+    lib = _lib.load()
+    maps = _lib.make_maps([t.data_ptr() for t in cls], [t.data_ptr() for t in bbox], [t.data_ptr() for t in iou])
+    ccfg = cfg.c_struct(rescale)
+    cap = int(lib.radet_candidates_capacity(ctypes.byref(grid), num_classes, cfg.nms_pre))
+    rows = torch.empty((B, cap, 9), dtype=torch.float32, device=dev)
+    labels = torch.empty((B, cap), dtype=torch.int64, device=dev)
+    num = torch.empty((B,), dtype=torch.int32, device=dev)
+    nws = lib.radet_get_bboxes_workspace_bytes(ctypes.byref(grid), B, num_classes, ctypes.byref(ccfg))
+    ws = _workspace(("det", B, level_shapes, num_classes, cfg.nms_pre), nws, dev)
+    check(lib.radet_get_candidates(ctypes.byref(grid), B, num_classes, ctypes.byref(maps), _ptr(img_shapes), _ptr(scale_factors),
+                                   ctypes.byref(ccfg), _ptr(rows), _ptr(labels), _ptr(num), _ptr(ws), ws.numel(), _stream()),
+          "radet_get_candidates")
+    return rows, labels, num

@@ -222,8 +222,6 @@ class RADetHead(nn.Module):
     def get_bboxes(self, cls_scores, bbox_preds, centernesses, img_metas, cfg=None, rescale=False, with_nms=True):
         cfg = self.test_cfg if cfg is None else cfg
         assert len(cls_scores) == len(bbox_preds)
-        if not with_nms:
-            raise NotImplementedError("with_nms=False (test-time-augmentation merge path) is a SURVEY §8 'next' row")
         dcfg = F.DetectConfig.from_test_cfg(cfg)
         dev = cls_scores[0].device
         B = len(img_metas)
@@ -231,6 +229,17 @@ class RADetHead(nn.Module):
         sf = np.asarray([np.broadcast_to(np.asarray(m.get('scale_factor', 1.0), np.float32), (4,)) for m in img_metas], np.float32)
         shp_d = torch.from_numpy(shp).to(dev, non_blocking=True)
         sf_d = torch.from_numpy(sf).to(dev, non_blocking=True)
+        if not with_nms:    # radet_head.py:165-169: [boxes, score*centerness, anchors] rows + categories, no suppression
+            rows, cats, num = F.get_candidates(self.geom, self.num_classes, [t.detach() for t in cls_scores],
+                                               [t.detach() for t in bbox_preds], [t.detach() for t in centernesses], shp_d,
+                                               sf_d, dcfg, rescale=rescale)
+            out = []
+            for b, k in enumerate(num.cpu().tolist()):
+                if k == 0:  # radet_head.py:137-138
+                    out.append((torch.empty((0, 5)), torch.empty((0, 1), dtype=torch.int)))
+                else:
+                    out.append((rows[b, :k], cats[b, :k]))
+            return out
         dets, labels, num = F.get_bboxes(self.geom, self.num_classes, [t.detach() for t in cls_scores],
                                          [t.detach() for t in bbox_preds], [t.detach() for t in centernesses], shp_d, sf_d,
                                          dcfg, rescale=rescale)

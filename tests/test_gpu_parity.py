@@ -496,3 +496,73 @@ def test_standalone_bce_class_index_labels():
 def test_standalone_losses_refuse_cpu_tensors():
     with pytest.raises(Exception):
         P.FocalLoss()(torch.zeros(4, 3), torch.zeros(4, dtype=torch.int64))
+
+
+# ------------------------------------------------------------------------------------------------ with_nms=False
+@pytest.mark.gpu
+@pytest.mark.parametrize("key", ["small", "cfg1"])
+def test_get_bboxes_without_nms_matches_reference(key):
+    """RADetHead.get_bboxes(with_nms=False) (radet_head.py:165-169): [box, score*centerness, prior] rows + categories.
+    Boxes, priors and categories bit-exact against the reference's golden rows (compared as sets: the reference's order
+    is topk(sorted=False)'s); score*centerness within 2 ulp of the torch-CPU golden and bit-exact against the oracle."""
+    g = hp.load("head.npz")
+    wl, batch, idx_l, w_l, ho = _head_inputs(key)
+    head = P.build_head(dict(type="RADetHead", num_classes=wl.C, in_channels=8, feat_channels=8, stacked_convs=1,
+                             norm_cfg=dict(type="GN", num_groups=4, requires_grad=True),
+                             test_cfg=dict(nms_pre=1000, score_thr=0.05, nms=dict(type="vote", iou_threshold=0.65), max_per_img=100))).to(DEV)
+    cls, bbox, iou = _to_dev(ho)
+    res = head.get_bboxes(cls, bbox, iou, syn.img_metas(batch), rescale=True, with_nms=False)
+    assert len(res) == len(batch)
+    for b, (rows, cats) in enumerate(res):
+        rows, cats = rows.cpu().numpy(), cats.cpu().numpy()
+        assert rows.shape[1] == 9 and cats.dtype == np.int64
+        # documented order: class-major, descending score*centerness inside a class
+        assert np.all(np.diff(cats) >= 0)
+        same = np.diff(cats) == 0
+        assert np.all(np.diff(rows[:, 4])[same] < 0)
+        o = np.lexsort((cats, rows[:, 8], rows[:, 7], rows[:, 6], rows[:, 5]))
+        ref = g[f"{key}/cand_{b}"]
+        cols = [0, 1, 2, 3, 5, 6, 7, 8]
+        assert rows.shape == ref.shape
+        assert np.array_equal(rows[o][:, cols].view(np.uint32), ref[:, cols].view(np.uint32))
+        # product of two sigmoids: the golden was made by torch-CPU kernels, each factor may sit 1 ulp away from the CUDA
+        # flavour the device (and the reference on a GPU) computes; the oracle check below is bit-exact
+        np.testing.assert_allclose(rows[o][:, 4], ref[:, 4], rtol=4e-7, atol=0)
+        assert np.array_equal(cats[o], g[f"{key}/candlab_{b}"].astype(np.int64))
+        im = batch[b]
+        bx, sc, ctr, ocats, anc = orc.select_candidates([m[b] for m in ho.cls], [m[b] for m in ho.bbox], [m[b] for m in ho.iou],
+                                                        (im.H, im.W, 3), np.ones(4, np.float32), 0.05, 1000)
+        full = np.concatenate([bx, (sc * ctr)[:, None], anc], 1).astype(np.float32)
+        oo = np.lexsort((ocats, full[:, 8], full[:, 7], full[:, 6], full[:, 5]))
+        assert np.array_equal(rows[o].view(np.uint32), full[oo].view(np.uint32))
+
+
+@pytest.mark.gpu
+def test_get_bboxes_without_nms_rescale_and_empty():
+    wl, batch, idx_l, w_l, ho = _head_inputs("small")
+    cls, bbox, iou = _to_dev(ho)
+    shp = torch.tensor([[im.H, im.W] for im in batch], dtype=torch.int32, device=DEV)
+    sf = torch.tensor([[2.0, 0.5, 2.0, 0.5]] * len(batch), dtype=torch.float32, device=DEV)
+    cfg = F.DetectConfig(score_thr=0.05, nms_pre=7, nms_type="vote", iou_threshold=0.65)
+    rows, cats, num = F.get_candidates(GEOM, wl.C, cls, bbox, iou, shp, sf, cfg, rescale=True)
+    for b, im in enumerate(batch):
+        bx, sc, ctr, ocats, anc = orc.select_candidates([m[b] for m in ho.cls], [m[b] for m in ho.bbox], [m[b] for m in ho.iou],
+                                                        (im.H, im.W, 3), np.array([2.0, 0.5, 2.0, 0.5], np.float32), 0.05, 7)
+        full = np.concatenate([bx, (sc * ctr)[:, None], anc], 1).astype(np.float32)
+        k = int(num[b])
+        assert k == full.shape[0] and k <= 7 * 5
+        r, c = rows[b, :k].cpu().numpy(), cats[b, :k].cpu().numpy()
+        o = np.lexsort((c, r[:, 8], r[:, 7], r[:, 6], r[:, 5], r[:, 4]))
+        oo = np.lexsort((ocats, full[:, 8], full[:, 7], full[:, 6], full[:, 5], full[:, 4]))
+        assert np.array_equal(r[o].view(np.uint32), full[oo].view(np.uint32))
+        assert np.array_equal(c[o], ocats[oo])
+    # nothing above the threshold -> the reference's empty return
+    cfg2 = F.DetectConfig(score_thr=0.9999999, nms_pre=1000, nms_type="vote", iou_threshold=0.65)
+    _, _, num2 = F.get_candidates(GEOM, wl.C, cls, bbox, iou, shp, sf, cfg2, rescale=False)
+    assert int(num2.sum()) == 0
+    # and a second call on the same workspace still works (counters re-armed)
+    rows3, cats3, num3 = F.get_candidates(GEOM, wl.C, cls, bbox, iou, shp, sf, cfg, rescale=True)
+    assert torch.equal(num3, num)
+    for b in range(len(batch)):
+        k = int(num[b])
+        assert torch.equal(cats3[b, :k], cats[b, :k]) and torch.equal(rows3[b, :k], rows[b, :k])
