@@ -329,6 +329,8 @@ def main():
                     losses, grads = do_loss(s, idx, w)
                 main.wait_stream(side2)
                 main.wait_stream(side)
+                if keep is not None:
+                    keep.append((idx, w, losses, grads, dets, dl, num))
                 return losses, num
             with torch.cuda.stream(side2):      # np.random.seed() per image: sequential, depends on nothing
                 states = F.seed_states((nxt or s)["seeds"])
@@ -442,9 +444,15 @@ def main():
 
     # overlapped replays must leave exactly what one-at-a-time replays leave (no scratch shared between lanes)
     overlap_check = None
-    if use_graph and U > 1 and len(stages) == 3:
-        flat = lambda keep: [t.clone() for t in (keep[0][0], keep[0][1], keep[0][2], *keep[0][3][0], *keep[0][3][1], *keep[0][3][2],
-                                                 keep[0][4], keep[0][5], keep[0][6])]
+    if use_graph and U > 1 and (len(stages) == 3 or os.environ.get("RADET_BENCH_DEBUG")):
+        def flat(keep):
+            ts = []
+            for t in keep[0]:
+                if isinstance(t, torch.Tensor):
+                    ts.append(t.clone())
+                elif isinstance(t, (tuple, list)):
+                    ts += [x.clone() for grp in t for x in grp]
+            return ts
         for i in range(2 * R):
             run(i)
         torch.cuda.synchronize()
@@ -453,9 +461,32 @@ def main():
             run(i, one_lane=True)
             torch.cuda.synchronize()
             want = flat(outs[i])
-            for a, b in zip(got[i], want):
+            if os.environ.get("RADET_BENCH_DEBUG"):
+                si = sets[i]
+                truth = F.loss_fwd_bwd(geom, wl.C, si["cls"], si["bbox"], si["iou"], si["counts"], si["boxes"], si["labels"],
+                                       si["abuf"][0], si["abuf"][1], lcfg, gt_offsets=si["off"])
+                torch.cuda.synchronize()
+                tl = [truth[0]] + [x for grp in truth[1] for x in grp]
+                for k, (a, b) in enumerate(zip(got[i], want)):
+                    if not torch.equal(a, b):
+                        bad = (a != b).nonzero()
+                        msg = f"set {i} output #{k} shape {tuple(a.shape)}: {bad.shape[0]} differ; first {bad[:3].tolist()}"
+                        if 2 <= k < 2 + len(tl):
+                            t = tl[k - 2]
+                            j = tuple(bad[0].tolist())
+                            msg += (f" overlapped_wrong={int((a != t).sum())} serial_wrong={int((b != t).sum())} "
+                                    f"vals ov={a[j].item():.6g} ser={b[j].item():.6g} truth={t[j].item():.6g}")
+                            if a.dim() == 4:
+                                bb, cc, yy, xx = j
+                                near = {dc: t[bb, cc + dc, yy, xx].item() for dc in (-8, -1, 1, 8) if 0 <= cc + dc < a.shape[1]}
+                                msg += f" truth at other planes {near}"
+                        print(msg, file=sys.stderr)
+            for k, (a, b) in enumerate(zip(got[i], want)):
                 if not torch.equal(a, b):
-                    raise RuntimeError(f"overlapped replay of input set {i} differs from its serial replay")
+                    bad = (a != b).nonzero()
+                    raise RuntimeError(f"overlapped replay of input set {i} differs from its serial replay: output #{k} "
+                                       f"shape {tuple(a.shape)}, {bad.shape[0]} elements, first at {bad[0].tolist()}: "
+                                       f"{a[tuple(bad[0])].item()} vs {b[tuple(bad[0])].item()}")
         overlap_check = f"outputs of {R} sets after overlapped replays bit-identical to one-at-a-time replays"
         del got
     ms_per_step = ms_total / args.steps

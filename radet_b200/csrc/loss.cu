@@ -299,8 +299,8 @@ struct DenseTable {
 // Sigmoid focal loss and its derivative for one logit (mmcv sigmoid_focal_loss semantics; restated from
 // focal_loss.py:10-41 because the mmcv op is not in the reference tree).  Tolerance parity (not bit parity), so the
 // transcendental part is kept to ~28 instructions per element (at 70+ the kernel is issue-bound, not HBM-bound):
-// one ex2.approx, one rcp.approx and a degree-7 polynomial
-//     log1p(e) = e * P(e),  P = near-minimax degree-7 fit of log1p(t)/t on [0,1]  (relative error 3.7e-7 in fp32).
+// one ex2.approx, one rcp.approx and one lg2.approx:
+//     e = exp(-|z|),  inv = 1/(1+e),  log1p(e) = -ln(inv).
 // The target case is folded into the non-target one by symmetry: with z = -x,
 //     FL_target(x) = alpha * sigmoid(z)^gamma * softplus(z),  dFL_target/dx = -d/dz[...],
 // so a single expression  m = coef * s^gamma,  loss = m * softplus(z),  dloss/dz = m * (s + gamma * (1-s) * softplus(z))
@@ -315,20 +315,19 @@ __device__ __forceinline__ float rcp_approx(float x) {
   asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
 }
+__device__ __forceinline__ float lg2_approx(float x) {
+  float y;
+  asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
 template <bool kGamma2>
 __device__ __forceinline__ void focal_elem(float x, bool is_t, float gamma, float alpha, float& loss, float& grad) {
   const float z = is_t ? -x : x;
   const float e = ex2_approx(fabsf(z) * -1.4426950408889634f);   // exp(-|z|) in (0, 1]
-  float P = -0.00837115292f;                                      // degree-7 fit: relative error 3.7e-7
-  P = fmaf(P, e, 0.0434939004f);
-  P = fmaf(P, e, -0.106850028f);
-  P = fmaf(P, e, 0.176874772f);
-  P = fmaf(P, e, -0.244747743f);
-  P = fmaf(P, e, 0.332719296f);
-  P = fmaf(P, e, -0.499971747f);
-  P = fmaf(P, e, 0.999999762f);
-  const float sp = fmaf(e, P, fmaxf(z, 0.f));     // softplus(z)
-  const float inv = rcp_approx(1.0f + e);
+  const float inv = rcp_approx(1.0f + e);                         // 1/(1+e) in [0.5, 1)
+  // softplus(z) = max(z,0) + log1p(e) = max(z,0) - ln(inv): one lg2.approx (absolute error ~1e-7 on a term that is
+  // only tiny where the whole element is negligible: its gradient carries the factor s^2 ~ e^2)
+  const float sp = fmaf(-0.6931471805599453f, lg2_approx(inv), fmaxf(z, 0.f));
   const float s = z >= 0.f ? inv : e * inv;       // sigmoid(z)
   const float coef = is_t ? alpha : 1.f - alpha;
   const float m = coef * (kGamma2 ? s * s : ex2_approx(gamma * -1.4426950408889634f * (sp - z)));   // s^gamma = exp(-gamma*softplus(-z))
@@ -526,6 +525,172 @@ loss_dense_kernel(GridDev grid, DenseTable tab, int B, int C, int cc /* channels
   }
 }
 
+// ---- TMA-pipelined variant (all planes 16-byte tileable: h*w % 4 == 0 on every level) ---------------------------
+// One CTA = one tile of up to 512 consecutive points of one (image, level), one warp per 128 of them.  The C class
+// planes of a warp's points stream through its private 8-stage shared-memory ring, filled by 1-D bulk copies
+// (cp.async.bulk + mbarrier complete_tx; no registers tied up by loads); lanes read their float4 from the ring,
+// compute, and store the gradient straight to global memory.  8 CTAs x 4 warps x 8 stages x 512 B = 128 KB of loads in
+// flight per SM (HBM latency x bandwidth is ~45 KB per SM; the register-pipelined kernel tops out at 48 KB).
+constexpr int kTilePts = 512;
+constexpr int kTmaStages = 8;
+struct TileTable {
+  int tpl[RADET_MAX_LEVELS];        // tiles per (image, level)
+  int toff[RADET_MAX_LEVELS + 1];   // tile offset of each level inside one image
+};
+
+constexpr int kTmaWarps = kTilePts / 128;             // one warp per 128 points of the tile (4 points per lane)
+constexpr int kTmaThreads = kTmaWarps * 32;
+
+template <bool kGamma2>
+__global__ void __launch_bounds__(kTmaThreads, 8)
+loss_dense_tma_kernel(GridDev grid, TileTable tt, int B, int C, MapsDev maps, GradsDev grads,
+                      const int* __restrict__ gt_offsets, const int64_t* __restrict__ gt_labels,
+                      const int64_t* __restrict__ pidx, const float* __restrict__ pw, radet_loss_cfg_t cfg,
+                      const float* __restrict__ grad_scale, LossWs* __restrict__ ws, double* __restrict__ partials,
+                      float* __restrict__ losses) {
+  // Every warp runs its own pipeline over its 128 points: a private 8-stage ring (512 B per stage) with one mbarrier
+  // per stage; lane 0 issues the bulk copy of plane c+8 as soon as the warp has consumed plane c.  Nothing couples the
+  // warps of a CTA inside the plane loop (no block barrier, no producer warp that could fall behind).
+  __shared__ __align__(128) float s_ring[kTmaWarps][kTmaStages][128];
+  __shared__ __align__(8) uint64_t s_full[kTmaWarps][kTmaStages];
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  if (lane == 0) {
+#pragma unroll
+    for (int k = 0; k < kTmaStages; ++k) mbar_init(&s_full[wid][k], 1);
+    fence_barrier_init();
+  }
+  __syncthreads();
+  const int P = grid.off[grid.num_levels];
+  const int tiles_per_image = tt.toff[grid.num_levels];
+  const int total_tiles = B * tiles_per_image;
+  const double num_pos = ws->norm[0], sum_wq = ws->norm[1];
+  const bool has_pos = ws->norm[6] > 0.0;                                        // radet_head.py:261
+  const float gs_cls = grad_scale ? grad_scale[0] : 1.f, gs_box = grad_scale ? grad_scale[1] : 1.f,
+              gs_iou = grad_scale ? grad_scale[2] : 1.f;
+  const float k_cls = gs_cls * cfg.w_cls / (float)(num_pos + (double)cfg.avg_extra);
+  const float k_box = has_pos ? gs_box * cfg.w_bbox / (float)sum_wq : gs_box;
+  const float k_iou = has_pos ? gs_iou * cfg.w_iou / (float)num_pos : gs_iou;
+  const bool want_grad = grads.cls[0] != nullptr;
+  const float gamma = cfg.gamma, alpha = cfg.alpha;
+  float* ring = &s_ring[wid][0][0];
+  uint64_t* full = &s_full[wid][0];
+  float lsum = 0.f;
+  unsigned fills = 0;                                   // planes this warp has pushed through its ring so far
+  for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+    const int b = t / tiles_per_image, r = t - b * tiles_per_image;
+    int l = 0;
+#pragma unroll
+    for (int k = 1; k < RADET_MAX_LEVELS; ++k) l += (k < grid.num_levels && r >= tt.toff[k]) ? 1 : 0;
+    const int hw = grid.h[l] * grid.w[l];
+    const int q_warp = (r - tt.toff[l]) * kTilePts + wid * 128;      // first point of this warp
+    const int npts = min(128, hw - q_warp);                          // multiple of 4; <= 0: nothing for this warp
+    if (npts <= 0) continue;                                          // warp-uniform
+    const uint32_t bytes = (uint32_t)npts * 4u;
+    const float* src = maps.cls[l] + (int64_t)b * C * hw + q_warp;
+    if (lane == 0) {                                                  // prologue: the first planes
+      const int n0 = min(kTmaStages, C);
+      for (int c = 0; c < n0; ++c) {
+        const unsigned st = (fills + c) % kTmaStages;
+        mbar_expect_tx(&full[st], bytes);
+        tma_bulk_g2s(ring + st * 128, src + (int64_t)c * hw, bytes, &full[st]);
+      }
+    }
+    // per-lane setup for its 4 points (index -> label, weight) while the ring fills
+    const int q0 = q_warp + 4 * lane;
+    const bool active = 4 * lane < npts;
+    const int g0 = gt_offsets[b], G = gt_offsets[b + 1] - g0;
+    const int64_t pbase = (int64_t)b * P + grid.off[l] + q0;
+    int idx[4], lab[4];
+    float w[4], kw[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      idx[i] = -1;
+      w[i] = 0.f;
+      if (active) {
+        const int64_t v = pidx[pbase + i];
+        idx[i] = v < 0 ? -1 : (int)(v > (int64_t)G ? (int64_t)G : v);
+        w[i] = pw[pbase + i];
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      lab[i] = (int)label_of(idx[i], G, gt_labels + g0, C);
+      kw[i] = k_cls * w[i];
+    }
+    float* dst = want_grad ? grads.cls[l] + (int64_t)b * C * hw + q0 : nullptr;
+    for (int c = 0; c < C; ++c, ++fills) {
+      const unsigned st = fills % kTmaStages;
+      mbar_wait(&full[st], (fills / kTmaStages) & 1u);
+      float4 xv = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (active) xv = *reinterpret_cast<const float4*>(ring + st * 128 + 4 * lane);
+      if (active) {
+        float lo_, gr_;
+        float4 gv;
+        focal_elem<kGamma2>(xv.x, lab[0] == c, gamma, alpha, lo_, gr_); lsum = fmaf(w[0], lo_, lsum); gv.x = kw[0] * gr_;
+        focal_elem<kGamma2>(xv.y, lab[1] == c, gamma, alpha, lo_, gr_); lsum = fmaf(w[1], lo_, lsum); gv.y = kw[1] * gr_;
+        focal_elem<kGamma2>(xv.z, lab[2] == c, gamma, alpha, lo_, gr_); lsum = fmaf(w[2], lo_, lsum); gv.z = kw[2] * gr_;
+        focal_elem<kGamma2>(xv.w, lab[3] == c, gamma, alpha, lo_, gr_); lsum = fmaf(w[3], lo_, lsum); gv.w = kw[3] * gr_;
+        if (dst) stg_stream4(dst + (int64_t)c * hw, gv);
+      }
+      // Refill the stage only AFTER the values have been consumed.  Issuing the copy right behind the LDS is not
+      // enough: neither a barrier nor an mbarrier arrive waits for a shared-memory read still in flight, and under
+      // load (other kernels' CTAs on the SM) the bulk copy was observed to overwrite the stage before the read.
+      __syncwarp();
+      if (lane == 0 && c + kTmaStages < C) {
+        mbar_expect_tx(&full[st], bytes);
+        tma_bulk_g2s(ring + st * 128, src + (int64_t)(c + kTmaStages) * hw, bytes, &full[st]);
+      }
+    }
+    // regression / IoU gradient planes: zero except at the positives parked by loss_pos_kernel (rescaled in place)
+    if (want_grad && active) {
+      const bool anypos = G > 0 && (idx[0] >= 0 || idx[1] >= 0 || idx[2] >= 0 || idx[3] >= 0);
+#pragma unroll
+      for (int kk = 0; kk < 5; ++kk) {
+        float* o = kk < 4 ? grads.bbox[l] + ((int64_t)b * 4 + kk) * hw + q0 : grads.iou[l] + (int64_t)b * hw + q0;
+        const float kn = kk < 4 ? k_box : k_iou, gs = kk < 4 ? gs_box : gs_iou;
+        float gv[4] = {0.f, 0.f, 0.f, 0.f};
+        if (anypos) {
+#pragma unroll
+          for (int i = 0; i < 4; ++i)
+            if (idx[i] >= 0) gv[i] = has_pos ? kn * o[i] : gs;                  // radet_head.py:280-281 when num_pos == 0
+        }
+        stg_stream4(o, make_float4(gv[0], gv[1], gv[2], gv[3]));
+      }
+    }
+  }
+  // loss_cls = w_cls * sum / (num_pos + num_imgs): deterministic block partials, last block finalises
+  __shared__ double s_part[kTmaThreads / 32];
+  __shared__ bool s_last;
+  const unsigned nblocks = gridDim.x, bid = blockIdx.x;
+  const double v = warp_sum((double)lsum);
+  if (lane == 0) s_part[wid] = v;
+  __syncthreads();
+  if (tid == 0) {
+    double s_ = 0.0;
+    for (int w_ = 0; w_ < kTmaThreads / 32; ++w_) s_ += s_part[w_];
+    partials[bid] = s_;
+    __threadfence();
+    s_last = (atomicAdd(&ws->counter_dense, 1u) == nblocks - 1);
+  }
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
+  double tot = 0.0;
+  for (int i = tid; i < (int)nblocks; i += kTmaThreads) tot += partials[i];
+  tot = warp_sum(tot);
+  if (lane == 0) s_part[wid] = tot;
+  __syncthreads();
+  if (tid == 0) {
+    double s_ = 0.0;
+    for (int w_ = 0; w_ < kTmaThreads / 32; ++w_) s_ += s_part[w_];
+    losses[0] = (float)((double)cfg.w_cls * s_ / (num_pos + (double)cfg.avg_extra));           // radet_head.py:256-259
+    losses[1] = has_pos ? (float)((double)cfg.w_bbox * ws->norm[2] / sum_wq) : (float)ws->norm[4];   // :269-274 / :280
+    losses[2] = has_pos ? (float)((double)cfg.w_iou * ws->norm[3] / num_pos) : (float)ws->norm[5];   // :275-278 / :281
+    losses[3] = (float)num_pos;
+    ws->counter_dense = 0u;
+  }
+}
+
 struct ScaleTable {
   float* ptr[3 * RADET_MAX_LEVELS];
   int64_t n[3 * RADET_MAX_LEVELS];
@@ -691,6 +856,28 @@ static int dense_plan(const GridDev& g, int B, int C, DenseTable* tab, int* cc, 
   return RADET_OK;
 }
 
+// Tiles of the TMA-pipelined dense kernel; false when some level is not 16-byte tileable (h*w % 4 != 0) or the
+// development override RADET_DENSE_IMPL=reg is set.
+static bool tile_plan(const GridDev& g, int B, TileTable* tt, int* blocks) {
+  static const char* impl = getenv("RADET_DENSE_IMPL");
+  if (impl && impl[0] == 'r') return false;
+  int t = 0;
+  for (int l = 0; l < g.num_levels; ++l) {
+    const int hw = g.h[l] * g.w[l];
+    if (hw & 3) return false;
+    tt->tpl[l] = (hw + kTilePts - 1) / kTilePts;
+    tt->toff[l] = t;
+    t += tt->tpl[l];
+  }
+  for (int l = g.num_levels; l <= RADET_MAX_LEVELS; ++l) tt->toff[l] = t;
+  for (int l = g.num_levels; l < RADET_MAX_LEVELS; ++l) tt->tpl[l] = 0;
+  const int64_t total = (int64_t)B * t;
+  if (total > (1ll << 30)) return false;
+  const int64_t slots = (int64_t)kSMs * 8;
+  *blocks = (int)(total < slots ? total : slots);
+  return true;
+}
+
 extern "C" size_t radet_loss_workspace_bytes(const radet_grid_t* grid, int32_t batch, int32_t num_classes) {
   GridDev g;
   if (make_grid_dev(grid, &g) != RADET_OK || batch <= 0 || num_classes <= 0) return 0;
@@ -699,7 +886,11 @@ extern "C" size_t radet_loss_workspace_bytes(const radet_grid_t* grid, int32_t b
   if (dense_plan(g, batch, num_classes, &tab, &cc, &nj, &dblk) != RADET_OK) return 0;
   const int64_t n = (int64_t)batch * g.off[g.num_levels];
   const int64_t pos_blocks = (n + kPosThreads * kPosPerThread - 1) / (kPosThreads * kPosPerThread);
-  const int64_t dense_blocks = dblk;
+  TileTable tt;
+  int tma_blocks = 0;
+  tile_plan(g, batch, &tt, &tma_blocks);
+  const int64_t dense_blocks = dblk > (int)(kSMs * 8) ? dblk : (int)(kSMs * 8);   // either kernel's partial-sum slots
+  (void)tma_blocks;
   return align_up(sizeof(LossWs), 256) + align_up((size_t)pos_blocks * 6 * 8, 256) + align_up((size_t)dense_blocks * 8, 256);
 }
 
@@ -738,6 +929,10 @@ extern "C" int radet_loss_fwd_bwd(const radet_grid_t* grid, int32_t batch, int32
   int cc, nj, dblk;
   rc = dense_plan(g, batch, num_classes, &tab, &cc, &nj, &dblk);
   if (rc != RADET_OK) return rc;
+  TileTable tt;
+  int tma_blocks = 0;
+  const bool use_tma = tile_plan(g, batch, &tt, &tma_blocks);
+  if (use_tma && tma_blocks > dblk) dblk = tma_blocks;       // partial-sum slots (workspace_bytes sizes for the max)
   unsigned char* wsb = static_cast<unsigned char*>(workspace);
   LossWs* ws = reinterpret_cast<LossWs*>(wsb);
   const int64_t n = (int64_t)batch * g.off[g.num_levels];
@@ -751,6 +946,18 @@ extern "C" int radet_loss_fwd_bwd(const radet_grid_t* grid, int32_t batch, int32
     RADET_LAUNCH_CHECK();
   }
   if (!(phases & RADET_LOSS_PHASE_DENSE)) return RADET_OK;
+  if (use_tma) {
+    if (cfg->gamma == 2.0f)
+      loss_dense_tma_kernel<true><<<(unsigned)tma_blocks, kTmaThreads, 0, st>>>(g, tt, batch, num_classes, md, gd, gt_offsets, gt_labels,
+                                                                                  points_to_gt_index, points_weight, *cfg, grad_scale,
+                                                                                  ws, dense_part, losses);
+    else
+      loss_dense_tma_kernel<false><<<(unsigned)tma_blocks, kTmaThreads, 0, st>>>(g, tt, batch, num_classes, md, gd, gt_offsets, gt_labels,
+                                                                                   points_to_gt_index, points_weight, *cfg, grad_scale,
+                                                                                   ws, dense_part, losses);
+    RADET_LAUNCH_CHECK();
+    return RADET_OK;
+  }
   const unsigned dblocks = (unsigned)dblk;
   if (cfg->gamma == 2.0f)
     loss_dense_kernel<true><<<dblocks, kDenseThreads, 0, st>>>(g, tab, batch, num_classes, cc, nj, md, gd, gt_offsets, gt_bboxes,
