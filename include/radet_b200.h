@@ -30,6 +30,10 @@ extern "C" {
 #define RADET_MAX_LEVELS 8
 #define RADET_MAX_GT_PER_IMAGE 256   /* per image; masks are bit sets of 32-bit words */
 #define RADET_MAX_POSITIVE_NUM 32    /* LabelAssignment.positive_num (config: 10) */
+/* bits of radet_assign's `balance_sample` argument (a plain 0 / 1 keeps its original meaning) */
+#define RADET_ASSIGN_BALANCE 1        /* LabelAssignment.balance_sample (label_assignment.py:109-116) */
+#define RADET_ASSIGN_ADAPT_K 2        /* adapt_positive_num: per-GT positive_num = adapt_cal_k(...) (:88-95, :104-105) */
+#define RADET_ASSIGN_WEIGHT_BY_PRO 4  /* multiply_samplepro_for_weight: weight *= sample probability (:127-128) */
 #define RADET_MT_STATE_WORDS 625     /* 624 key words + position, numpy legacy MT19937 */
 
 enum {
@@ -113,11 +117,15 @@ int radet_mt19937_seed(const uint32_t* seeds, int32_t batch, uint32_t* mt_states
  *     seeds      u32   [B]             np.random.seed(seeds[b]) right before image b, or
  *     mt_states  u32   [B, 625]        full legacy state (key[624], pos); updated in place to the
  *                                      state after the call (so the host RNG can be advanced exactly)
- *   positive_num, balance_sample: LabelAssignment(positive_num, balance_sample)
+ *   positive_num, balance_sample: LabelAssignment(positive_num, balance_sample); balance_sample also carries the
+ *                      RADET_ASSIGN_* option bits.  With RADET_ASSIGN_ADAPT_K the per-GT draw count is
+ *                      int(positive_num * sum_l ratio_l * exp((max(w,h) - size_l) / (2 size_l)) + 0.5) over the levels of the
+ *                      GT's remaining candidates (float32 exp as numpy's); it must stay <= 32.
  * Outputs:
  *   points_to_gt_index int64 [B,P]  1-based GT index; -1 negative; 0 ignore   (label_assignment.py:198)
  *   points_weight      f32   [B,P]                                           (label_assignment.py:199)
- *   consumed           int32 [B]    doubles drawn from the stream; -1 if `uniforms` ran out (outputs invalid)
+ *   consumed           int32 [B]    doubles drawn from the stream; -1 if `uniforms` ran out, -2 if an adaptive
+ *                                   positive_num exceeded 32 (outputs invalid in both cases)
  * workspace: radet_assign_workspace_bytes(). */
 size_t radet_assign_workspace_bytes(const radet_grid_t* grid, int32_t batch);
 int radet_assign(const radet_grid_t* grid, int32_t batch, const int32_t* gt_offsets, const int32_t* gt_offsets_host,

@@ -144,10 +144,21 @@ def sample_cells(masks: np.ndarray, H: int, W: int, strides=STRIDES, grid_step: 
     return np.asarray(masks)[:, ys, xs].T.astype(np.float32)
 
 
+def adapt_cal_k(candidate_anchor_sizes, object_size, positive_num):
+    """LabelAssignment.adapt_cal_k (label_assignment.py:88-95); sizes float32, object_size float32 scalar."""
+    size_lvl, num_lvl = np.unique(candidate_anchor_sizes, return_counts=True)
+    ratio = num_lvl / candidate_anchor_sizes.shape[0]
+    dk = np.exp((object_size - size_lvl) / (2 * size_lvl))
+    dk = (ratio * dk).sum()
+    return int(positive_num * dk + 0.5)
+
+
 def assign_image(gt_bboxes, masks, H, W, stream, strides=STRIDES, regress_ranges=REGRESS_RANGES,
-                 positive_num=10, neg_threshold=0.2, balance_sample=True, grid_step=None):
+                 positive_num=10, neg_threshold=0.2, balance_sample=True, grid_step=None, adapt_positive_num=False,
+                 multiply_samplepro_for_weight=False, octave_base_scale=8):
     """LabelAssignment.__call__ (label_assignment.py:136-201) + random_sample (:97-131), config defaults
-    (ambiguous_sample='min_area', random_sample_by_distance=True, adapt_positive_num=False).
+    (ambiguous_sample='min_area', random_sample_by_distance=True); adapt_positive_num (:88-95, :104-107) and
+    multiply_samplepro_for_weight (:127-128) are the two optional switches of the constructor.
 
     Returns points_to_gt_index int64 [P] (1-based; -1 negative, 0 ignore), points_weight f32 [P],
     and the number of uniforms consumed.
@@ -162,6 +173,8 @@ def assign_image(gt_bboxes, masks, H, W, stream, strides=STRIDES, regress_ranges
         return idx, wts, 0
     cand = candidate_flags(gt_bboxes, H, W, strides, regress_ranges)
     cell = sample_cells(masks, H, W, strides, grid_step)
+    anchor_sizes = np.concatenate([np.full(h * w, np.float32(octave_base_scale * s), np.float32)
+                                   for (h, w), s in zip(level_shapes(H, W, strides), strides)])            # :149
     areas = (gt_bboxes[:, 2] - gt_bboxes[:, 0]) * (gt_bboxes[:, 3] - gt_bboxes[:, 1])   # f32, :156
     order = sorted(range(G), key=lambda k: areas[k])                                    # stable, :170
     for g in order:
@@ -175,19 +188,26 @@ def assign_image(gt_bboxes, masks, H, W, stream, strides=STRIDES, regress_ranges
         pro_n = pro[nonneg]
         p = pro_n / np.sum(pro_n)                                                       # :103 (f32)
         n = N.size
-        if n < positive_num:
+        k = positive_num
+        if adapt_positive_num:                                                          # :104-105
+            wh = (gt_bboxes[g, 2] - gt_bboxes[g, 0], gt_bboxes[g, 3] - gt_bboxes[g, 1])
+            k = adapt_cal_k(anchor_sizes[R], max(wh[0], wh[1]), positive_num)
+        if n < k:
             if balance_sample:
-                chosen = legacy_choice(stream, p, positive_num, True)                   # :112
+                chosen = legacy_choice(stream, p, k, True)                              # :112
             else:
                 chosen = np.arange(n)                                                   # :116
         else:
-            chosen = legacy_choice(stream, p, positive_num, False)                      # :119
+            chosen = legacy_choice(stream, p, k, False)                                 # :119
         pos, cnt = np.unique(chosen, return_counts=True)                                # :125
         sampled = np.zeros(n, bool)
         sampled[chosen] = True
+        weight = cnt.astype(np.float32)
+        if multiply_samplepro_for_weight:                                               # :127-128
+            weight *= pro_n[pos]
         idx[N[pos]] = g + 1                                                             # :193
         idx[N[~sampled]] = 0                                                            # :194
-        wts[N[pos]] = cnt.astype(np.float32)                                            # :195
+        wts[N[pos]] = weight                                                            # :195
         wts[N[~sampled]] = 0.0                                                          # :196
     return idx, wts, stream.pos - start
 

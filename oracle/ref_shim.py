@@ -277,11 +277,13 @@ def build_reference_head(num_classes=21, **tc):
     return RADetHead(train_cfg=None, test_cfg=test_cfg(**tc), **head_kwargs(num_classes))
 
 
-def build_reference_assigner():
+def build_reference_assigner(**overrides):
     install()
     from radet.datasets.pipelines.label_assignment import LabelAssignment
 
-    return LabelAssignment(**assignment_kwargs())
+    kw = assignment_kwargs()
+    kw.update(overrides)
+    return LabelAssignment(**kw)
 
 
 class BitmapMasksStandIn:

@@ -435,6 +435,7 @@ __host__ __device__ inline size_t resolve_smem_bytes(int maxG, int K, bool list_
   s += (size_t)maxG * K * 4;                // sel_pos
   s += (size_t)maxG * K;                    // sel_cnt
   s += (size_t)maxG * 4;                    // n_sel
+  s += (size_t)maxG * RADET_MAX_LEVELS * 4; // remaining candidates per (GT, level)
   s = (s + 15) & ~size_t(15);
   if (list_in_smem) s += (size_t)kListCap * 4 + (size_t)kListCap * 2;
   return s;
@@ -443,7 +444,8 @@ __host__ __device__ inline size_t resolve_smem_bytes(int maxG, int K, bool list_
 template <int W32>
 __global__ void __launch_bounds__(kResolveThreads)
 assign_resolve_kernel(GridDev grid, const int* __restrict__ gt_offsets, const float* __restrict__ gt_bboxes,
-                      const uint32_t* __restrict__ pair_bits, int maxG, int K, int balance,
+                      const uint32_t* __restrict__ pair_bits, int maxG, int Kcap /* smem stride, <= 32 */, int Kbase /* positive_num */,
+                      int flags /* RADET_ASSIGN_* */,
                       const double* __restrict__ uniforms, int n_uniform, const uint32_t* __restrict__ seeds,
                       uint32_t* __restrict__ mt_states, uint32_t* __restrict__ g_list, uint16_t* __restrict__ g_own,
                       int list_in_smem, int64_t* __restrict__ out_idx, float* __restrict__ out_w,
@@ -463,9 +465,10 @@ assign_resolve_kernel(GridDev grid, const int* __restrict__ gt_offsets, const fl
   float* s_area = reinterpret_cast<float*>(cur); cur += (size_t)maxG * 4;
   int* s_rank2gt = reinterpret_cast<int*>(cur); cur += (size_t)maxG * 4;
   int* s_nr = reinterpret_cast<int*>(cur); cur += (size_t)maxG * 4;
-  int* s_selpos = reinterpret_cast<int*>(cur); cur += (size_t)maxG * K * 4;
+  int* s_selpos = reinterpret_cast<int*>(cur); cur += (size_t)maxG * Kcap * 4;
   int* s_nsel = reinterpret_cast<int*>(cur); cur += (size_t)maxG * 4;
-  unsigned char* s_selcnt = cur; cur += (size_t)maxG * K;
+  int* s_lcnt = reinterpret_cast<int*>(cur); cur += (size_t)maxG * RADET_MAX_LEVELS * 4;   // remaining candidates per (GT, level)
+  unsigned char* s_selcnt = cur; cur += (size_t)maxG * Kcap;
   cur = smem_raw + (((size_t)(cur - smem_raw) + 15) & ~size_t(15));
   uint32_t* list;
   uint16_t* own;
@@ -486,10 +489,14 @@ assign_resolve_kernel(GridDev grid, const int* __restrict__ gt_offsets, const fl
     return;
   }
   area_ranks(gt_bboxes + 4 * (int64_t)g0, G, s_area, s_rank2gt);
+  const int balance = flags & RADET_ASSIGN_BALANCE;
+  const bool adapt = (flags & RADET_ASSIGN_ADAPT_K) != 0, mult = (flags & RADET_ASSIGN_WEIGHT_BY_PRO) != 0;
   for (int r = tid; r < G; r += kResolveThreads) {
     s_nr[r] = 0;
     s_nsel[r] = 0;
   }
+  if (adapt)
+    for (int i = tid; i < G * RADET_MAX_LEVELS; i += kResolveThreads) s_lcnt[i] = 0;
   if (tid < 8) S->F[tid] = 0u;
   __syncthreads();
 
@@ -642,6 +649,20 @@ assign_resolve_kernel(GridDev grid, const int* __restrict__ gt_offsets, const fl
         }
       }
       own[e] = (uint16_t)(r < 0 ? 0xffff : r);
+      if (adapt) {
+        // adapt_cal_k (label_assignment.py:88-95) looks at ALL remaining candidates of a GT at its turn: the point
+        // counts for every GT it is a candidate of up to and including its owner
+        const int lvl = level_of(grid, p);
+#pragma unroll
+        for (int w = 0; w < W32; ++w) {
+          uint32_t cb = pb[w];
+          while (cb) {
+            const int g_ = w * 32 + __ffs((int)cb) - 1;
+            cb &= cb - 1u;
+            if (r < 0 || g_ <= r) atomicAdd(&s_lcnt[g_ * RADET_MAX_LEVELS + lvl], 1);
+          }
+        }
+      }
       if (r >= 0) {
         atomicAdd(&s_nr[r], 1);
       } else {
@@ -661,7 +682,7 @@ assign_resolve_kernel(GridDev grid, const int* __restrict__ gt_offsets, const fl
   if (wid == 0) {
     int* s_found = S->found;
     int used = 0;
-    bool overflow = false;
+    bool overflow = false, adapt_too_large = false;
     // next `count` uniforms as 53-bit integers (bit 63 set: not of the form X/2^53 -> use the fp64 search on ux)
     double ux = 0.0;
     auto draw = [&](int count) -> unsigned long long {
@@ -684,8 +705,37 @@ assign_resolve_kernel(GridDev grid, const int* __restrict__ gt_offsets, const fl
     for (int r = 0; r < G && !overflow; ++r) {
       const int n = s_nr[r];
       if (n == 0) continue;                                         // label_assignment.py:182-183: no RNG use
-      int* selpos = s_selpos + r * K;
-      unsigned char* selcnt = s_selcnt + r * K;
+      int K = Kbase;
+      if (adapt) {                                                  // :104-105 positive_num = adapt_cal_k(...)
+        int kk = 0;
+        if (lane == 0) {
+          const float4 gb = *reinterpret_cast<const float4*>(gt_bboxes + 4 * (int64_t)(g0 + s_rank2gt[r]));
+          const float obj = fmaxf(gb.z - gb.x, gb.w - gb.y);
+          int ntot = 0;
+          for (int l = 0; l < grid.num_levels; ++l) ntot += s_lcnt[r * RADET_MAX_LEVELS + l];
+          double dk = 0.0;
+          for (int l = 0; l < grid.num_levels; ++l) {               // np.unique: ascending anchor size = ascending level
+            const int c_ = s_lcnt[r * RADET_MAX_LEVELS + l];
+            if (c_ == 0) continue;
+            const float size = __fmul_rn(grid.anchor_scale, (float)grid.stride[l]);
+            const float ex = (float)exp((double)__fdiv_rn(__fsub_rn(obj, size), __fmul_rn(2.f, size)));   // float32 np.exp
+            dk += ((double)c_ / (double)ntot) * (double)ex;
+          }
+          kk = (int)((double)Kbase * dk + 0.5);
+        }
+        K = __shfl_sync(kFull, kk, 0);
+        if (K > Kcap) {                                             // more draws than lanes / slots: not representable here
+          overflow = true;
+          adapt_too_large = true;
+          break;
+        }
+        if (K == 0) {                                               // choice(size=0): no draws, everything non-neg is ignored
+          if (lane == 0) s_nsel[r] = 0;
+          continue;
+        }
+      }
+      int* selpos = s_selpos + r * Kcap;
+      unsigned char* selcnt = s_selcnt + r * Kcap;
       if (n < K) {
         if (!balance) {                                             // :116 chosen = arange(n)
           if (lane == 0) s_nsel[r] = -1;
@@ -738,7 +788,7 @@ assign_resolve_kernel(GridDev grid, const int* __restrict__ gt_offsets, const fl
       }
       __syncwarp();
     }
-    if (lane == 0) consumed[b] = overflow ? -1 : used;
+    if (lane == 0) consumed[b] = adapt_too_large ? -2 : (overflow ? -1 : used);
     RESOLVE_DBG(4);
     if (dbg && lane == 0) {
       dbg[(int64_t)blockIdx.x * 16 + 8] = G;
@@ -757,8 +807,11 @@ assign_resolve_kernel(GridDev grid, const int* __restrict__ gt_offsets, const fl
     if (s_nr[r] == 0) continue;
     const int gt1 = s_rank2gt[r] + 1;
     const int nsel = s_nsel[r];
-    const int* selpos = s_selpos + r * K;
-    const unsigned char* selcnt = s_selcnt + r * K;
+    const int* selpos = s_selpos + r * Kcap;
+    const unsigned char* selcnt = s_selcnt + r * Kcap;
+    // multiply_sample_pro_for_weight (:127-128): binary masks give pro = 1 for a visible point, clip(min=1e-8) otherwise
+    // (a GT sampling from its fallback set has only such points)
+    const float pro = (mult && ((S->F[r >> 5] >> (r & 31)) & 1u)) ? 1e-8f : 1.0f;
     int running = 0;
     for (int base = 0; base < M; base += 32) {
       const int e = base + lane;
@@ -772,7 +825,7 @@ assign_resolve_kernel(GridDev grid, const int* __restrict__ gt_offsets, const fl
           if (selpos[j] == mpos) cnt = selcnt[j];
         const int p = (int)list[e];
         idx[p] = cnt > 0 ? gt1 : 0;          // label_assignment.py:193-194
-        wt[p] = (float)cnt;                  // :195-196
+        wt[p] = __fmul_rn((float)cnt, pro);  // :195-196, :127-128
       }
       running += __popc(ball);
     }
@@ -885,7 +938,8 @@ extern "C" int radet_assign(const radet_grid_t* grid, int32_t batch, const int32
   uint32_t* states_arg = seeds ? seeded_states : mt_states;
   const bool list_in_smem = P <= kListCap;
   const int mg = maxG > 0 ? maxG : 1;
-  const size_t rs = resolve_smem_bytes(mg, positive_num, list_in_smem);
+  const int kcap = (balance_sample & RADET_ASSIGN_ADAPT_K) ? RADET_MAX_POSITIVE_NUM : positive_num;
+  const size_t rs = resolve_smem_bytes(mg, kcap, list_in_smem);
 #define RADET_ASSIGN_LAUNCH(WW)                                                                                          \
   do {                                                                                                                   \
     cudaFuncSetAttribute(assign_pairs_kernel<WW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pair_smem);          \
@@ -894,8 +948,9 @@ extern "C" int radet_assign(const radet_grid_t* grid, int32_t batch, const int32
                                                                      seeds, seeded_states, pair_blocks);                 \
     RADET_LAUNCH_CHECK();                                                                                                \
     cudaFuncSetAttribute(assign_resolve_kernel<WW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rs);               \
-    assign_resolve_kernel<WW><<<batch, kResolveThreads, rs, st>>>(g, gt_offsets, gt_bboxes, pair_bits, mg, positive_num, \
-                                                                   balance_sample, uniforms, n_uniform, nullptr,          \
+    assign_resolve_kernel<WW><<<batch, kResolveThreads, rs, st>>>(g, gt_offsets, gt_bboxes, pair_bits, mg, kcap,          \
+                                                                   positive_num, balance_sample, uniforms, n_uniform,     \
+                                                                   nullptr,                                               \
                                                                    states_arg,                                            \
                                                                    g_list, g_own, list_in_smem ? 1 : 0,                  \
                                                                    points_to_gt_index, points_weight, consumed,          \

@@ -116,9 +116,11 @@ def seed_states(seeds: torch.Tensor) -> torch.Tensor:
 def assign(geom: Geometry, level_shapes, gt_counts: Sequence[int], gt_bboxes: torch.Tensor, mask_bits: torch.Tensor,
            mask_hw: Tuple[int, int], *, uniforms: Optional[torch.Tensor] = None, seeds: Optional[torch.Tensor] = None,
            mt_states: Optional[torch.Tensor] = None, positive_num: int = 10, balance_sample: bool = True,
-           gt_offsets: Optional[Tuple[np.ndarray, torch.Tensor]] = None, out=None):
+           gt_offsets: Optional[Tuple[np.ndarray, torch.Tensor]] = None, out=None, adapt_positive_num: bool = False,
+           multiply_samplepro_for_weight: bool = False):
     """Batched LabelAssignment (label_assignment.py:136-201).  Returns points_to_gt_index int64 [B,P],
-    points_weight f32 [B,P], consumed int32 [B] (written into `out` = (idx, w, consumed) when given)."""
+    points_weight f32 [B,P], consumed int32 [B] (written into `out` = (idx, w, consumed) when given; -1 = the uniforms
+    ran out, -2 = an adaptive positive_num above 32)."""
     _require_cuda(gt_bboxes, "gt_bboxes")
     dev = gt_bboxes.device
     off_h, off_d = gt_offsets if gt_offsets is not None else offsets_of(gt_counts, dev)
@@ -145,7 +147,8 @@ def assign(geom: Geometry, level_shapes, gt_counts: Sequence[int], gt_bboxes: to
         seeds = seeds.to(torch.int32)
     check(lib.radet_assign(ctypes.byref(grid), B, _ptr(off_d), off_h.ctypes.data_as(ctypes.POINTER(ctypes.c_int32)),
                            _ptr(gt_bboxes.contiguous()), _ptr(mask_bits), mask_hw[0], mask_hw[1], geom.mask_step,
-                           _ptr(uniforms), n_uniform, _ptr(seeds), _ptr(mt_states), positive_num, int(bool(balance_sample)),
+                           _ptr(uniforms), n_uniform, _ptr(seeds), _ptr(mt_states), positive_num,
+                           int(bool(balance_sample)) | (2 if adapt_positive_num else 0) | (4 if multiply_samplepro_for_weight else 0),
                            _ptr(idx), _ptr(w), _ptr(consumed), _ptr(ws), ws.numel(), _stream()), "radet_assign")
     return idx, w, consumed
 

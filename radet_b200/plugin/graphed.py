@@ -136,6 +136,8 @@ class GraphedHotPath:
         main.wait_stream(s_seed)
         idx, w, consumed = F.assign(self.geom, self.shapes, None, d["gt_bboxes"], bits, (self.gh, self.gw), mt_states=states,
                                     positive_num=self.assigner.positive_num, balance_sample=self.assigner.balance_sample,
+                                    adapt_positive_num=self.assigner.adapt_positive_num,
+                                    multiply_samplepro_for_weight=self.assigner.multiply_sample_pro_for_weight,
                                     gt_offsets=off)
         losses, grads = F.loss_fwd_bwd(self.geom, self.C, cls, bbox, iou, None, d["gt_bboxes"], d["gt_labels"], idx, w,
                                        self.head.loss_cfg, gt_offsets=off)

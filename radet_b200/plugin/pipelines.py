@@ -30,10 +30,9 @@ class LabelAssignment:
                  random_sample_by_distance=True, device=None):
         assert len(strides) == len(regress_ranges)
         # configuration surface implemented on the device (include/radet_b200.h, radet_assign)
-        if adapt_positive_num or multiply_samplepro_for_weight or not random_sample_by_distance:
-            raise NotImplementedError("radet_b200.LabelAssignment implements the shipped configuration: "
-                                      "adapt_positive_num=False, multiply_samplepro_for_weight=False, "
-                                      "random_sample_by_distance=True")
+        if not random_sample_by_distance:
+            raise NotImplementedError("radet_b200.LabelAssignment implements random_sample_by_distance=True (every shipped "
+                                      "config); the unweighted np.random.choice / permutation streams are not on the device")
         if ambiguous_sample != 'min_area':
             # 'max_dis' references an undefined variable in the reference (label_assignment.py:158-161) and crashes there
             raise NotImplementedError("ambiguous_sample must be 'min_area'")
@@ -97,7 +96,9 @@ class LabelAssignment:
             boxes = torch.zeros((0, 4), dtype=torch.float32, device=dev)
             bits = torch.zeros((0, gh, (gw + 31) // 32), dtype=torch.int32, device=dev)
         return F.assign(self.geom, shapes, counts, boxes, bits, (gh, gw), seeds=seeds, mt_states=mt_states, uniforms=uniforms,
-                        positive_num=self.positive_num, balance_sample=self.balance_sample)
+                        positive_num=self.positive_num, balance_sample=self.balance_sample,
+                        adapt_positive_num=self.adapt_positive_num,
+                        multiply_samplepro_for_weight=self.multiply_sample_pro_for_weight)
 
     # ------------------------------------------------------------------ reference contract
     def __call__(self, results):
@@ -115,6 +116,9 @@ class LabelAssignment:
         st[624] = pos
         st_d = torch.from_numpy(st.view(np.int32)).to(dev).reshape(1, 625)
         idx, w, consumed = self.assign_batch([(image_h, image_w)], [gt_bboxes], [grid], mt_states=st_d)
+        if int(consumed[0]) < 0:
+            raise RadetError("LabelAssignment: adaptive positive_num above 32 for a ground truth of this image "
+                             "(radet_assign consumed = %d)" % int(consumed[0]))
         st_back = st_d.cpu().numpy().view(np.uint32).reshape(625)
         np.random.set_state((kind, st_back[:624].copy(), int(st_back[624]), has_gauss, cached))
         results['points_to_gt_index'] = idx[0].cpu().numpy()

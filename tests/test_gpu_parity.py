@@ -566,3 +566,53 @@ def test_get_bboxes_without_nms_rescale_and_empty():
     for b in range(len(batch)):
         k = int(num[b])
         assert torch.equal(cats3[b, :k], cats[b, :k]) and torch.equal(rows3[b, :k], rows[b, :k])
+
+
+# ------------------------------------------------------------------------------------------------ LabelAssignment options
+from tests.test_oracle_golden import ASSIGN_OPT_IMAGES, ASSIGN_OPT_VARIANTS  # noqa: E402
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("variant", sorted(ASSIGN_OPT_VARIANTS))
+def test_assignment_options_bit_exact(variant):
+    """adapt_positive_num / multiply_samplepro_for_weight / balance_sample=False (label_assignment.py:88-95,104-116,127-128):
+    indices, weights and the stream position bit-exact against the reference's golden output, all images in one launch."""
+    g = hp.load("assign_opts.npz")
+    kw = dict(ASSIGN_OPT_VARIANTS[variant])
+    for key in ("cfg2", "cfg3", "cfg5"):
+        ids = [i for k, i in ASSIGN_OPT_IMAGES if k == key]
+        wl = syn.WORKLOADS[key]
+        batch = syn.make_batch(wl, len(ids), ids[0])
+        shapes = GEOM.level_shapes(wl.H, wl.W)
+        counts = [im.gt_bboxes.shape[0] for im in batch]
+        grids = torch.from_numpy(np.concatenate([syn.sample_grid(im.masks) for im in batch])).to(DEV)
+        gh, gw = grids.shape[1:]
+        boxes = torch.from_numpy(np.concatenate([im.gt_bboxes for im in batch])).to(DEV)
+        seeds = torch.tensor([im.seed for im in batch], dtype=torch.int32, device=DEV)
+        idx, w, used = F.assign(GEOM, shapes, counts, boxes, F.pack_masks(grids, 1, gh, gw), (gh, gw), seeds=seeds,
+                                balance_sample=kw.get("balance_sample", True), adapt_positive_num=kw.get("adapt_positive_num", False),
+                                multiply_samplepro_for_weight=kw.get("multiply_samplepro_for_weight", False))
+        idx, w, used = idx.cpu().numpy(), w.cpu().numpy(), used.cpu().numpy()
+        for b, i in enumerate(ids):
+            name = f"{variant}/{key}_{i}"
+            assert np.array_equal(idx[b], g[f"{name}/idx"].astype(np.int64)), name
+            assert np.array_equal(w[b].view(np.uint32), g[f"{name}/w"].view(np.uint32)), name
+            rs = np.random.RandomState(batch[b].seed)
+            rs.random_sample(int(used[b]))
+            assert np.array_equal(rs.random_sample(2), g[f"{name}/tail"]), name
+
+
+@pytest.mark.gpu
+def test_label_assignment_pipeline_with_options():
+    """The PIPELINES entry with the optional switches on: same results dict as the reference, numpy stream advanced alike."""
+    g = hp.load("assign_opts.npz")
+    la = P.LabelAssignment(anchor_generator_cfg=dict(type="AnchorGenerator", ratios=[1.0], octave_base_scale=8, scales_per_octave=1,
+                                                     strides=[8, 16, 32, 64, 128]),
+                           neg_threshold=0.2, positive_num=10, adapt_positive_num=True, balance_sample=True,
+                           multiply_samplepro_for_weight=True)
+    im = syn.make_batch(syn.WORKLOADS["cfg3"], 1, 1)[0]
+    np.random.seed(im.seed)
+    res = la(dict(img_shape=(im.H, im.W, 3), gt_bboxes=im.gt_bboxes, gt_labels=im.gt_labels, distance_maps=im.masks))
+    assert np.array_equal(res["points_to_gt_index"], g["both/cfg3_1/idx"].astype(np.int64))
+    assert np.array_equal(res["points_weight"], g["both/cfg3_1/w"])
+    assert np.array_equal(np.random.random_sample(2), g["both/cfg3_1/tail"])

@@ -72,7 +72,9 @@ def test_detect_config_reads_the_reference_test_cfg():
 
 def test_unsupported_surface_fails_loudly():
     with pytest.raises(NotImplementedError):
-        P.build_from_cfg(dict(ASSIGN_CFG, adapt_positive_num=True), P.PIPELINES)
+        P.build_from_cfg(dict(ASSIGN_CFG, random_sample_by_distance=False), P.PIPELINES)
+    la = P.build_from_cfg(dict(ASSIGN_CFG, adapt_positive_num=True, multiply_samplepro_for_weight=True), P.PIPELINES)
+    assert la.adapt_positive_num and la.multiply_sample_pro_for_weight        # both switches are on the device now
     with pytest.raises(NotImplementedError):
         P.build_from_cfg(dict(ASSIGN_CFG, ambiguous_sample='max_dis'), P.PIPELINES)     # crashes in the reference too
     with pytest.raises(NotImplementedError):

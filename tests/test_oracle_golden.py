@@ -165,3 +165,24 @@ def test_standalone_bce_onehot_matches_reference():
                                      dtype="float32")
     np.testing.assert_allclose(loss, g["bce/onehot/loss"], rtol=2e-6)
     np.testing.assert_allclose(grad, g["bce/onehot/grad"], rtol=2e-5, atol=1e-8)
+
+
+ASSIGN_OPT_VARIANTS = {"adapt": dict(adapt_positive_num=True), "mult": dict(multiply_samplepro_for_weight=True),
+                       "both": dict(adapt_positive_num=True, multiply_samplepro_for_weight=True),
+                       "adapt_nobal": dict(adapt_positive_num=True, balance_sample=False)}
+ASSIGN_OPT_IMAGES = [("cfg2", i) for i in range(4)] + [("cfg3", i) for i in range(3)] + [("cfg5", i) for i in range(2)]
+
+
+@pytest.mark.parametrize("variant", sorted(ASSIGN_OPT_VARIANTS))
+def test_assignment_options_match_reference_bit_exact(variant):
+    """adapt_positive_num (label_assignment.py:88-95) / multiply_samplepro_for_weight (:127-128) / balance_sample=False."""
+    g = hp.load("assign_opts.npz")
+    for key, i in ASSIGN_OPT_IMAGES:
+        im = syn.make_batch(syn.WORKLOADS[key], 1, i)[0]
+        idx, w, used = orc.assign_image_seeded(im.gt_bboxes, im.masks, im.H, im.W, im.seed, **ASSIGN_OPT_VARIANTS[variant])
+        name = f"{variant}/{key}_{i}"
+        assert np.array_equal(idx, g[f"{name}/idx"].astype(np.int64)), name
+        assert np.array_equal(w, g[f"{name}/w"]), name
+        rs = np.random.RandomState(im.seed)
+        rs.random_sample(used)
+        assert np.array_equal(rs.random_sample(2), g[f"{name}/tail"]), name
