@@ -720,6 +720,25 @@ def run_e2e(args, wl, B, host_sets, dev, P, F, world):
     sink = 0.0
     for i in range(2 * NP):
         sink += float(pipes[i % NP].run(arenas[i % len(arenas)])["losses"][0])
+    # pipelined launches must return what one-at-a-time runs return (every instance owns its streams and workspaces)
+    snap = lambda res: {k: v.clone() for k, v in res.items()}
+    serial = [snap(pipes[0].run(a)) for a in arenas]
+    m = 4 * NP * len(arenas)
+    for i in range(m + NP - 1):
+        if i < m:
+            pipes[i % NP].launch(arenas[i % len(arenas)])
+        j = i - (NP - 1)
+        if j >= 0:
+            res = pipes[j % NP].wait()
+            want = serial[j % len(arenas)]
+            nd = want["num"]
+            for k in ("losses", "num", "consumed"):
+                if not torch.equal(res[k], want[k]):
+                    raise RuntimeError(f"e2e: pipelined batch {j} differs from its serial run in `{k}`")
+            for b_ in range(B):
+                kk = int(nd[b_])
+                if not (torch.equal(res["dets"][b_, :kk], want["dets"][b_, :kk]) and torch.equal(res["labels"][b_, :kk], want["labels"][b_, :kk])):
+                    raise RuntimeError(f"e2e: pipelined batch {j} differs from its serial run in the detections of image {b_}")
     if world > 1:
         dist.barrier()
     torch.cuda.synchronize()
@@ -737,6 +756,7 @@ def run_e2e(args, wl, B, host_sets, dev, P, F, world):
     out = {"value": world * B * n / dt, "unit": "images/s", "h2d_bytes_per_step": int(h2d_mean),
            "d2h_bytes_per_step": int(pipes[0].d2h_bytes), "steps": n, "ms_per_step": 1e3 * dt / n,
            "h2d_GBps_per_gpu": h2d_mean * n / dt / 1e9,
+           "pipelined_check": f"{4 * NP * len(arenas)} pipelined batches bit-identical to their serial runs (losses, detections)",
            "timing": "host wall clock between device synchronisations (max over ranks)",
            "api": "plugin.GraphedHotPath.launch/wait: pinned host arena -> H2D -> CUDA graph (seed | pack+assign+loss fwd/bwd | "
                   f"decode+vote-NMS) -> D2H of losses/detections; {NP} instances in flight; the step is bound by the "
