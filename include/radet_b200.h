@@ -268,6 +268,14 @@ int radet_get_candidates(const radet_grid_t* grid, int32_t batch, int32_t num_cl
                          const int32_t* img_shapes, const float* scale_factors, const radet_detect_cfg_t* cfg, float* rows,
                          int64_t* labels, int32_t* num_rows, void* workspace, size_t workspace_bytes, void* stream);
 
+/* Post-NMS formatting, batched on the device.  Replaces bbox2result (core/bbox/transforms.py:99-116): per image the
+ * detections regrouped by class, original (score) order kept inside a class.  out f32 [batch][max_rows][5] holds the
+ * class-sorted rows, class_offsets int32 [batch][num_classes+1] the row range of each class (rows with a label
+ * outside [0,num_classes) are dropped, as `labels == i` never selects them).  xywh != 0 additionally rewrites the box
+ * as (x1, y1, x2-x1, y2-y1) = BOPDataset.xyxy2xywh used by _bop_det2json (datasets/bop.py:99-118).  max_rows <= 1024. */
+int radet_bbox2result(const float* dets, const int64_t* labels, const int32_t* num, int32_t batch, int32_t max_rows,
+                      int32_t num_classes, int32_t xywh, float* out, int32_t* class_offsets, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

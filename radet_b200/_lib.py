@@ -69,6 +69,7 @@ _SIGS = {
                                  c_int32, c_int32, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                                  c_size_t, c_void_p]),
     "radet_get_bboxes_workspace_bytes": (c_size_t, [POINTER(Grid), c_int32, c_int32, POINTER(DetectCfg)]),
+    "radet_bbox2result": (c_int32, [c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_int32, c_int32, c_void_p, c_void_p, c_void_p]),
     "radet_candidates_capacity": (c_int64, [POINTER(Grid), c_int32, c_int32]),
     "radet_get_candidates": (c_int32, [POINTER(Grid), c_int32, c_int32, POINTER(Maps), c_void_p, c_void_p, POINTER(DetectCfg),
                                        c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),

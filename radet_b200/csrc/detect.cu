@@ -1096,6 +1096,47 @@ extern "C" int radet_get_bboxes(const radet_grid_t* grid, int32_t batch, int32_t
   return RADET_OK;
 }
 
+// bbox2result (core/bbox/transforms.py:99-116), batched: per image, detections regrouped by class in their original
+// (score) order.  One warp per image; rows <= 1024.
+__global__ void bbox2result_kernel(const float* __restrict__ dets, const int64_t* __restrict__ labels,
+                                   const int* __restrict__ num, int max_rows, int C, int xywh, float* __restrict__ out,
+                                   int* __restrict__ class_offsets) {
+  const int b = blockIdx.x, lane = threadIdx.x;
+  const int n = min(num[b], max_rows);
+  const float* d = dets + (int64_t)b * max_rows * 5;
+  const int64_t* lb = labels + (int64_t)b * max_rows;
+  float* o = out + (int64_t)b * max_rows * 5;
+  int* off = class_offsets + (int64_t)b * (C + 1);
+  // offsets: exclusive prefix of the class histogram (serial over C per lane-strided chunk is enough at these sizes)
+  for (int c = lane; c <= C; c += 32) {
+    int before = 0;
+    for (int i = 0; i < n; ++i) before += (lb[i] >= 0 && lb[i] < c) ? 1 : 0;
+    off[c] = before;
+  }
+  for (int i = lane; i < n; i += 32) {
+    const int64_t c = lb[i];
+    if (c < 0 || c >= C) continue;                 // labels outside [0, C) appear in no class list (labels == i never true)
+    int pos = 0;
+    for (int j = 0; j < n; ++j) pos += (lb[j] >= 0 && (lb[j] < c || (lb[j] == c && j < i))) ? 1 : 0;
+    float x1 = d[i * 5 + 0], y1 = d[i * 5 + 1], x2 = d[i * 5 + 2], y2 = d[i * 5 + 3];
+    if (xywh) {                                    // BOPDataset.xyxy2xywh (datasets/bop.py): [x1, y1, x2 - x1, y2 - y1]
+      x2 = __fsub_rn(x2, x1);
+      y2 = __fsub_rn(y2, y1);
+    }
+    o[pos * 5 + 0] = x1; o[pos * 5 + 1] = y1; o[pos * 5 + 2] = x2; o[pos * 5 + 3] = y2; o[pos * 5 + 4] = d[i * 5 + 4];
+  }
+}
+
+extern "C" int radet_bbox2result(const float* dets, const int64_t* labels, const int32_t* num, int32_t batch, int32_t max_rows,
+                                 int32_t num_classes, int32_t xywh, float* out, int32_t* class_offsets, void* stream) {
+  if (batch == 0) return RADET_OK;
+  if (batch < 0 || max_rows < 0 || num_classes <= 0 || !dets || !labels || !num || !out || !class_offsets) return RADET_E_BADARG;
+  if (max_rows > 1024) return RADET_E_UNSUPPORTED;
+  bbox2result_kernel<<<batch, 32, 0, (cudaStream_t)stream>>>(dets, labels, num, max_rows, num_classes, xywh, out, class_offsets);
+  RADET_LAUNCH_CHECK();
+  return RADET_OK;
+}
+
 // radet_head.py:165-169 (with_nms=False): select -> per-level top-k / class bins -> emit
 extern "C" int radet_get_candidates(const radet_grid_t* grid, int32_t batch, int32_t num_classes, const radet_maps_t* maps,
                                     const int32_t* img_shapes, const float* scale_factors, const radet_detect_cfg_t* cfg,

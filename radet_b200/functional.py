@@ -498,3 +498,18 @@ def get_candidates(geom: Geometry, num_classes: int, cls, bbox, iou, img_shapes:
                                    ctypes.byref(ccfg), _ptr(rows), _ptr(labels), _ptr(num), _ptr(ws), ws.numel(), _stream()),
           "radet_get_candidates")
     return rows, labels, num
+
+
+def bbox2result_batch(dets: torch.Tensor, labels: torch.Tensor, num: torch.Tensor, num_classes: int, xywh: bool = False):
+    """Batched bbox2result (core/bbox/transforms.py:99-116) on the device: dets [B,max,5], labels [B,max], num [B] ->
+    class-sorted rows [B,max,5] and class offsets int32 [B,C+1] (one D2H copy then serves every per-class slice)."""
+    _require_cuda(dets, "dets")
+    B, mx = int(dets.shape[0]), int(dets.shape[1])
+    dets = dets.contiguous().float()
+    labels = labels.contiguous().to(torch.int64)
+    num = num.contiguous().to(torch.int32)
+    out = torch.empty_like(dets)
+    off = torch.empty((B, num_classes + 1), dtype=torch.int32, device=dets.device)
+    check(_lib.load().radet_bbox2result(_ptr(dets), _ptr(labels), _ptr(num), B, mx, num_classes, int(bool(xywh)), _ptr(out), _ptr(off),
+                                        _stream()), "radet_bbox2result")
+    return out, off

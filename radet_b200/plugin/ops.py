@@ -98,3 +98,22 @@ def batched_nms(boxes, scores, idxs, nms_cfg, class_agnostic=False):
     if not on_gpu:
         dets, keep = dets.cpu(), keep.cpu()
     return dets, keep
+
+
+def bbox2result(bboxes, labels, num_classes):
+    """bbox2result (core/bbox/transforms.py:99-116): `[bboxes[labels == i, :] for i in range(num_classes)]` as numpy
+    arrays, computed as one class-sort on the device and one copy back (CPU tensors / numpy are staged like vote_nms)."""
+    if bboxes.shape[0] == 0:
+        return [np.zeros((0, 5), dtype=np.float32) for _ in range(num_classes)]
+    b = _stage(bboxes, torch.float32)[0].reshape(1, -1, 5)
+    l = _stage(labels, torch.int64)[0].reshape(1, -1)
+    n = torch.tensor([b.shape[1]], dtype=torch.int32, device=b.device)
+    return bbox2result_batch(b, l, n, num_classes)[0]
+
+
+def bbox2result_batch(dets, labels, num, num_classes, xywh=False):
+    """Batched form for the [B,max,5] / [B,max] / [B] outputs of `functional.get_bboxes` / `GraphedHotPath`:
+    list over images of the reference's per-class list.  xywh=True gives BOPDataset.xyxy2xywh boxes (bop.py:99-118)."""
+    out, off = F.bbox2result_batch(dets, labels, num, num_classes, xywh)
+    out, off = out.cpu().numpy(), off.cpu().numpy()
+    return [[out[i, off[i, c]:off[i, c + 1]] for c in range(num_classes)] for i in range(out.shape[0])]

@@ -616,3 +616,32 @@ def test_label_assignment_pipeline_with_options():
     assert np.array_equal(res["points_to_gt_index"], g["both/cfg3_1/idx"].astype(np.int64))
     assert np.array_equal(res["points_weight"], g["both/cfg3_1/w"])
     assert np.array_equal(np.random.random_sample(2), g["both/cfg3_1/tail"])
+
+
+# ------------------------------------------------------------------------------------------------ bbox2result
+@pytest.mark.gpu
+def test_bbox2result_matches_reference_semantics():
+    """core/bbox/transforms.py:99-116: `[bboxes[labels == i, :] for i in range(num_classes)]`; batched + xywh variant."""
+    rs = np.random.RandomState(5)
+    B, mx, C = 3, 100, 21
+    dets = rs.uniform(0, 600, (B, mx, 5)).astype(np.float32)
+    labels = rs.randint(0, C, (B, mx)).astype(np.int64)
+    labels[0, :5] = C                                   # out-of-range labels appear in no class list
+    num = np.array([100, 37, 0], np.int32)
+    res = P.ops.bbox2result_batch(torch.from_numpy(dets).to(DEV), torch.from_numpy(labels).to(DEV), torch.from_numpy(num).to(DEV), C)
+    resx = P.ops.bbox2result_batch(torch.from_numpy(dets).to(DEV), torch.from_numpy(labels).to(DEV), torch.from_numpy(num).to(DEV), C,
+                                   xywh=True)
+    for b in range(B):
+        d, l = dets[b, :num[b]], labels[b, :num[b]]
+        want = [d[l == i, :] for i in range(C)]
+        assert len(res[b]) == C
+        for i in range(C):
+            assert np.array_equal(res[b][i], want[i]), (b, i)
+            w = want[i].copy()
+            w[:, 2] = want[i][:, 2] - want[i][:, 0]
+            w[:, 3] = want[i][:, 3] - want[i][:, 1]
+            assert np.array_equal(resx[b][i], w)
+    single = P.ops.bbox2result(torch.from_numpy(dets[1, :37]), torch.from_numpy(labels[1, :37]), C)      # CPU tensors are staged
+    assert all(np.array_equal(a, d_) for a, d_ in zip(single, [dets[1, :37][labels[1, :37] == i] for i in range(C)]))
+    empty = P.ops.bbox2result(torch.zeros((0, 5)), torch.zeros((0,), dtype=torch.int64), C)
+    assert len(empty) == C and all(e.shape == (0, 5) for e in empty)
