@@ -645,3 +645,101 @@ def test_bbox2result_matches_reference_semantics():
     assert all(np.array_equal(a, d_) for a, d_ in zip(single, [dets[1, :37][labels[1, :37] == i] for i in range(C)]))
     empty = P.ops.bbox2result(torch.zeros((0, 5)), torch.zeros((0,), dtype=torch.int64), C)
     assert len(empty) == C and all(e.shape == (0, 5) for e in empty)
+
+
+# ------------------------------------------------------------------------------------------------ full BASELINE sizes
+def _device_assign(wl, batch, **kw):
+    shapes = GEOM.level_shapes(wl.H, wl.W)
+    counts = [im.gt_bboxes.shape[0] for im in batch]
+    grids = torch.from_numpy(np.concatenate([syn.sample_grid(im.masks) for im in batch])).to(DEV)
+    gh, gw = grids.shape[1:]
+    boxes = torch.from_numpy(np.concatenate([im.gt_bboxes for im in batch])).to(DEV)
+    seeds = torch.tensor([im.seed for im in batch], dtype=torch.int32, device=DEV)
+    idx, w, used = F.assign(GEOM, shapes, counts, boxes, F.pack_masks(grids, 1, gh, gw), (gh, gw), seeds=seeds, **kw)
+    return shapes, counts, boxes, idx, w, used
+
+
+@pytest.mark.gpu
+def test_full_size_cfg5_assignment_and_loss_properties():
+    """cfg5 at its full per-GPU size (16 images of 1280x960, C=30, 5-30 GT): properties that do not need the oracle.
+    Assignment: index range, weights of a GT's positives sum to positive_num, ignored weight 0 / negative weight 1,
+    one launch of 16 == two launches of 8 (images shard without a collective).  Loss: the batch loss is the
+    normaliser-weighted combination of the half-batch losses, gradients scale linearly with the upstream gradient."""
+    wl = syn.WORKLOADS["cfg5"]
+    batch = syn.make_batch(wl, wl.B)
+    shapes, counts, boxes, idx, w, used = _device_assign(wl, batch)
+    h = wl.B // 2
+    _, c0, b0, idx0, w0, used0 = _device_assign(wl, batch[:h])
+    _, c1, b1, idx1, w1, used1 = _device_assign(wl, batch[h:])
+    assert torch.equal(idx, torch.cat([idx0, idx1])) and torch.equal(w, torch.cat([w0, w1])) and torch.equal(used, torch.cat([used0, used1]))
+    idx_h, w_h = idx.cpu().numpy(), w.cpu().numpy()
+    for b, im in enumerate(batch):
+        G = im.gt_bboxes.shape[0]
+        assert idx_h[b].min() >= -1 and idx_h[b].max() <= G
+        assert np.all(w_h[b][idx_h[b] == -1] == 1.0) and np.all(w_h[b][idx_h[b] == 0] == 0.0)
+        for g in range(1, G + 1):
+            s = w_h[b][idx_h[b] == g].sum()
+            assert s in (0.0, 10.0), (b, g, s)                        # a GT either found no candidate or drew 10 (with multiplicity)
+        assert int(used[b]) >= 10 * int((np.bincount(idx_h[b][idx_h[b] > 0], minlength=G + 1)[1:] > 0).sum())
+    # ---- loss at the 119.5 MB shape (device-generated head outputs: values are irrelevant for the properties)
+    g = torch.Generator(device=DEV).manual_seed(7)
+    cls = [torch.randn((wl.B, wl.C, hh, ww), device=DEV, generator=g) - 4.6 for hh, ww in shapes]
+    bbox = [torch.relu(torch.randn((wl.B, 4, hh, ww), device=DEV, generator=g) + 1) for hh, ww in shapes]
+    iou = [torch.randn((wl.B, 1, hh, ww), device=DEV, generator=g) for hh, ww in shapes]
+    labels = torch.from_numpy(np.concatenate([im.gt_labels for im in batch])).to(DEV)
+    lcfg = F.LossConfig()
+    losses, grads = F.loss_fwd_bwd(GEOM, wl.C, cls, bbox, iou, counts, boxes, labels, idx, w, lcfg)
+    losses = losses.cpu().numpy().astype(np.float64)
+    gsum = [float(t.double().abs().sum()) for t in grads[0]]
+    parts = []
+    for sl, cc, bb, ii, ww_ in ((slice(0, h), c0, b0, idx0, w0), (slice(h, None), c1, b1, idx1, w1)):
+        lab = torch.from_numpy(np.concatenate([im.gt_labels for im in batch[sl]])).to(DEV)
+        l_, _ = F.loss_fwd_bwd(GEOM, wl.C, [t[sl].contiguous() for t in cls], [t[sl].contiguous() for t in bbox],
+                               [t[sl].contiguous() for t in iou], cc, bb, lab, ii, ww_, lcfg)
+        parts.append(l_.cpu().numpy().astype(np.float64))
+    n0, n1 = parts[0][3], parts[1][3]
+    assert losses[3] == n0 + n1                                          # num_pos adds up exactly (sums of small integers)
+    comb = (parts[0][0] * (n0 + h) + parts[1][0] * (n1 + h)) / (n0 + n1 + wl.B)    # loss_cls: avg_factor = num_pos + B
+    assert abs(comb - losses[0]) <= 2e-6 * abs(losses[0])
+    comb_iou = (parts[0][2] * n0 + parts[1][2] * n1) / (n0 + n1)          # loss_iou: avg_factor = num_pos
+    assert abs(comb_iou - losses[2]) <= 2e-6 * abs(losses[2])
+    up = torch.tensor([2.0, 4.0, 0.5], device=DEV)                        # powers of two: scaling is exact
+    _, g2 = F.loss_fwd_bwd(GEOM, wl.C, cls, bbox, iou, counts, boxes, labels, idx, w, lcfg)
+    F.scale_grads(GEOM, wl.C, g2, up)
+    for k, f in enumerate((2.0, 4.0, 0.5)):
+        for a, b_ in zip(g2[k], grads[k]):
+            assert torch.equal(a, b_ * f)
+    assert all(s > 0 for s in gsum)
+
+
+@pytest.mark.gpu
+def test_full_size_cfg4_inference_properties():
+    """cfg4 at its full size (64 images, score_thr 0.1, nms_pre 1000, vote-NMS, max 100 per image): one launch of 64 ==
+    two launches of 32; per image scores descending, labels in range, at most max_per_img, boxes inside the image."""
+    wl = syn.WORKLOADS["cfg4"]
+    shapes = GEOM.level_shapes(wl.H, wl.W)
+    g = torch.Generator(device=DEV).manual_seed(11)
+    cls = [torch.randn((wl.B, wl.C, hh, ww), device=DEV, generator=g) * 1.3 - 4.0 for hh, ww in shapes]
+    bbox = [torch.relu(torch.randn((wl.B, 4, hh, ww), device=DEV, generator=g) * 2 + 3) for hh, ww in shapes]
+    iou = [torch.randn((wl.B, 1, hh, ww), device=DEV, generator=g) for hh, ww in shapes]
+    cfg = F.DetectConfig(score_thr=wl.score_thr, nms_pre=1000, max_per_img=100, nms_type="vote", iou_threshold=0.65,
+                         cluster_score=["cls", "iou"], vote_score=["iou", "cls"])
+    shp = torch.tensor([[wl.H, wl.W]] * wl.B, dtype=torch.int32, device=DEV)
+    sf = torch.ones((wl.B, 4), device=DEV)
+    dets, labels, num = F.get_bboxes(GEOM, wl.C, cls, bbox, iou, shp, sf, cfg, rescale=True)
+    h = wl.B // 2
+    for sl in (slice(0, h), slice(h, None)):
+        d_, l_, n_ = F.get_bboxes(GEOM, wl.C, [t[sl].contiguous() for t in cls], [t[sl].contiguous() for t in bbox],
+                                  [t[sl].contiguous() for t in iou], shp[sl].contiguous(), sf[sl].contiguous(), cfg, rescale=True)
+        assert torch.equal(n_, num[sl])
+        for b in range(h):
+            k = int(n_[b])
+            assert torch.equal(d_[b, :k].view(torch.int32), dets[sl][b, :k].view(torch.int32)) and torch.equal(l_[b, :k], labels[sl][b, :k])
+    assert int(num.max()) <= 100 and int(num.min()) > 0
+    for b in range(wl.B):
+        k = int(num[b])
+        d, l = dets[b, :k], labels[b, :k]
+        assert bool((d[:-1, 4] >= d[1:, 4]).all()) and bool((l >= 0).all()) and bool((l < wl.C).all())
+        ok = ~torch.isnan(d[:, :4]).any(1)                                 # a cluster voted from an empty sigma band is NaN, as in the reference
+        e = 1e-3                                                           # (s*x)/s of clamped coordinates may round one ulp past the border
+        assert bool((d[ok, 0] >= -e).all()) and bool((d[ok, 2] <= wl.W + e).all()) and bool((d[ok, 1] >= -e).all()) and bool((d[ok, 3] <= wl.H + e).all())
