@@ -353,7 +353,7 @@ assign_pairs_kernel(GridDev grid, const int* __restrict__ gt_offsets, const floa
 }
 
 // ------------------------------------------------------------------------------------------------ resolve + sample
-constexpr int kResolveThreads = 1024;
+constexpr int kResolveThreads = 512;
 constexpr int kListCap = 16384;  // shared-memory capacity of the candidate-point list
 
 // t = max{c in [0,m] : fl64(c/m) <= x}: position in numpy's normalised cumulative sum of m equal weights
@@ -507,7 +507,7 @@ assign_resolve_kernel(GridDev grid, const int* __restrict__ gt_offsets, const fl
   int M = 0;
   if (wid == 0) RESOLVE_DBG(0);
   if (wid == 0) {
-    // ---- warp 0 (specialised): bring up the MT19937 state while the other 31 warps resolve the claiming.
+    // ---- warp 0 (specialised): bring up the MT19937 state while the worker warps resolve the claiming.
     // np.random.seed() is an inherently sequential 624-step recurrence (~6 us); it is fully hidden here.
     if (!ub) {
       if (mt_states) {
@@ -531,12 +531,12 @@ assign_resolve_kernel(GridDev grid, const int* __restrict__ gt_offsets, const fl
     }
     RESOLVE_DBG(1);
   } else {
-    // ---- warps 1..31 (992 worker threads, named barrier 1)
+    // ---- worker warps 1.. (kWorkers threads, named barrier 1)
     const int wt_ = tid - 32;
     // 1. ordered compaction of points that are a candidate of at least one GT; everything else keeps the defaults.
     //    Worker warp ww owns a contiguous chunk of the points and walks it 32 points at a time (coalesced loads and
     //    default stores, independent iterations); lane `it` keeps the ballot word of iteration `it`, so one tile
-    //    covers up to 31 * 1024 points with a single cross-warp scan.
+    //    covers up to kWW * 1024 points with a single cross-warp scan.
     const int ww = wid - 1;
     constexpr int kWW = kWorkers / 32;
     for (int base = 0; base < P; base += kWW * 1024) {

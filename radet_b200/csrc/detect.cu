@@ -130,7 +130,7 @@ detect_select_kernel(GridDev grid, SelPlan plan, int C, MapsDev maps, float thr,
 }
 
 // ------------------------------------------------------------------------------------------------ 2. top-k + binning
-constexpr int kBinThreads = 1024;
+constexpr int kBinThreads = 512;
 
 // k-th largest of `n` unique 64-bit keys (k >= 1): returns the smallest key to keep.  Block-wide, 8-bit radix passes
 // from the top; stops as soon as the selected bucket is needed entirely.
@@ -225,7 +225,7 @@ detect_bin_kernel(BinParams p) {
 }
 
 // ------------------------------------------------------------------------------------------------ 3. per-class NMS + vote
-constexpr int kClsThreads = 512;
+constexpr int kClsThreads = 256;
 constexpr int kMaskItems = 512;                  // bit-matrix path: up to 512 boxes of one class in one image
 constexpr int kMaskWords = kMaskItems / 32;
 
@@ -421,7 +421,7 @@ __device__ float vote_axis_members(const unsigned* words, int nw, int seed, GetS
   return __fdiv_rn(fx, fs);
 }
 
-__global__ void __launch_bounds__(kClsThreads, 3)
+__global__ void __launch_bounds__(kClsThreads, 4)
 class_nms_kernel(ClsParams p) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   __shared__ int s_nseed, s_base;
@@ -443,39 +443,49 @@ class_nms_kernel(ClsParams p) {
     short* seeds = reinterpret_cast<short*>(mask + kMaskItems * kMaskWords);        // [512]
     float* area = reinterpret_cast<float*>(seeds + kMaskItems) + 2 * kMaskWords;    // [512] (after nzrow, seedbits)
     const int W = (m + 31) >> 5;
-    // One thread per item (m <= 512 = kClsThreads).  Sort by counting: rank_i = #{j : key_j > key_i} (keys are unique),
-    // m broadcast reads of shared memory per thread, no barriers inside.  The item's global loads (4 regression planes,
-    // class and IoU logits) are issued first and land while the rank loop runs.
+    // kItems items per thread (m <= 512).  Sort by counting: rank_i = #{j : key_j > key_i} (keys are unique), m
+    // broadcast reads of shared memory per item, no barriers inside.  The items' global loads (4 regression planes,
+    // class and IoU logits) are issued first and land while the rank loops run.
+    constexpr int kItems = kMaskItems / kClsThreads;
     u64* ukeys = reinterpret_cast<u64*>(mask);                     // unsorted keys; the mask area is free until later
-    u64 mykey = 0ull;
-    DecodeRaw raw;
-    if (tid < m) {
-      mykey = gkeys[tid];
-      ukeys[tid] = mykey;
-      raw = decode_load(p, b, c, mykey);
+    u64 mykey[kItems];
+    DecodeRaw raw[kItems];
+#pragma unroll
+    for (int u = 0; u < kItems; ++u) {
+      const int i = tid + u * kClsThreads;
+      mykey[u] = 0ull;
+      if (i < m) {
+        mykey[u] = gkeys[i];
+        ukeys[i] = mykey[u];
+        raw[u] = decode_load(p, b, c, mykey[u]);
+      }
     }
-    if (tid == m && (m & 1)) ukeys[m] = 0ull;                      // pad to an even count for the 128-bit reads
+    if (tid == 0 && (m & 1)) ukeys[m] = 0ull;                      // pad to an even count for the 128-bit reads
     __syncthreads();
     RADET_DBG(1);
-    if (tid < m) {
-      int rank = 0;
-      const ulonglong2* uk2 = reinterpret_cast<const ulonglong2*>(ukeys);
-      const int n2 = (m + 1) >> 1;
+#pragma unroll
+    for (int u = 0; u < kItems; ++u) {
+      const int i = tid + u * kClsThreads;
+      if (i < m) {
+        int rank = 0;
+        const ulonglong2* uk2 = reinterpret_cast<const ulonglong2*>(ukeys);
+        const int n2 = (m + 1) >> 1;
 #pragma unroll 4
-      for (int j = 0; j < n2; ++j) {
-        const ulonglong2 k2 = uk2[j];
-        rank += (k2.x > mykey ? 1 : 0) + (k2.y > mykey ? 1 : 0);
+        for (int j = 0; j < n2; ++j) {
+          const ulonglong2 k2 = uk2[j];
+          rank += (k2.x > mykey[u] ? 1 : 0) + (k2.y > mykey[u] ? 1 : 0);
+        }
+        float4 bx;
+        float c_, v_;
+        decode_finish(p, raw[u], bx, c_, v_);
+        keys[rank] = mykey[u];
+        box[rank] = bx;
+        area[rank] = box_area_rn(bx);
+        cs[rank] = c_;
+        vs[rank] = v_;
       }
-      RADET_DBG(2);
-      float4 bx;
-      float c_, v_;
-      decode_finish(p, raw, bx, c_, v_);
-      keys[rank] = mykey;
-      box[rank] = bx;
-      area[rank] = box_area_rn(bx);
-      cs[rank] = c_;
-      vs[rank] = v_;
     }
+    RADET_DBG(2);
     __syncthreads();
     RADET_DBG(3);
     // IoU bit matrix, upper triangle: one warp per row i (round-robin), lane = column inside each 32-wide word.
@@ -748,7 +758,7 @@ class_nms_kernel(ClsParams p) {
 }
 
 // ------------------------------------------------------------------------------------------------ 4. rank + emit
-constexpr int kRankThreads = 1024;
+constexpr int kRankThreads = 512;
 constexpr int kRankMaxOut = 4096;
 
 struct RankParams {
