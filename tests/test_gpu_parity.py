@@ -743,3 +743,33 @@ def test_full_size_cfg4_inference_properties():
         ok = ~torch.isnan(d[:, :4]).any(1)                                 # a cluster voted from an empty sigma band is NaN, as in the reference
         e = 1e-3                                                           # (s*x)/s of clamped coordinates may round one ulp past the border
         assert bool((d[ok, 0] >= -e).all()) and bool((d[ok, 2] <= wl.W + e).all()) and bool((d[ok, 1] >= -e).all()) and bool((d[ok, 3] <= wl.H + e).all())
+
+
+@pytest.mark.gpu
+def test_get_bboxes_low_threshold_fills_the_select_staging():
+    """score_thr so low that nearly every (point, class) passes: detect_select_kernel's staging buffer overflows into
+    its direct path, the per-level top-k (nms_pre) has real work.  Candidates as sets + detections bit-exact vs the oracle."""
+    wl, batch, idx_l, w_l, ho = _head_inputs("small")
+    cls, bbox, iou = _to_dev(ho)
+    thr = 1e-4
+    shp = torch.tensor([[im.H, im.W] for im in batch], dtype=torch.int32, device=DEV)
+    sf = torch.ones((len(batch), 4), device=DEV)
+    cfg = F.DetectConfig(score_thr=thr, nms_pre=300, nms_type="vote", **{k: v for k, v in NMS_CFG.items() if k != "sima"})
+    rows, cats, num = F.get_candidates(GEOM, wl.C, cls, bbox, iou, shp, sf, cfg, rescale=True)
+    dets, labels, nd = F.get_bboxes(GEOM, wl.C, cls, bbox, iou, shp, sf, cfg, rescale=True)
+    for b, im in enumerate(batch):
+        maps = ([m[b] for m in ho.cls], [m[b] for m in ho.bbox], [m[b] for m in ho.iou])
+        assert float((torch.sigmoid(cls[0][b]) > thr).float().mean()) > 0.9          # the staging capacity is exceeded on level 0
+        bx, sc, ctr, ocats, anc = orc.select_candidates(*maps, (im.H, im.W, 3), np.ones(4, np.float32), thr, 300)
+        full = np.concatenate([bx, (sc * ctr)[:, None], anc], 1).astype(np.float32)
+        k = int(num[b])
+        assert k == full.shape[0]
+        r, c = rows[b, :k].cpu().numpy(), cats[b, :k].cpu().numpy()
+        o = np.lexsort((c, r[:, 8], r[:, 7], r[:, 6], r[:, 5], r[:, 4]))
+        oo = np.lexsort((ocats, full[:, 8], full[:, 7], full[:, 6], full[:, 5], full[:, 4]))
+        assert np.array_equal(r[o].view(np.uint32), full[oo].view(np.uint32)) and np.array_equal(c[o], ocats[oo])
+        od, ol = orc.get_bboxes_image(*maps, (im.H, im.W, 3), np.ones(4, np.float32), score_thr=thr, nms_pre=300,
+                                      nms_cfg=dict(type="vote", **NMS_CFG))
+        kk = int(nd[b])
+        assert kk == od.shape[0]
+        assert np.array_equal(dets[b, :kk].cpu().numpy().view(np.uint32), od.view(np.uint32)) and np.array_equal(labels[b, :kk].cpu().numpy(), ol)
