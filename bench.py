@@ -190,6 +190,36 @@ class ClockSampler:
 
 
 # ------------------------------------------------------------------------------------------------ ours
+def bind_to_gpu_numa_node(index):
+    """Run this rank on the cores of the NUMA node its GPU hangs off, so that the pinned host arenas of the e2e leg are
+    allocated next to the GPU's PCIe root (with 8 ranks on a two-socket host, half the copies otherwise cross sockets).
+    Returns the node, or None when the topology is not exposed."""
+    try:
+        import pynvml
+
+        pynvml.nvmlInit()
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+        phys = int(vis.split(",")[index]) if vis and all(t.strip().isdigit() for t in vis.split(",")) else index
+        bus = pynvml.nvmlDeviceGetPciInfo(pynvml.nvmlDeviceGetHandleByIndex(phys)).busId
+        bus = (bus.decode() if isinstance(bus, bytes) else bus).lower()
+        if len(bus.split(":")[0]) == 8:           # nvml prints an 8-digit domain, sysfs a 4-digit one
+            bus = bus[4:]
+        node = int(open(f"/sys/bus/pci/devices/{bus}/numa_node").read())
+        if node < 0:
+            return None
+        cpus = set()
+        for part in open(f"/sys/devices/system/node/node{node}/cpulist").read().strip().split(","):
+            a, _, b = part.partition("-")
+            cpus.update(range(int(a), int(b or a) + 1))
+        cpus &= os.sched_getaffinity(0)
+        if not cpus:
+            return None
+        os.sched_setaffinity(0, cpus)
+        return node
+    except Exception:
+        return None
+
+
 def main():
     args = parse()
     wl = syn.WORKLOADS[args.workload]
@@ -216,6 +246,8 @@ def main():
             cpu_base = json.loads(cpu_proc_out[0].strip().splitlines()[-1])
         except Exception:
             cpu_base = {"error": (cpu_proc_out[1] or "")[-300:]}
+
+    numa = bind_to_gpu_numa_node(local_rank)   # before any pinned allocation: first touch decides where the pages live
 
     import torch
     import torch.distributed as dist
@@ -604,7 +636,8 @@ def main():
                        "steps_in_flight": U, "ms_per_step_one_in_flight": one_lane_ms, "overlap_check": overlap_check,
                        "host_enqueue_us_per_step": host_enqueue_us[0],
                        "l2": f"{R} rotating input sets, {R * per_set / 1e6:.0f} MB total > L2 ({L2_BYTES / 1e6:.0f} MB)",
-                       "parallelism": f"images sharded over {world} rank(s), no data-path collective"},
+                       "parallelism": f"images sharded over {world} rank(s), no data-path collective",
+                       "numa_node_of_rank0": numa},
             "point_gt_pairs_per_s": world * pairs / (stage_us["assign(pairs+resolve)"] * 1e-6),
             "point_gt_pairs_per_s_train_path": world * pairs / ((stage_us["assign(pairs+resolve)"] + stage_us["loss(pos+dense)"]) * 1e-6),
             "stage_us": stage_us, "gpu_launches": launches_per_step * args.steps, "launches_per_step": launches_per_step,
