@@ -343,7 +343,8 @@ def head_loss(cls_maps, bbox_maps, iou_maps, gt_bboxes_list, gt_labels_list, idx
     else:
         loss_bbox = flat_box[pos].sum()                                                    # :280-281
         loss_iou = flat_iou[pos].sum()
-    out = dict(loss_cls=float(loss_cls), loss_bbox=float(loss_bbox), loss_iou=float(loss_iou), num_pos=float(num_pos))
+    out = dict(loss_cls=float(loss_cls.detach()), loss_bbox=float(loss_bbox.detach()), loss_iou=float(loss_iou.detach()),
+               num_pos=float(num_pos))
     if need_grad:
         (loss_cls + loss_bbox + loss_iou).backward()
         z = lambda t: np.zeros(t.shape, np.dtype(dtype)) if t.grad is None else t.grad.numpy()
