@@ -773,3 +773,40 @@ def test_get_bboxes_low_threshold_fills_the_select_staging():
         kk = int(nd[b])
         assert kk == od.shape[0]
         assert np.array_equal(dets[b, :kk].cpu().numpy().view(np.uint32), od.view(np.uint32)) and np.array_equal(labels[b, :kk].cpu().numpy(), ol)
+
+
+@pytest.mark.gpu
+def test_whole_path_coco_like_shape():
+    """80 classes, 40 GT per image (two 32-bit GT words), a 333x500 image (every level size odd, planes not 16-byte
+    tileable -> the register-pipelined dense kernel, the scalar select path): assignment bit-exact, loss / gradients
+    within the head tolerances, vote-NMS detections bit-exact against the oracle."""
+    wl = syn.Workload("coco_like_333x500_B3_C80_G40", 333, 500, 80, 3, 40, 40, 17)
+    batch = syn.make_batch(wl)
+    a = [orc.assign_image_seeded(im.gt_bboxes, im.masks, im.H, im.W, im.seed) for im in batch]
+    idx_l, w_l = [x[0] for x in a], [x[1] for x in a]
+    cases = [dict(boxes=im.gt_bboxes, grid=syn.sample_grid(im.masks), H=im.H, W=im.W, seed=im.seed) for im in batch]
+    idx, w, used = _assign_gpu(cases)
+    for i in range(len(batch)):
+        assert np.array_equal(idx[i], idx_l[i]) and np.array_equal(w[i], w_l[i]) and int(used[i]) == a[i][2]
+    ho = syn.make_head_outputs(wl, batch, idx_l)
+    cls, bbox, iou = _to_dev(ho)
+    counts, boxes, labels = _gt_dev(batch)
+    losses, grads = F.loss_fwd_bwd(GEOM, wl.C, cls, bbox, iou, counts, boxes, labels, torch.from_numpy(np.stack(idx_l)).to(DEV),
+                                   torch.from_numpy(np.stack(w_l)).to(DEV), F.LossConfig())
+    o = orc.head_loss(ho.cls, ho.bbox, ho.iou, [b.gt_bboxes for b in batch], [b.gt_labels for b in batch], idx_l, w_l, wl.C, wl.H, wl.W)
+    losses = losses.cpu().numpy()
+    for i, k in enumerate(("loss_cls", "loss_bbox", "loss_iou")):
+        assert abs(losses[i] - o[k]) <= 1e-5 * abs(o[k]), k
+    _check_grads(grads[0], o["grad_cls"], 1e-4, 1e-6)
+    _check_grads(grads[1], o["grad_bbox"], 1e-4, 1e-6)
+    _check_grads(grads[2], o["grad_iou"], 1e-4, 1e-6)
+    cfg = F.DetectConfig(score_thr=0.05, nms_type="vote", **{k: v for k, v in NMS_CFG.items() if k != "sima"})
+    shp = torch.tensor([[im.H, im.W] for im in batch], dtype=torch.int32, device=DEV)
+    sf = torch.full((len(batch), 4), 0.8, device=DEV)
+    dets, dl, num = F.get_bboxes(GEOM, wl.C, cls, bbox, iou, shp, sf, cfg, rescale=True)
+    for b, im in enumerate(batch):
+        od, ol = orc.get_bboxes_image([m[b] for m in ho.cls], [m[b] for m in ho.bbox], [m[b] for m in ho.iou], (im.H, im.W, 3),
+                                      np.full(4, 0.8, np.float32), score_thr=0.05, nms_cfg=dict(type="vote", **NMS_CFG))
+        k = int(num[b])
+        assert k == od.shape[0]
+        assert np.array_equal(dets[b, :k].cpu().numpy().view(np.uint32), od.view(np.uint32)) and np.array_equal(dl[b, :k].cpu().numpy(), ol)
