@@ -486,6 +486,10 @@ class_nms_kernel(ClsParams p) {
       }
     }
     RADET_DBG(2);
+    for (int i = m + tid; i < ((m + 31) & ~31) + 1 && i < kMaskItems; i += kClsThreads) {   // sentinel columns (+ row m)
+      box[i] = make_float4(-1.f, -1.f, -1.f, -1.f);                 // clamped boxes are >= 0: never overlaps
+      area[i] = 0.f;
+    }
     __syncthreads();
     RADET_DBG(3);
     // IoU bit matrix, upper triangle: one warp per row i (round-robin), lane = column inside each 32-wide word.
@@ -495,48 +499,67 @@ class_nms_kernel(ClsParams p) {
     if (tid < kMaskWords) nzrow[tid] = 0u;
     __syncthreads();
     // Two adjacent rows per warp trip (iA, iA + 1 share the column loads and the diagonal word); lanes = columns.
+    // Columns m .. 32 W - 1 hold a sentinel box that overlaps nothing (written with the sort above), so the loop has no
+    // bounds tests; "column above the diagonal" is a mask on the first word; threshold decisions that the rcp-filtered
+    // test cannot make are only flagged, and the (very rare) row pair with a flag is redone with the exact division.
     constexpr int kNW = kClsThreads / 32;
-    const bool fast_ok = p.thr >= 1e-30f;                           // rcp-filtered decision (iou_gt_fast) needs thr > 0
+    const bool fast_ok = p.thr >= 1e-30f;                           // iou_gt_fast needs thr > 0
     const float thr_lo = p.thr * (1.f - 1e-6f), thr_hi = p.thr * (1.f + 1e-6f);
     for (int iA = 2 * wid; iA < m; iA += 2 * kNW) {
-      const int iB = iA + 1;
-      const bool hasB = iB < m;
-      const float4 bA = box[iA], bB = box[hasB ? iB : iA];
-      const float areaA = area[iA], areaB = area[hasB ? iB : iA];
-      unsigned anyA = 0u, anyB = 0u;
+      const int iB = iA + 1;                                        // <= 511: the row exists in shared memory even when iB == m
+      const float4 bA = box[iA], bB = box[iB];                      // iB == m reads the sentinel
+      const float areaA = area[iA], areaB = area[iB];
       const int w0 = iA >> 5;                                       // == iB >> 5 (iA is even)
+      unsigned* mA = mask + iA * W;
+      unsigned* mB = mask + iB * W;
       if (lane < w0) {                                              // words below the diagonal
-        mask[iA * W + lane] = 0u;
-        if (hasB) mask[iB * W + lane] = 0u;
+        mA[lane] = 0u;
+        mB[lane] = 0u;
       }
+      const unsigned aboveA = ~((2u << (iA & 31)) - 1u), aboveB = ~((2u << (iB & 31)) - 1u);   // columns > i in word w0
+      unsigned anyA = 0u, anyB = 0u;
+      bool redo = !fast_ok;
+      if (fast_ok) {
+        bool amb = false;
+        const float4* bp = box + w0 * 32 + lane;
+        const float* ap = area + w0 * 32 + lane;
 #pragma unroll 2
-      for (int wj = w0; wj < W; ++wj) {
-        const int j = wj * 32 + lane;
-        const bool in = j < m;
-        const float4 bj = box[in ? j : 0];
-        const float aj = area[in ? j : 0];
-        bool hitA, hitB;
-        if (fast_ok) {                                              // warp-uniform
+        for (int wj = w0; wj < W; ++wj, bp += 32, ap += 32) {
+          const float4 bj = *bp;
+          const float aj = *ap;
           bool ambA, ambB;
-          hitA = iou_gt_fast(bA, areaA, bj, aj, thr_lo, thr_hi, ambA);                     // vote_ext.cpp:169
-          hitB = iou_gt_fast(bB, areaB, bj, aj, thr_lo, thr_hi, ambB);
-          if (__any_sync(kFull, ambA || ambB)) {                    // a quotient within 8 ulp of thr: exact division
-            if (ambA) hitA = iou_gt(bA, areaA, bj, p.thr);
-            if (ambB) hitB = iou_gt(bB, areaB, bj, p.thr);
+          const bool hitA = iou_gt_fast(bA, areaA, bj, aj, thr_lo, thr_hi, ambA);            // vote_ext.cpp:169
+          const bool hitB = iou_gt_fast(bB, areaB, bj, aj, thr_lo, thr_hi, ambB);
+          amb = amb || ambA || ambB;
+          unsigned wordA = __ballot_sync(kFull, hitA), wordB = __ballot_sync(kFull, hitB);
+          if (wj == w0) {
+            wordA &= aboveA;
+            wordB &= aboveB;
           }
-          hitA = hitA && in && j > iA;
-          hitB = hitB && in && hasB && j > iB;
-        } else {
-          hitA = in && j > iA && iou_gt(bA, areaA, bj, p.thr);
-          hitB = in && hasB && j > iB && iou_gt(bB, areaB, bj, p.thr);
+          if (lane == 0) {
+            mA[wj] = wordA;
+            mB[wj] = wordB;
+          }
+          anyA |= wordA;
+          anyB |= wordB;
         }
-        const unsigned wordA = __ballot_sync(kFull, hitA), wordB = __ballot_sync(kFull, hitB);
-        if (lane == 0) {
-          mask[iA * W + wj] = wordA;
-          if (hasB) mask[iB * W + wj] = wordB;
+        redo = __any_sync(kFull, amb);
+      }
+      if (redo) {                                                   // exact division for the whole row pair
+        anyA = anyB = 0u;
+        for (int wj = w0; wj < W; ++wj) {
+          const int j = wj * 32 + lane;
+          const float4 bj = box[j];
+          const bool hitA = j > iA && j < m && iou_gt(bA, areaA, bj, p.thr);
+          const bool hitB = j > iB && j < m && iB < m && iou_gt(bB, areaB, bj, p.thr);
+          const unsigned wordA = __ballot_sync(kFull, hitA), wordB = __ballot_sync(kFull, hitB);
+          if (lane == 0) {
+            mA[wj] = wordA;
+            mB[wj] = wordB;
+          }
+          anyA |= wordA;
+          anyB |= wordB;
         }
-        anyA |= wordA;
-        anyB |= wordB;
       }
       if (lane == 0 && anyA) atomicOr(&nzrow[iA >> 5], 1u << (iA & 31));
       if (lane == 0 && anyB) atomicOr(&nzrow[iB >> 5], 1u << (iB & 31));
