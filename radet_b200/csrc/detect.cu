@@ -89,14 +89,35 @@ detect_select_kernel(GridDev grid, SelPlan plan, int C, MapsDev maps, float thr,
       }
     }
     // A. conservative prefilter on the raw logit: the few survivors are staged so that the sigmoid below runs on
-    //    dense warps instead of inside a branch that one lane in 32 takes
+    //    dense warps instead of inside a branch that one lane in 32 takes.  Each lane first collects a bit mask of
+    //    its survivors; one warp scan and one shared-memory atomic per warp then give every lane its slots.
+    unsigned pm = 0u;
 #pragma unroll
     for (int k = 0; k < kSelChunk; ++k) {
 #pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        if (i < nv && xv[k][i] > x_lo) {
-          const unsigned flat = (unsigned)(q0 + i) * (unsigned)C + (unsigned)(cb + k);
-          s_buf[atomicAdd(&s_cnt, 1)] = ((u64)__float_as_uint(xv[k][i]) << 32) | (u64)flat;
+      for (int i = 0; i < 4; ++i)
+        if (i < nv && xv[k][i] > x_lo) pm |= 1u << (k * 4 + i);
+    }
+    {
+      const int cnt_ = __popc(pm);
+      int inc = cnt_;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const int t = __shfl_up_sync(kFull, inc, o);
+        if (lane >= o) inc += t;
+      }
+      int wbase = 0;
+      if (lane == 31 && inc) wbase = atomicAdd(&s_cnt, inc);
+      wbase = __shfl_sync(kFull, wbase, 31);
+      int pos = wbase + inc - cnt_;
+#pragma unroll
+      for (int k = 0; k < kSelChunk; ++k) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          if ((pm >> (k * 4 + i)) & 1u) {
+            const unsigned flat = (unsigned)(q0 + i) * (unsigned)C + (unsigned)(cb + k);
+            s_buf[pos++] = ((u64)__float_as_uint(xv[k][i]) << 32) | (u64)flat;
+          }
         }
       }
     }
