@@ -110,14 +110,24 @@ detect_select_kernel(GridDev grid, SelPlan plan, int C, MapsDev maps, float thr,
       if (lane == 31 && inc) wbase = atomicAdd(&s_cnt, inc);
       wbase = __shfl_sync(kFull, wbase, 31);
       int pos = wbase + inc - cnt_;
+      // lanes with survivors peel them off one per trip (typically one or two trips per warp); the value is picked
+      // by a 4-level select tree so that xv[][] stays in registers
+      static_assert(kSelChunk == 4, "the select tree below picks one of 16 values");
+      while (__any_sync(kFull, pm != 0u)) {
+        if (pm) {
+          const int e = __ffs((int)pm) - 1;
+          pm &= pm - 1u;
+          const bool b0 = e & 1, b1 = e & 2, b2 = e & 4, b3 = e & 8;
+          float t8[8], t4[4], t2[2];
 #pragma unroll
-      for (int k = 0; k < kSelChunk; ++k) {
+          for (int q = 0; q < 8; ++q) t8[q] = b0 ? xv[(2 * q + 1) >> 2][(2 * q + 1) & 3] : xv[(2 * q) >> 2][(2 * q) & 3];
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          if ((pm >> (k * 4 + i)) & 1u) {
-            const unsigned flat = (unsigned)(q0 + i) * (unsigned)C + (unsigned)(cb + k);
-            s_buf[pos++] = ((u64)__float_as_uint(xv[k][i]) << 32) | (u64)flat;
-          }
+          for (int q = 0; q < 4; ++q) t4[q] = b1 ? t8[2 * q + 1] : t8[2 * q];
+#pragma unroll
+          for (int q = 0; q < 2; ++q) t2[q] = b2 ? t4[2 * q + 1] : t4[2 * q];
+          const float v = b3 ? t2[1] : t2[0];
+          const unsigned flat = (unsigned)(q0 + (e & 3)) * (unsigned)C + (unsigned)(cb + (e >> 2));
+          s_buf[pos++] = ((u64)__float_as_uint(v) << 32) | (u64)flat;
         }
       }
     }
