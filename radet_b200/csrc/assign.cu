@@ -320,7 +320,8 @@ assign_pairs_kernel(GridDev grid, const int* __restrict__ gt_offsets, const floa
   const int s = grid.stride[l];
   const float cx = (float)(x * s), cy = (float)(y * s);
   const float lo = grid.lo[l], hi = grid.hi[l];
-  const int my = (y * s) / mask_step, mx = (x * s) / mask_step;  // int(cy), int(cx) on the sample grid
+  const int ratio = s / mask_step;                               // stride is a multiple of the sample step (checked by the entry)
+  const int my = y * ratio, mx = x * ratio;                      // int(cy), int(cx) on the sample grid
   const int mword = my * mask_pitch + (mx >> 5);
   const uint32_t mbit = 1u << (mx & 31);
 

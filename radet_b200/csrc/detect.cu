@@ -77,11 +77,12 @@ detect_select_kernel(GridDev grid, SelPlan plan, int C, MapsDev maps, float thr,
     const int ce = min(c1, cb + kSelChunk);
     float xv[kSelChunk][4];
 #pragma unroll
-    for (int k = 0; k < kSelChunk; ++k) {   // all loads of the chunk in flight first
+    const float* pk = cp + (int64_t)cb * hw;
+    for (int k = 0; k < kSelChunk; ++k, pk += hw) {   // all loads of the chunk in flight first
       xv[k][0] = xv[k][1] = xv[k][2] = xv[k][3] = -INFINITY;
       if (cb + k < ce && nv > 0) {
         if (vec) {
-          const float4 v4 = ldg_stream4(cp + (int64_t)(cb + k) * hw);
+          const float4 v4 = ldg_stream4(pk);
           xv[k][0] = v4.x; xv[k][1] = v4.y; xv[k][2] = v4.z; xv[k][3] = v4.w;
         } else {
           for (int i = 0; i < nv; ++i) xv[k][i] = cp[(int64_t)(cb + k) * hw + i];
@@ -666,8 +667,10 @@ class_nms_kernel(ClsParams p) {
           return s_;
         };
         auto gx = [&](int j) -> float { return reinterpret_cast<const float*>(&box[j])[axis]; };
+        // a row that had no overlap at all (nzrow bit clear) is a singleton cluster without looking at the matrix
         unsigned anym = 0u;
-        for (int w_ = i >> 5; w_ < W; ++w_) anym |= mask[i * W + w_];
+        if ((nzrow[i >> 5] >> (i & 31)) & 1u)
+          for (int w_ = i >> 5; w_ < W; ++w_) anym |= mask[i * W + w_];
         if (anym == 0u) {
           // singleton cluster: the same operation sequence as vote_single_dim with n = 1 (vote_ext.cpp:8-35)
           const float s1 = vs[i], x = gx(i);
