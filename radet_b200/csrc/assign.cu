@@ -400,34 +400,6 @@ struct ResolveSmem {
 constexpr int kWorkers = kResolveThreads - 32;
 __device__ __forceinline__ void worker_barrier() { asm volatile("bar.sync 1, %0;" ::"n"(kWorkers) : "memory"); }
 
-// exclusive prefix sum of one int per worker thread (threads 32..1023); scratch holds 33 ints
-__device__ __forceinline__ int worker_exclusive_scan(int v, int* scratch, int* total) {
-  const int lane = threadIdx.x & 31, ww = (threadIdx.x >> 5) - 1;  // worker warp 0..30
-  int inc = v;
-#pragma unroll
-  for (int o = 1; o < 32; o <<= 1) {
-    int t = __shfl_up_sync(kFull, inc, o);
-    if (lane >= o) inc += t;
-  }
-  worker_barrier();  // scratch reuse across calls
-  if (lane == 31) scratch[ww] = inc;
-  worker_barrier();
-  if (ww == 0) {
-    int s = lane < 31 ? scratch[lane] : 0;
-    int si = s;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-      int t = __shfl_up_sync(kFull, si, o);
-      if (lane >= o) si += t;
-    }
-    scratch[lane] = si - s;
-    if (lane == 31) scratch[32] = si;
-  }
-  worker_barrier();
-  *total = scratch[32];
-  return scratch[ww] + inc - v;
-}
-
 __host__ __device__ inline size_t resolve_smem_bytes(int maxG, int K, bool list_in_smem) {
   size_t s = sizeof(ResolveSmem);
   s = (s + 15) & ~size_t(15);
