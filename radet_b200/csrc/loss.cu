@@ -991,7 +991,7 @@ extern "C" int radet_scale_grads(const radet_grid_t* grid, int32_t batch, int32_
       nmax = n[k] > nmax ? n[k] : nmax;
     }
   }
-  const unsigned bx = (unsigned)((nmax + 255) / 256 > 74 ? 74 : (nmax + 255) / 256);
+  const unsigned bx = (unsigned)((nmax + 255) / 256 > 16 ? 16 : (nmax + 255) / 256);   // the usual call exits at once: keep the grid small
   scale_grads_kernel<<<dim3(bx, 3 * g.num_levels), 256, 0, (cudaStream_t)stream>>>(tab, upstream);
   RADET_LAUNCH_CHECK();
   return RADET_OK;
