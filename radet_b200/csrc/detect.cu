@@ -925,9 +925,9 @@ static int sel_plan(const GridDev& g, int B, int C, SelPlan* plan) {
     plan->coff[l] = (int64_t)C * g.off[g.num_levels];
   }
   for (int l = g.num_levels; l < RADET_MAX_LEVELS; ++l) plan->bpl[l] = 0;
-  // class chunks: enough CTAs for ~4 per SM, otherwise as many classes per thread as possible (deeper load queues)
-  const int per_j = blocks * B;
-  int nj_target = (4 * 148 + per_j - 1) / per_j;
+  // class chunks: two rounds of kSelChunk planes per CTA.  The kernel is latency-bound; fewer, longer-lived CTAs cost the
+  // other kernels in flight less than many short ones (measured: 7 chunks of 3 classes -> 3 chunks of 7 at C = 21).
+  int nj_target = (C + 2 * kSelChunk - 1) / (2 * kSelChunk);
   if (nj_target < 1) nj_target = 1;
   int cc = (C + nj_target - 1) / nj_target;
   if (cc < 1) cc = 1;
