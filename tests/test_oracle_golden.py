@@ -186,3 +186,35 @@ def test_assignment_options_match_reference_bit_exact(variant):
         rs = np.random.RandomState(im.seed)
         rs.random_sample(used)
         assert np.array_equal(rs.random_sample(2), g[f"{name}/tail"]), name
+
+
+def test_legacy_choice_restatement_equals_numpy():
+    """The third-party arithmetic on the assignment path is numpy's legacy RandomState.choice (label_assignment.py:112,119;
+    numpy is unpinned in requirements.txt).  The oracle's restatement must reproduce numpy's own outputs AND leave the
+    stream at the same position, for uniform p (binary masks) and for arbitrary p, with and without replacement."""
+    rs = np.random.RandomState(2024)
+    for case in range(400):
+        n = int(rs.randint(1, 60))
+        k = int(rs.randint(1, 33))
+        replace = bool(rs.randint(0, 2)) or k > n
+        if case % 2:
+            p32 = np.full(n, np.float32(1.0)) / np.float32(n)                # what binary masks give (:103)
+        else:
+            w = rs.uniform(0.05, 1.0, n).astype(np.float32)
+            p32 = w / np.sum(w)
+        seed = int(rs.randint(0, 2 ** 31 - 1))
+        ref_rs = np.random.RandomState(seed)
+        want = ref_rs.choice(a=n, size=k, p=p32, replace=replace)
+        tail_want = ref_rs.random_sample(3)
+        mine_rs = np.random.RandomState(seed)
+
+        class S:
+            pos = 0
+
+            def random_sample(self, m):
+                self.pos += m
+                return mine_rs.random_sample(m)
+
+        got = orc.legacy_choice(S(), p32, k, replace)
+        assert np.array_equal(got, want), (case, n, k, replace)
+        assert np.array_equal(mine_rs.random_sample(3), tail_want), (case, "stream position")
