@@ -85,9 +85,11 @@ int64_t oracle_vote_nms(const float *boxes, const float *cluster_scores, const f
       const float area_j = (bj[2] - bj[0]) * (bj[3] - bj[1]);
       const float iou = inter / (area_j + area_i - inter);
       float vj = vote_scores[j];
-      if (iou_enable) { /* exp() resolves to the double overload in the reference (vote_ext.cpp:165) */
-        const double fac = exp((double)(-(1 - iou) * (1 - iou) / sigma));
-        vj = (float)((double)vj * fac);
+      if (iou_enable) { /* vote_ext.cpp:164-167: with <torch/extension.h> included first, the unqualified exp() on a
+                           float resolves to the float overload (verified against the compiled reference, see
+                           tests/test_oracle_golden.py::test_c_oracle_equals_the_compiled_reference_ops) */
+        const float fac = expf(-(1 - iou) * (1 - iou) / sigma);
+        vj = vj * fac;
       }
       if (iou > thr) {
         gone[j] = 1;

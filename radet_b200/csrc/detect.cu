@@ -659,10 +659,11 @@ class_nms_kernel(ClsParams p) {
         const float area_i = box_area_rn(bi);
         auto gs = [&](int j) -> float {
           float s_ = vs[j];
-          if (p.iou_enable && j != i) {   // vote_ext.cpp:164-167, exp() in double as in the reference build
+          if (p.iou_enable && j != i) {   // vote_ext.cpp:164-167: float exp() (glibc expf, <= 0.502 ulp) and a float multiply;
+                                          // the correctly rounded value computed through double is what it returns bar near-ties
             const float d = __fsub_rn(1.f, iou_rn(bi, area_i, box[j]));
             const float e = __fdiv_rn(-__fmul_rn(d, d), p.sigma);
-            s_ = (float)((double)s_ * exp((double)e));
+            s_ = __fmul_rn(s_, (float)exp((double)e));
           }
           return s_;
         };
@@ -746,7 +747,7 @@ class_nms_kernel(ClsParams p) {
         if (p.iou_enable) {
           const float d = __fsub_rn(1.f, iou);
           const float e = __fdiv_rn(-__fmul_rn(d, d), p.sigma);
-          vs[j] = (float)((double)vs[j] * exp((double)e));
+          vs[j] = __fmul_rn(vs[j], (float)exp((double)e));
         }
       }
     }

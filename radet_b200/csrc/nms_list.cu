@@ -260,10 +260,10 @@ nms_list_kernel(NmsParams p) {
         const float iou = __fdiv_rn(inter, __fsub_rn(__fadd_rn(area_j, area_i), inter));  // vote_ext.cpp:162
         if (iou > p.thr) {                                                                // :169 (strict; NaN -> false)
           A.owner[ij] = (IdxT)ia;
-          if (p.iou_enable) {  // :164-167, exp() evaluated in double as in the reference build
+          if (p.iou_enable) {  // :164-167: float exp() and a float multiply (see detect.cu)
             const float d = __fsub_rn(1.f, iou);
             const float e = __fdiv_rn(-__fmul_rn(d, d), p.sigma);
-            A.vs[ij] = (float)((double)A.vs[ij] * exp((double)e));
+            A.vs[ij] = __fmul_rn(A.vs[ij], (float)exp((double)e));
           }
         }
       }

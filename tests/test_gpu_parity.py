@@ -810,3 +810,41 @@ def test_whole_path_coco_like_shape():
         k = int(num[b])
         assert k == od.shape[0]
         assert np.array_equal(dets[b, :k].cpu().numpy().view(np.uint32), od.view(np.uint32)) and np.array_equal(dl[b, :k].cpu().numpy(), ol)
+
+
+# ------------------------------------------------------------------------------------------------ iou_enable=True
+@pytest.mark.gpu
+@pytest.mark.parametrize("case", range(3))
+def test_ops_iou_enable_golden_bit_exact(case):
+    """vote_nms / global_vote_nms with the IoU score decay switched on (vote_ext.cpp:164-167: float exp, float multiply)
+    against the reference's golden output; the shipped configs never enable it, so it has its own vectors."""
+    g = hp.load("ops_iou.npz")
+    boxes = torch.from_numpy(g[f"c{case}/boxes"]).to(DEV)
+    labels = torch.from_numpy(g[f"c{case}/labels"].astype(np.int64)).to(DEV)
+    cls = torch.from_numpy(g[f"c{case}/cls"]).to(DEV)
+    ctr = torch.from_numpy(g[f"c{case}/ctr"]).to(DEV)
+    cfg = P.ConfigDict(type="vote", iou_threshold=0.65, cluster_score=["cls", "iou"], vote_score=["iou", "cls"], iou_enable=True,
+                       sigma=float(g[f"c{case}/sigma"]))
+    for nm, fn in (("vote", P.ops.vote_nms), ("gvote", P.ops.global_vote_nms)):
+        d, l = fn(boxes, cls, labels, cfg, score_factor=ctr, max_num=0)
+        assert np.array_equal(d.cpu().numpy().view(np.uint32), g[f"c{case}/{nm}_dets"].view(np.uint32)), nm
+        assert np.array_equal(l.cpu().numpy(), g[f"c{case}/{nm}_labels"].astype(np.int64))
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("typ", ["vote", "global_vote"])
+def test_get_bboxes_iou_enable_vs_oracle(typ):
+    """The same switch through the detection pipeline (class_nms_kernel's vote) against the oracle."""
+    wl, batch, idx_l, w_l, ho = _head_inputs("cfg1")
+    cls, bbox, iou = _to_dev(ho)
+    nms = dict(iou_threshold=0.65, cluster_score=["cls", "iou"], vote_score=["iou", "cls"], iou_enable=True, sigma=0.3)
+    cfg = F.DetectConfig(score_thr=0.05, nms_type=typ, **nms)
+    shp = torch.tensor([[im.H, im.W] for im in batch], dtype=torch.int32, device=DEV)
+    sf = torch.ones((len(batch), 4), device=DEV)
+    dets, labels, num = F.get_bboxes(GEOM, wl.C, cls, bbox, iou, shp, sf, cfg, rescale=True)
+    for b, im in enumerate(batch):
+        od, ol = orc.get_bboxes_image([m[b] for m in ho.cls], [m[b] for m in ho.bbox], [m[b] for m in ho.iou], (im.H, im.W, 3),
+                                      np.ones(4, np.float32), score_thr=0.05, nms_cfg=dict(type=typ, **nms))
+        k = int(num[b])
+        assert k == od.shape[0]
+        assert np.array_equal(dets[b, :k].cpu().numpy().view(np.uint32), od.view(np.uint32)) and np.array_equal(labels[b, :k].cpu().numpy(), ol)

@@ -218,3 +218,66 @@ def test_legacy_choice_restatement_equals_numpy():
         got = orc.legacy_choice(S(), p32, k, replace)
         assert np.array_equal(got, want), (case, n, k, replace)
         assert np.array_equal(mine_rs.random_sample(3), tail_want), (case, "stream position")
+
+
+def _live_reference_ext(name):
+    """The reference's own C++ op, compiled unmodified into oracle/_ref/ by oracle/build_ref.py (build container only)."""
+    import importlib.util
+    import os
+
+    so = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "oracle", "_ref", name, name + ".so")
+    if not os.path.exists(so):
+        pytest.skip(f"{so} not built (the reference tree only exists in the build container)")
+    import torch  # noqa: F401  (the extension links against libtorch)
+
+    spec = importlib.util.spec_from_file_location(name, so)
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod
+
+
+@pytest.mark.parametrize("iou_enable,sigma", [(False, 0.025), (True, 0.025), (True, 0.5)])
+def test_c_oracle_equals_the_compiled_reference_ops(iou_enable, sigma):
+    """Fuzz: oracle/vote_oracle.c against the reference's compiled vote_ext / cluster_ext on clustered random boxes,
+    including the iou_enable score decay that no shipped config (and hence no golden) switches on."""
+    import torch
+
+    vote_ext = _live_reference_ext("vote_ext")
+    cluster_ext = _live_reference_ext("cluster_ext")
+    rs = np.random.RandomState(77)
+    for case in range(12):
+        n, ncls, nobj = int(rs.randint(1, 400)), int(rs.randint(1, 6)), int(rs.randint(1, 40))
+        ctr = rs.uniform(50, 590, (nobj, 2))
+        wh = rs.uniform(20, 200, (nobj, 2))
+        pick = rs.randint(0, nobj, n)
+        c = ctr[pick] + rs.normal(0, 3, (n, 2))
+        s = wh[pick] * np.exp(rs.normal(0, 0.06, (n, 2)))
+        boxes = np.concatenate([c - s / 2, c + s / 2], 1).astype(np.float32)
+        labels = rs.randint(0, ncls, n).astype(np.int64)
+        cs = rs.uniform(0.05, 1, n).astype(np.float32)
+        vs = rs.uniform(0.05, 1, n).astype(np.float32)
+        if np.unique(cs).size != n:
+            continue
+        T = torch.from_numpy
+        for gmode, fn in ((False, vote_ext.vote_nms), (True, vote_ext.global_vote_nms)):
+            rb, rl, rsc = fn(T(boxes), T(cs), T(vs.copy()), T(labels), 0.65, iou_enable, sigma)      # vote_wrapper.py:32
+            ob, ol, os_, inst, cnum = orc.vote_nms_c(boxes, cs, vs, labels, 0.65, global_mode=gmode, iou_enable=iou_enable, sigma=sigma)
+            assert rb.shape[0] == ob.shape[0], (case, gmode)
+            assert np.array_equal(rb.numpy().view(np.uint32), ob.view(np.uint32)), (case, gmode)
+            assert np.array_equal(rl.numpy(), ol) and np.array_equal(rsc.numpy(), os_)
+        ri, rn = cluster_ext.cluster_nms(T(boxes), T(cs), T(labels), 0.65)
+        _, _, _, inst, cnum = orc.vote_nms_c(boxes, cs, cs, labels, 0.65)
+        assert np.array_equal(ri.numpy(), inst) and np.array_equal(rn.numpy(), cnum)
+
+
+@pytest.mark.parametrize("case", range(3))
+def test_ops_iou_enable_match_reference_bit_exact(case):
+    """iou_enable=True (vote_ext.cpp:164-167) through the reference's wrappers: golden ops_iou.npz vs the C oracle."""
+    g = hp.load("ops_iou.npz")
+    cfg = dict(type="vote", iou_threshold=0.65, cluster_score=["cls", "iou"], vote_score=["iou", "cls"], iou_enable=True,
+               sigma=float(g[f"c{case}/sigma"]))
+    for nm, gm in (("vote", False), ("gvote", True)):
+        d, l = orc.vote_nms_wrapper(g[f"c{case}/boxes"], g[f"c{case}/cls"], g[f"c{case}/labels"].astype(np.int64), cfg,
+                                    score_factor=g[f"c{case}/ctr"], global_mode=gm)
+        assert np.array_equal(d.view(np.uint32), g[f"c{case}/{nm}_dets"].view(np.uint32)), nm
+        assert np.array_equal(l, g[f"c{case}/{nm}_labels"].astype(np.int64))
