@@ -281,3 +281,28 @@ def test_ops_iou_enable_match_reference_bit_exact(case):
                                     score_factor=g[f"c{case}/ctr"], global_mode=gm)
         assert np.array_equal(d.view(np.uint32), g[f"c{case}/{nm}_dets"].view(np.uint32)), nm
         assert np.array_equal(l, g[f"c{case}/{nm}_labels"].astype(np.int64))
+
+
+def test_greedy_nms_restatement_equals_torchvision():
+    """mmcv.ops.batched_nms is not in the reference tree (mmcv==1.3.18, requirements.txt:8) and its branch of
+    _get_bboxes_single (radet_head.py:159-163) has no reference golden; torchvision.ops.batched_nms implements the same
+    greedy `iou > thr` rule (SURVEY §8c names it as the second oracle): keep sets and order must agree."""
+    import torch
+    import torchvision
+
+    rs = np.random.RandomState(5)
+    for case in range(30):
+        n, ncls, nobj = int(rs.randint(1, 500)), int(rs.randint(1, 8)), int(rs.randint(1, 40))
+        ctr = rs.uniform(50, 590, (nobj, 2))
+        wh = rs.uniform(20, 200, (nobj, 2))
+        pick = rs.randint(0, nobj, n)
+        c = ctr[pick] + rs.normal(0, 3, (n, 2))
+        s = wh[pick] * np.exp(rs.normal(0, 0.06, (n, 2)))
+        boxes = np.concatenate([c - s / 2, c + s / 2], 1).astype(np.float32)
+        labels = rs.randint(0, ncls, n).astype(np.int64)
+        sc = rs.uniform(0.05, 1, n).astype(np.float32)
+        if np.unique(sc).size != n:
+            continue
+        keep = orc.greedy_nms_keep(boxes, sc, labels, 0.65)
+        tv = torchvision.ops.boxes._batched_nms_vanilla(torch.from_numpy(boxes), torch.from_numpy(sc), torch.from_numpy(labels), 0.65)
+        assert np.array_equal(keep, tv.numpy()), case
