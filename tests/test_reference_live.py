@@ -1,0 +1,96 @@
+"""CPU, build container only: the oracle against the UNMODIFIED reference executed live (through oracle/ref_shim.py) on
+randomly drawn small problems — wider than the committed goldens (odd image sizes, empty images, many option
+combinations).  Skipped wherever /root/reference is absent (the GPU box)."""
+import os
+
+import numpy as np
+import pytest
+
+from oracle import radet_oracle as orc
+from radet_b200 import synthetic as syn
+
+pytestmark = pytest.mark.skipif(not os.path.isdir("/root/reference/radet"), reason="the reference tree only exists in the build container")
+
+
+@pytest.fixture(scope="module")
+def shim():
+    from oracle import ref_shim
+
+    ref_shim.install()
+    return ref_shim
+
+
+def _random_workload(rs, i):
+    H, W = int(rs.randint(64, 301)), int(rs.randint(64, 401))
+    C = int(rs.randint(1, 31))
+    g0 = int(rs.randint(0, 4))
+    return syn.Workload(f"live{i}_{H}x{W}", H, W, C, int(rs.randint(1, 4)), g0, g0 + int(rs.randint(0, 10)), 1000 + i)
+
+
+@pytest.mark.parametrize("opts", [dict(), dict(adapt_positive_num=True), dict(multiply_samplepro_for_weight=True),
+                                  dict(balance_sample=False), dict(positive_num=3), dict(positive_num=17, neg_threshold=0.5)])
+def test_assignment_live(shim, opts):
+    la = shim.build_reference_assigner(**opts)
+    rs = np.random.RandomState(hash(tuple(sorted(opts))) % 2 ** 31)
+    for i in range(10):
+        wl = _random_workload(rs, i)
+        for im in syn.make_batch(wl):
+            np.random.seed(im.seed)
+            res = la(dict(img_shape=(im.H, im.W, 3), gt_bboxes=im.gt_bboxes, gt_labels=im.gt_labels,
+                          distance_maps=shim.BitmapMasksStandIn(im.masks)))
+            tail = np.random.random_sample(2)
+            idx, w, used = orc.assign_image_seeded(im.gt_bboxes, im.masks, im.H, im.W, im.seed, **opts)
+            assert np.array_equal(idx, res["points_to_gt_index"]), (wl.name, opts)
+            assert np.array_equal(w, res["points_weight"]), (wl.name, opts)
+            r2 = np.random.RandomState(im.seed)
+            r2.random_sample(used)
+            assert np.array_equal(r2.random_sample(2), tail), (wl.name, opts, "stream position")
+
+
+def test_targets_loss_and_get_bboxes_live(shim):
+    import torch
+
+    rs = np.random.RandomState(4321)
+    la = shim.build_reference_assigner()
+    for i in range(6):
+        wl = _random_workload(rs, 100 + i)
+        batch = syn.make_batch(wl)
+        assigned = []
+        for im in batch:
+            np.random.seed(im.seed)
+            r = la(dict(img_shape=(im.H, im.W, 3), gt_bboxes=im.gt_bboxes, gt_labels=im.gt_labels, distance_maps=shim.BitmapMasksStandIn(im.masks)))
+            assigned.append((r["points_to_gt_index"], r["points_weight"]))
+        idx_l, w_l = [a[0] for a in assigned], [a[1] for a in assigned]
+        ho = syn.make_head_outputs(wl, batch, idx_l)
+        thr = float(rs.choice([0.02, 0.05, 0.2]))
+        typ = str(rs.choice(["vote", "global_vote"]))
+        nms_pre = int(rs.choice([50, 1000]))
+        head = shim.build_reference_head(wl.C, nms_type=typ, score_thr=thr, nms_pre=nms_pre, max_per_img=int(rs.choice([5, 100])))
+        metas = syn.img_metas(batch, scale=float(rs.choice([1.0, 0.75, 1.6])))
+        T = lambda a: torch.from_numpy(np.ascontiguousarray(a))
+        cls = [T(m).requires_grad_() for m in ho.cls]
+        box = [T(m).requires_grad_() for m in ho.bbox]
+        iou = [T(m).requires_grad_() for m in ho.iou]
+        gtb, gtl = [T(im.gt_bboxes) for im in batch], [T(im.gt_labels) for im in batch]
+        losses = head.loss(cls, box, iou, gtb, gtl, [T(a) for a in idx_l], [T(a) for a in w_l], metas)
+        (losses["loss_cls"] + losses["loss_bbox"] + losses["loss_iou"]).backward()
+        o = orc.head_loss(ho.cls, ho.bbox, ho.iou, [im.gt_bboxes for im in batch], [im.gt_labels for im in batch], idx_l, w_l,
+                          wl.C, wl.H, wl.W)
+        for k in ("loss_cls", "loss_bbox", "loss_iou"):
+            assert abs(o[k] - float(losses[k].detach())) <= 1e-5 * abs(float(losses[k].detach())) + 1e-7, (wl.name, k)
+        for mine, ref in zip(o["grad_cls"] + o["grad_bbox"] + o["grad_iou"], cls + box + iou):
+            g = np.zeros(mine.shape, np.float32) if ref.grad is None else ref.grad.numpy()
+            np.testing.assert_allclose(mine, g, rtol=1e-4, atol=1e-6 * max(1e-30, float(np.abs(g).max())))
+        with torch.no_grad():
+            res = head.get_bboxes([T(m) for m in ho.cls], [T(m) for m in ho.bbox], [T(m) for m in ho.iou], metas, rescale=True)
+        sf = np.asarray(metas[0]["scale_factor"], np.float32)
+        cfgd = dict(type=typ, iou_threshold=0.65, cluster_score=["cls", "iou"], vote_score=["iou", "cls"], iou_enable=False)
+        for b, (im, (dets, labs)) in enumerate(zip(batch, res)):
+            od, ol = orc.get_bboxes_image([m[b] for m in ho.cls], [m[b] for m in ho.bbox], [m[b] for m in ho.iou], (im.H, im.W, 3), sf,
+                                          score_thr=thr, nms_pre=nms_pre, max_per_img=head.test_cfg.max_per_img, nms_cfg=cfgd)
+            dets, labs = dets.numpy(), labs.numpy().reshape(-1)
+            assert dets.shape[0] == od.shape[0], (wl.name, typ, thr)
+            if od.shape[0]:
+                assert np.array_equal(dets[:, :4].view(np.uint32), od[:, :4].view(np.uint32)), (wl.name, typ, thr)
+                np.testing.assert_allclose(dets[:, 4], od[:, 4], rtol=4e-7)      # torch-CPU sigmoid flavour
+                assert np.array_equal(labs, ol)
