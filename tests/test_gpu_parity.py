@@ -848,3 +848,14 @@ def test_get_bboxes_iou_enable_vs_oracle(typ):
         k = int(num[b])
         assert k == od.shape[0]
         assert np.array_equal(dets[b, :k].cpu().numpy().view(np.uint32), od.view(np.uint32)) and np.array_equal(labels[b, :k].cpu().numpy(), ol)
+@pytest.mark.gpu
+@pytest.mark.parametrize("positive_num", [1, 3, 17, 32])
+def test_assignment_other_positive_num(positive_num):
+    """positive_num other than the config's 10 (1 and RADET_MAX_POSITIVE_NUM = 32 included), odd image size, against the
+    oracle (itself checked against the live reference for 3 and 17 in tests/test_reference_live.py)."""
+    wl = syn.Workload("pn_211x333_B4_C5_G0-12", 211, 333, 5, 4, 0, 12, 23)
+    batch = syn.make_batch(wl)
+    shapes, counts, boxes, idx, w, used = _device_assign(wl, batch, positive_num=positive_num)
+    for b, im in enumerate(batch):
+        oi, ow, ou = orc.assign_image_seeded(im.gt_bboxes, im.masks, im.H, im.W, im.seed, positive_num=positive_num)
+        assert np.array_equal(idx[b].cpu().numpy(), oi) and np.array_equal(w[b].cpu().numpy(), ow) and int(used[b]) == ou
