@@ -354,6 +354,32 @@ def head_loss(cls_maps, bbox_maps, iou_maps, gt_bboxes_list, gt_labels_list, idx
     return out
 
 
+# --------------------------------------------------------------------------- standalone TBLR coder
+def tblr_encode(priors, gts, normalizer=0.125):
+    """bboxes2tblr (tblr_bbox_coder.py:71-114), normalize_by_wh=True, scalar normalizer; float32, one rounding per op."""
+    f = np.float32
+    p, g = np.asarray(priors, f), np.asarray(gts, f)
+    cx, cy = (p[:, 0] + p[:, 2]) / f(2), (p[:, 1] + p[:, 3]) / f(2)
+    w, h = p[:, 2] - p[:, 0], p[:, 3] - p[:, 1]
+    loc = np.stack([(cy - g[:, 1]) / h, (g[:, 3] - cy) / h, (cx - g[:, 0]) / w, (g[:, 2] - cx) / w], 1).astype(f)
+    return (loc / f(normalizer)).astype(f)
+
+
+def tblr_decode(priors, tblr, normalizer=0.125, max_shape=None, clip_border=True):
+    """tblr2bboxes (tblr_bbox_coder.py:117-172)."""
+    f = np.float32
+    p, t = np.asarray(priors, f), np.asarray(tblr, f)
+    loc = (t * f(normalizer)).astype(f)
+    cx, cy = (p[:, 0] + p[:, 2]) / f(2), (p[:, 1] + p[:, 3]) / f(2)
+    w, h = p[:, 2] - p[:, 0], p[:, 3] - p[:, 1]
+    top, bot, left, right = loc[:, 0] * h, loc[:, 1] * h, loc[:, 2] * w, loc[:, 3] * w
+    out = np.stack([cx - left, cy - top, cx + right, cy + bot], 1).astype(f)
+    if clip_border and max_shape is not None:
+        out[:, 0::2] = np.clip(out[:, 0::2], 0, f(max_shape[1]))
+        out[:, 1::2] = np.clip(out[:, 1::2], 0, f(max_shape[0]))
+    return out
+
+
 # --------------------------------------------------------------------------- standalone LOSSES modules
 def weight_reduce(loss, weight=None, reduction="mean", avg_factor=None):
     """losses/utils.py:26-52."""

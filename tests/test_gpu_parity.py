@@ -859,3 +859,18 @@ def test_assignment_other_positive_num(positive_num):
     for b, im in enumerate(batch):
         oi, ow, ou = orc.assign_image_seeded(im.gt_bboxes, im.masks, im.H, im.W, im.seed, positive_num=positive_num)
         assert np.array_equal(idx[b].cpu().numpy(), oi) and np.array_equal(w[b].cpu().numpy(), ow) and int(used[b]) == ou
+
+
+@pytest.mark.gpu
+def test_tblr_coder_golden_bit_exact():
+    """plugin.TBLRBBoxCoder.encode / decode (radet_tblr_encode / radet_tblr_decode) against the reference's golden output."""
+    g = hp.load("coder.npz")
+    pri, gts, tblr = (torch.from_numpy(g[k]).to(DEV) for k in ("priors", "gts", "tblr"))
+    for nrm in (0.125, 4.0):
+        coder = P.TBLRBBoxCoder(normalizer=nrm)
+        assert np.array_equal(coder.encode(pri, gts).cpu().numpy().view(np.uint32), g[f"enc_{nrm}"].view(np.uint32))
+        assert np.array_equal(coder.decode(pri, tblr).cpu().numpy().view(np.uint32), g[f"dec_{nrm}"].view(np.uint32))
+        assert np.array_equal(coder.decode(pri, tblr, max_shape=(480, 640, 3)).cpu().numpy().view(np.uint32),
+                              g[f"dec_clip_{nrm}"].view(np.uint32))
+    nc = P.TBLRBBoxCoder(normalizer=0.125, clip_border=False)
+    assert np.array_equal(nc.decode(pri, tblr, max_shape=(480, 640, 3)).cpu().numpy().view(np.uint32), g["dec_noclip_0.125"].view(np.uint32))

@@ -306,3 +306,16 @@ def test_greedy_nms_restatement_equals_torchvision():
         keep = orc.greedy_nms_keep(boxes, sc, labels, 0.65)
         tv = torchvision.ops.boxes._batched_nms_vanilla(torch.from_numpy(boxes), torch.from_numpy(sc), torch.from_numpy(labels), 0.65)
         assert np.array_equal(keep, tv.numpy()), case
+
+
+def test_tblr_coder_matches_reference_bit_exact():
+    """TBLRBBoxCoder.encode / decode (tblr_bbox_coder.py:29-68, 71-172) on explicit lists: square and non-square priors,
+    normalizer 1/8 (the config's) and 4.0 (the class default), with / without clipping."""
+    g = hp.load("coder.npz")
+    for nrm in (0.125, 4.0):
+        assert np.array_equal(orc.tblr_encode(g["priors"], g["gts"], nrm).view(np.uint32), g[f"enc_{nrm}"].view(np.uint32))
+        assert np.array_equal(orc.tblr_decode(g["priors"], g["tblr"], nrm).view(np.uint32), g[f"dec_{nrm}"].view(np.uint32))
+        assert np.array_equal(orc.tblr_decode(g["priors"], g["tblr"], nrm, max_shape=(480, 640, 3)).view(np.uint32),
+                              g[f"dec_clip_{nrm}"].view(np.uint32))
+    assert np.array_equal(orc.tblr_decode(g["priors"], g["tblr"], 0.125, max_shape=(480, 640, 3), clip_border=False).view(np.uint32),
+                          g["dec_noclip_0.125"].view(np.uint32))
