@@ -94,3 +94,79 @@ def test_targets_loss_and_get_bboxes_live(shim):
                 assert np.array_equal(dets[:, :4].view(np.uint32), od[:, :4].view(np.uint32)), (wl.name, typ, thr)
                 np.testing.assert_allclose(dets[:, 4], od[:, 4], rtol=4e-7)      # torch-CPU sigmoid flavour
                 assert np.array_equal(labs, ol)
+
+
+def test_candidates_without_nms_live(shim):
+    """get_bboxes(with_nms=False) (radet_head.py:165-169) on random problems: rows compared as sets."""
+    import torch
+
+    rs = np.random.RandomState(99)
+    la = shim.build_reference_assigner()
+    for i in range(5):
+        wl = _random_workload(rs, 200 + i)
+        batch = syn.make_batch(wl)
+        idx_l = []
+        for im in batch:
+            np.random.seed(im.seed)
+            idx_l.append(la(dict(img_shape=(im.H, im.W, 3), gt_bboxes=im.gt_bboxes, gt_labels=im.gt_labels,
+                                 distance_maps=shim.BitmapMasksStandIn(im.masks)))["points_to_gt_index"])
+        ho = syn.make_head_outputs(wl, batch, idx_l)
+        thr, nms_pre = float(rs.choice([0.03, 0.1])), int(rs.choice([20, 1000]))
+        head = shim.build_reference_head(wl.C, score_thr=thr, nms_pre=nms_pre)
+        scale = float(rs.choice([1.0, 1.3]))
+        metas = syn.img_metas(batch, scale=scale)
+        T = lambda a: torch.from_numpy(np.ascontiguousarray(a))
+        with torch.no_grad():
+            res = head.get_bboxes([T(m) for m in ho.cls], [T(m) for m in ho.bbox], [T(m) for m in ho.iou], metas, rescale=True,
+                                  with_nms=False)
+        for b, (im, (rows, cats)) in enumerate(zip(batch, res)):
+            bx, sc, ctr, ocats, anc = orc.select_candidates([m[b] for m in ho.cls], [m[b] for m in ho.bbox], [m[b] for m in ho.iou],
+                                                            (im.H, im.W, 3), np.full(4, scale, np.float32), thr, nms_pre)
+            rows, cats = rows.numpy(), cats.numpy().reshape(-1)
+            if bx.shape[0] == 0:
+                assert rows.shape[0] == 0
+                continue
+            full = np.concatenate([bx, (sc * ctr)[:, None], anc], 1).astype(np.float32)
+            assert rows.shape == full.shape, wl.name
+            o = np.lexsort((cats, rows[:, 8], rows[:, 7], rows[:, 6], rows[:, 5], rows[:, 3], rows[:, 2], rows[:, 1], rows[:, 0]))
+            oo = np.lexsort((ocats, full[:, 8], full[:, 7], full[:, 6], full[:, 5], full[:, 3], full[:, 2], full[:, 1], full[:, 0]))
+            cols = [0, 1, 2, 3, 5, 6, 7, 8]
+            assert np.array_equal(rows[o][:, cols].view(np.uint32), full[oo][:, cols].view(np.uint32)), wl.name
+            np.testing.assert_allclose(rows[o][:, 4], full[oo][:, 4], rtol=4e-7)
+            assert np.array_equal(cats[o], ocats[oo])
+
+
+def test_standalone_losses_live(shim):
+    import torch
+    from radet.models.losses import CrossEntropyLoss, FocalLoss, GIoULoss
+
+    rs = np.random.RandomState(7)
+    for i in range(8):
+        n, C = int(rs.randint(1, 200)), int(rs.randint(1, 40))
+        gamma, alpha = float(rs.choice([2.0, 1.5, 0.5])), float(rs.choice([0.25, 0.5]))
+        pred = rs.normal(-1, 3, (n, C)).astype(np.float32)
+        target = rs.randint(0, C + 1, n).astype(np.int64)
+        w = rs.uniform(0, 2, n).astype(np.float32)
+        x = torch.from_numpy(pred).requires_grad_()
+        out = FocalLoss(use_sigmoid=True, gamma=gamma, alpha=alpha, loss_weight=1.5)(x, torch.from_numpy(target), torch.from_numpy(w), avg_factor=3.0)
+        out.backward()
+        l, g = orc.standalone_loss("focal", pred, target, w, "mean", 3.0, loss_weight=1.5, gamma=gamma, alpha=alpha, dtype="float32")
+        np.testing.assert_allclose(l, out.detach().numpy(), rtol=3e-6)
+        np.testing.assert_allclose(g, x.grad.numpy(), rtol=5e-5, atol=1e-8)
+        c = rs.uniform(0, 500, (n, 2))
+        s = rs.uniform(1, 200, (n, 2))
+        tb = np.concatenate([c - s / 2, c + s / 2], 1).astype(np.float32)
+        pb = (tb + rs.normal(0, 20, (n, 4))).astype(np.float32)
+        x = torch.from_numpy(pb).requires_grad_()
+        out = GIoULoss(eps=1e-6, loss_weight=2.0)(x, torch.from_numpy(tb), torch.from_numpy(w), reduction_override="sum")
+        out.backward()
+        l, g = orc.standalone_loss("giou", pb, tb, w, "sum", None, loss_weight=2.0, dtype="float32")
+        np.testing.assert_allclose(l, out.detach().numpy(), rtol=3e-6)
+        np.testing.assert_allclose(g, x.grad.numpy(), rtol=5e-5, atol=1e-7)
+        logit, soft = rs.normal(0, 3, n).astype(np.float32), rs.uniform(0, 1, n).astype(np.float32)
+        x = torch.from_numpy(logit).requires_grad_()
+        out = CrossEntropyLoss(use_sigmoid=True)(x, torch.from_numpy(soft), torch.from_numpy(w), avg_factor=float(w.sum()) + 1)
+        out.backward()
+        l, g = orc.standalone_loss("bce", logit, soft, w, "mean", float(w.sum()) + 1, dtype="float32")
+        np.testing.assert_allclose(l, out.detach().numpy(), rtol=3e-6)
+        np.testing.assert_allclose(g, x.grad.numpy(), rtol=5e-5, atol=1e-8)
