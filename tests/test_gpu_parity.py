@@ -874,3 +874,48 @@ def test_tblr_coder_golden_bit_exact():
                               g[f"dec_clip_{nrm}"].view(np.uint32))
     nc = P.TBLRBBoxCoder(normalizer=0.125, clip_border=False)
     assert np.array_equal(nc.decode(pri, tblr, max_shape=(480, 640, 3)).cpu().numpy().view(np.uint32), g["dec_noclip_0.125"].view(np.uint32))
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("key", ["small", "odd"])
+def test_loss_other_hyper_parameters(key):
+    """gamma != 2 (the general-gamma instantiation of both dense kernels), other alpha / loss weights / eps, against the
+    oracle (fp32 and fp64); `odd` has plane sizes that are not multiples of 4 (register kernel), `small` the TMA one."""
+    if key == "odd":
+        wl = syn.Workload("odd", 100, 100, 7, 3, 2, 5, 11)
+        batch = syn.make_batch(wl)
+        a = [orc.assign_image_seeded(im.gt_bboxes, im.masks, im.H, im.W, im.seed) for im in batch]
+        idx_l, w_l = [x[0] for x in a], [x[1] for x in a]
+        ho = syn.make_head_outputs(wl, batch, idx_l)
+    else:
+        wl, batch, idx_l, w_l, ho = _head_inputs("small")
+    cls, bbox, iou = _to_dev(ho)
+    counts, boxes, labels = _gt_dev(batch)
+    hp_ = dict(gamma=1.5, alpha=0.4, w_cls=0.7, w_bbox=1.3, w_iou=0.9, eps=1e-5)
+    losses, grads = F.loss_fwd_bwd(GEOM, wl.C, cls, bbox, iou, counts, boxes, labels, torch.from_numpy(np.stack(idx_l)).to(DEV),
+                                   torch.from_numpy(np.stack(w_l)).to(DEV), F.LossConfig(**hp_))
+    gt_b, gt_l = [b.gt_bboxes for b in batch], [b.gt_labels for b in batch]
+    losses = losses.cpu().numpy()
+    for dtype, lt, gr, ga in (("float32", 1e-5, 1e-4, 1e-6), ("float64", 5e-6, 5e-5, 1e-6)):
+        o = orc.head_loss(ho.cls, ho.bbox, ho.iou, gt_b, gt_l, idx_l, w_l, wl.C, wl.H, wl.W, dtype=dtype, **hp_)
+        for i, k in enumerate(("loss_cls", "loss_bbox", "loss_iou")):
+            assert abs(losses[i] - o[k]) <= lt * abs(o[k]), (k, dtype)
+        _check_grads(grads[0], o["grad_cls"], gr, ga)
+        _check_grads(grads[1], o["grad_bbox"], gr, ga)
+        _check_grads(grads[2], o["grad_iou"], gr, ga)
+
+
+@pytest.mark.gpu
+def test_standalone_focal_other_gamma():
+    rs = np.random.RandomState(3)
+    pred = rs.normal(-1, 3, (123, 9)).astype(np.float32)
+    target = rs.randint(0, 10, 123).astype(np.int64)
+    w = rs.uniform(0, 2, 123).astype(np.float32)
+    for gamma, alpha in ((1.5, 0.4), (0.5, 0.25), (3.0, 0.75)):
+        x = torch.from_numpy(pred).to(DEV).requires_grad_()
+        out = P.FocalLoss(use_sigmoid=True, gamma=gamma, alpha=alpha, loss_weight=1.5)(x, torch.from_numpy(target).to(DEV),
+                                                                                        torch.from_numpy(w).to(DEV), avg_factor=3.0)
+        out.backward()
+        l, g = orc.standalone_loss("focal", pred, target, w, "mean", 3.0, loss_weight=1.5, gamma=gamma, alpha=alpha, dtype="float64")
+        np.testing.assert_allclose(out.item(), l, rtol=1e-5)
+        np.testing.assert_allclose(x.grad.cpu().numpy(), g, rtol=1e-4, atol=1e-6 * float(np.abs(g).max()))
