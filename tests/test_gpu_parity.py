@@ -919,3 +919,25 @@ def test_standalone_focal_other_gamma():
         l, g = orc.standalone_loss("focal", pred, target, w, "mean", 3.0, loss_weight=1.5, gamma=gamma, alpha=alpha, dtype="float64")
         np.testing.assert_allclose(out.item(), l, rtol=1e-5)
         np.testing.assert_allclose(x.grad.cpu().numpy(), g, rtol=1e-4, atol=1e-6 * float(np.abs(g).max()))
+
+
+@pytest.mark.gpu
+def test_loss_two_phase_normaliser_sync_path():
+    """sync_num_pos: radet_loss_fwd_bwd(phases=1) -> reduce_mean of the two normalisers -> phases=2.  In a single process
+    the reduce is the identity, so the split call must give exactly what the one-call form gives (same kernels)."""
+    wl, batch, idx_l, w_l, ho = _head_inputs("cfg1")
+    cls, bbox, iou = _to_dev(ho)
+    counts, boxes, labels = _gt_dev(batch)
+    idx = torch.from_numpy(np.stack(idx_l)).to(DEV)
+    w = torch.from_numpy(np.stack(w_l)).to(DEV)
+    l1, g1 = F.loss_fwd_bwd(GEOM, wl.C, cls, bbox, iou, counts, boxes, labels, idx, w, F.LossConfig())
+    l2, g2 = F.loss_fwd_bwd(GEOM, wl.C, cls, bbox, iou, counts, boxes, labels, idx, w, F.LossConfig(), sync_group="world")
+    assert torch.equal(l1, l2)
+    for a, b in zip(g1[0] + g1[1] + g1[2], g2[0] + g2[1] + g2[2]):
+        assert torch.equal(a, b)
+    head = P.build_head(dict(type="RADetHead", num_classes=wl.C, in_channels=8, feat_channels=8, stacked_convs=1,
+                             norm_cfg=dict(type="GN", num_groups=4, requires_grad=True), sync_num_pos=True)).to(DEV)
+    T = lambda a: torch.from_numpy(a).to(DEV)
+    out = head.loss(cls, bbox, iou, [T(b.gt_bboxes) for b in batch], [T(b.gt_labels) for b in batch], [T(i) for i in idx_l],
+                    [T(x) for x in w_l], syn.img_metas(batch))
+    assert abs(float(out["loss_cls"]) - float(l1[0])) <= 1e-7 * abs(float(l1[0]))
