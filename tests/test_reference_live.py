@@ -170,3 +170,34 @@ def test_standalone_losses_live(shim):
         l, g = orc.standalone_loss("bce", logit, soft, w, "mean", float(w.sum()) + 1, dtype="float32")
         np.testing.assert_allclose(l, out.detach().numpy(), rtol=3e-6)
         np.testing.assert_allclose(g, x.grad.numpy(), rtol=5e-5, atol=1e-8)
+
+
+def test_get_targets_live(shim):
+    """RADetHead.get_targets (radet_head.py:290-392) on random problems: labels (incl. the idx == 0 -> last GT label quirk),
+    TBLR targets, weights and priors, level-major / image-minor, bit-exact."""
+    import torch
+
+    rs = np.random.RandomState(555)
+    la = shim.build_reference_assigner()
+    for i in range(6):
+        wl = _random_workload(rs, 300 + i)
+        batch = syn.make_batch(wl)
+        idx_l, w_l = [], []
+        for im in batch:
+            np.random.seed(im.seed)
+            r = la(dict(img_shape=(im.H, im.W, 3), gt_bboxes=im.gt_bboxes, gt_labels=im.gt_labels, distance_maps=shim.BitmapMasksStandIn(im.masks)))
+            idx_l.append(r["points_to_gt_index"])
+            w_l.append(r["points_weight"])
+        ho = syn.make_head_outputs(wl, batch, idx_l)
+        head = shim.build_reference_head(wl.C)
+        metas = syn.img_metas(batch)
+        T = lambda a: torch.from_numpy(np.ascontiguousarray(a))
+        cls, box = [T(m) for m in ho.cls], [T(m) for m in ho.bbox]
+        anchors, _ = head.get_anchors([m.shape[-2:] for m in cls], metas, device="cpu")
+        lab, tg, wt, anc = head.get_targets(anchors, cls, box, [T(im.gt_bboxes) for im in batch], [T(im.gt_labels) for im in batch],
+                                            [T(a) for a in idx_l], [T(a) for a in w_l], metas)
+        olab, otg, owt, oanc = orc.get_targets([im.gt_bboxes for im in batch], [im.gt_labels for im in batch], idx_l, w_l, wl.C, wl.H, wl.W)
+        for l in range(5):
+            assert np.array_equal(lab[l].numpy(), olab[l]), (wl.name, l)
+            assert np.array_equal(tg[l].numpy().view(np.uint32), otg[l].view(np.uint32)), (wl.name, l)
+            assert np.array_equal(wt[l].numpy(), owt[l]) and np.array_equal(anc[l].numpy(), oanc[l])
