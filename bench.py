@@ -32,13 +32,15 @@ from radet_b200 import synthetic as syn  # noqa: E402
 
 L2_BYTES = 126 * 1024 * 1024
 NMS_CFG = dict(iou_threshold=0.65, cluster_score=["cls", "iou"], vote_score=["iou", "cls"], iou_enable=False)
+METRIC = "images/s (assign + loss fwd/bwd + decode/vote-NMS)"
 
 
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=2000)
-    ap.add_argument("--warmup", type=int, default=50)
+    ap.add_argument("--steps", type=int, default=None, help="timed steps per block (default 2000; 20 for --impl reference)")
+    ap.add_argument("--warmup", type=int, default=None, help="untimed warm-up steps (default 50; 3 for --impl reference)")
+    ap.add_argument("--repeats", type=int, default=9, help="the --steps block is timed this many times; the median is reported")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="cfg2", choices=sorted(syn.WORKLOADS))
     ap.add_argument("--batch", type=int, default=0, help="images per GPU (default: the workload's)")
@@ -48,43 +50,68 @@ def parse():
     ap.add_argument("--profile", action="store_true", help="few eager steps, nothing else (for ncu)")
     ap.add_argument("--serial", action="store_true", help="one stream: train and inference branches back to back")
     ap.add_argument("--stages", default="assign,loss,detect", help="development aid: run only these stages of the step")
-    ap.add_argument("--inflight", type=int, default=8, help="steps in flight: step graphs are replayed round-robin on this many "
-                    "streams, the assignment running this many batches ahead (1 = one step at a time)")
+    ap.add_argument("--inflight", type=int, default=8, help="steps in flight: every lane (stream) replays graphs of consecutive steps, "
+                    "the assignment running this many batches ahead (1 = one step at a time)")
+    ap.add_argument("--no-gate", action="store_true", help="do not hold the timed block behind a device-side gate")
+    ap.add_argument("--no-side-configs", action="store_true", help="skip the cfg3/cfg4/cfg5 side measurements")
     ap.add_argument("--no-prefetch", action="store_true", help="assignment and loss of the same batch in sequence (no one-batch-ahead assignment)")
     ap.add_argument("--sets", type=int, default=0, help="rotating input sets (default: enough to exceed 2x L2)")
     ap.add_argument("--cpu-baseline-json", action="store_true", help=argparse.SUPPRESS)
-    return ap.parse_args()
+    a = ap.parse_args()
+    ref = a.impl == "reference"
+    a.steps = (20 if ref else 2000) if a.steps is None else max(1, a.steps)
+    a.warmup = (3 if ref else 50) if a.warmup is None else max(0, a.warmup)
+    return a
 
 
-# ------------------------------------------------------------------------------------------------ CPU path (oracle)
-def _cpu_assign(args):
+# ------------------------------------------------------------------------------------------------ CPU path (reference arm)
+# The Python reference cannot travel to the GPU box (mmcv is not installable offline), so the CPU arm is the numpy
+# restatement in oracle/ for assignment / loss / candidate selection, and the REFERENCE'S OWN compiled vote_ext.cpp
+# (oracle/_ref/vote_ext, built unmodified by oracle/build_ref.py) for the vote-NMS stage when that binary is present.
+_CPU = {}     # inputs handed to the fork pool ONCE (workers inherit them copy-on-write; tasks carry an image index)
+
+
+def _cpu_assign(i):
     from oracle import radet_oracle as orc
 
-    boxes, masks, H, W, seed = args
-    return orc.assign_image_seeded(boxes, masks, H, W, seed)[:2]
+    im = _CPU["batch"][i]
+    return orc.assign_image_seeded(im.gt_bboxes, im.masks, im.H, im.W, im.seed)[:2]
 
 
-def _cpu_detect(args):
+def _cpu_detect(i):
     from oracle import radet_oracle as orc
 
-    cls, bbox, iou, H, W, thr = args
-    return orc.get_bboxes_image(cls, bbox, iou, (H, W, 3), np.ones(4, np.float32), score_thr=thr,
-                                nms_cfg=dict(type="vote", **NMS_CFG))
+    wl, ho, im, ext = _CPU["wl"], _CPU["ho"], _CPU["batch"][i], _CPU["vote_ext"]
+    cls, bbox, iou = [m[i] for m in ho.cls], [m[i] for m in ho.bbox], [m[i] for m in ho.iou]
+    if ext is None:
+        return orc.get_bboxes_image(cls, bbox, iou, (im.H, im.W, 3), np.ones(4, np.float32), score_thr=wl.score_thr,
+                                    nms_pre=wl.nms_pre, max_per_img=wl.max_per_img, nms_cfg=dict(type="vote", **NMS_CFG))
+    import torch
+
+    boxes, sc, ctr, cats, _ = orc.select_candidates(cls, bbox, iou, (im.H, im.W, 3), np.ones(4, np.float32), wl.score_thr,
+                                                    wl.nms_pre)
+    if boxes.shape[0] == 0:
+        return np.zeros((0, 5), np.float32), np.zeros((0,), np.int64)
+    cs = torch.from_numpy(sc) * torch.from_numpy(ctr)            # vote_wrapper.py:14-25 with the shipped list-valued score types
+    vb, vl, vsc = ext.vote_nms(torch.from_numpy(boxes), cs, cs.clone(), torch.from_numpy(cats), NMS_CFG["iou_threshold"],
+                               NMS_CFG["iou_enable"], 0.025)
+    dets = torch.cat([vb, vsc.view(-1, 1)], dim=-1)[:wl.max_per_img]
+    return dets.numpy(), vl[:wl.max_per_img].numpy()
 
 
-def cpu_step(wl, batch, ho, pool, idx_w=None):
+def cpu_step(wl, batch, ho, pool):
     """The reference path on host cores: per-image assignment and decode+vote-NMS fanned out over `pool`
     (mirrors workers_per_gpu), loss forward+backward with torch intra-op threads.  Returns seconds per stage."""
     from oracle import radet_oracle as orc
 
+    n = len(batch)
     t0 = time.perf_counter()
-    aw = pool.map(_cpu_assign, [(im.gt_bboxes, im.masks, im.H, im.W, im.seed) for im in batch])
+    aw = pool.map(_cpu_assign, range(n))
     t1 = time.perf_counter()
     orc.head_loss(ho.cls, ho.bbox, ho.iou, [im.gt_bboxes for im in batch], [im.gt_labels for im in batch],
                   [a[0] for a in aw], [a[1] for a in aw], wl.C, wl.H, wl.W)
     t2 = time.perf_counter()
-    pool.map(_cpu_detect, [([m[b] for m in ho.cls], [m[b] for m in ho.bbox], [m[b] for m in ho.iou], im.H, im.W, wl.score_thr)
-                           for b, im in enumerate(batch)])
+    pool.map(_cpu_detect, range(n))
     t3 = time.perf_counter()
     return dict(assign=t1 - t0, loss=t2 - t1, detect=t3 - t2, total=t3 - t0)
 
@@ -105,46 +132,63 @@ def oracle_assign_fn(batch):
 
 
 def cpu_baseline_leg(wl, B, reps=3, warm=1):
-    """Times the CPU port on a bounded sample; runs in its own process (see --cpu-baseline-json) so that the fork pool
-    never coexists with a CUDA context and the GPU process never imports oracle/."""
+    """Times the CPU arm; runs in its own process (see --cpu-baseline-json) so that the fork pool never coexists with
+    a CUDA context and the GPU process never imports oracle/."""
     import multiprocessing as mp
 
     import torch
 
-    cores = os.cpu_count() or 1
+    cores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
     torch.set_num_threads(cores)
     from oracle import radet_oracle as orc
 
     orc.build_c_oracle()
+    orc._clib()                      # mapped in the parent: the fork pool inherits it
+    ext = None
+    try:
+        from oracle import build_ref
+
+        ext = build_ref.load_prebuilt("vote_ext")       # the reference's own compiled op
+    except Exception:
+        ext = None
     batch, ho = make_inputs(wl, B, 0, oracle_assign_fn)
-    with mp.get_context("fork").Pool(min(cores, B)) as pool:
+    _CPU.update(wl=wl, batch=batch, ho=ho, vote_ext=ext)
+    nproc = min(cores, B)
+    with mp.get_context("fork").Pool(nproc) as pool:
         for _ in range(warm):
             cpu_step(wl, batch, ho, pool)
         t0 = time.perf_counter()
         st = [cpu_step(wl, batch, ho, pool) for _ in range(reps)]
         dt = time.perf_counter() - t0
-    return {"value": B * reps / dt, "unit": "images/s", "cores": cores, "kind": "port",
-            "sample": f"{reps} steps x {B} images of {wl.name}; numpy/C oracle port of the reference path (the Python reference "
-                      f"cannot travel to this box), per-image stages over a {min(cores, B)}-process pool, loss fwd+bwd on {cores} "
-                      "torch threads; stage ms/step: " +
+    kind = "reference+port" if ext is not None else "port"
+    what = ("vote-NMS by the reference's own compiled vote_ext.cpp (oracle/_ref), assignment / loss / candidate selection by the "
+            "numpy restatement in oracle/" if ext is not None else "numpy/C restatement in oracle/ for every stage")
+    return {"value": B * reps / dt, "unit": "images/s", "cores": cores, "kind": kind,
+            "sample": f"{reps} steps x {B} images of {wl.name}; {what} (the Python reference cannot travel to this box); per-image "
+                      f"stages over a {nproc}-process pool fed once, loss fwd+bwd on {cores} torch threads; stage ms/step: " +
                       ", ".join(f"{k}={1e3 * np.mean([x[k] for x in st]):.1f}" for k in ("assign", "loss", "detect"))}, dt / reps
 
 
+def bench_config(wl, B, Ppts):
+    """The `config` object: identical in both arms (the driver compares them)."""
+    return {"workload": wl.name, "images_per_gpu": B, "points_per_image": Ppts, "classes": wl.C, "score_thr": wl.score_thr,
+            "nms_pre": wl.nms_pre, "max_per_img": wl.max_per_img, "nms": "vote(0.65)",
+            "l2": "inputs rotate over sets totalling > 2x L2 (126 MB) and L2 is flushed between timed blocks"}
+
+
 def run_reference(args, wl, B):
-    """--impl reference: the reference's CPU implementation of the path (oracle port; NMS loops in compiled C) on all
-    host cores, same workload/metric/unit."""
+    """--impl reference: the reference's CPU implementation of the path on all host cores, same workload / metric /
+    unit / config; --steps and --warmup are honoured as given (one step = one batch of B images, ~0.1 s)."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    steps = max(1, min(args.steps, 10))
-    warm = max(1, min(args.warmup, 2))
-    cb, sec = cpu_baseline_leg(wl, B, reps=steps, warm=warm)
+    cb, sec = cpu_baseline_leg(wl, B, reps=args.steps, warm=args.warmup)
     v = cb["value"]
     print(json.dumps({
-        "metric": "images/s (assign + loss fwd/bwd + decode/vote-NMS)", "value": v, "unit": "images/s", "impl": "reference",
-        "n_gpus": args.gpus, "steps": steps, "warmup": warm, "ms_per_step": 1e3 * sec,
+        "metric": METRIC, "value": v, "unit": "images/s", "impl": "reference",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * sec,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": wl.name, "images_per_step": B}, "cpu_baseline": cb,
+        "config": bench_config(wl, B, syn.num_points(wl.H, wl.W)), "cpu_baseline": cb,
         "e2e": {"value": v, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }))
 
@@ -192,32 +236,34 @@ class ClockSampler:
 # ------------------------------------------------------------------------------------------------ ours
 def bind_to_gpu_numa_node(index):
     """Run this rank on the cores of the NUMA node its GPU hangs off, so that the pinned host arenas of the e2e leg are
-    allocated next to the GPU's PCIe root (with 8 ranks on a two-socket host, half the copies otherwise cross sockets).
-    Returns the node, or None when the topology is not exposed."""
+    allocated (first touch) next to the GPU's PCIe root: with 8 ranks on a two-socket host, half the copies otherwise
+    cross sockets.  The PCI address comes from the CUDA runtime (no NVML needed).  Returns a small report."""
+    rep = {"node": None, "nodes_online": None, "cpus_bound": None}
     try:
-        import pynvml
+        rep["nodes_online"] = open("/sys/devices/system/node/online").read().strip()
+    except Exception:
+        pass
+    try:
+        import torch
 
-        pynvml.nvmlInit()
-        vis = os.environ.get("CUDA_VISIBLE_DEVICES")
-        phys = int(vis.split(",")[index]) if vis and all(t.strip().isdigit() for t in vis.split(",")) else index
-        bus = pynvml.nvmlDeviceGetPciInfo(pynvml.nvmlDeviceGetHandleByIndex(phys)).busId
-        bus = (bus.decode() if isinstance(bus, bytes) else bus).lower()
-        if len(bus.split(":")[0]) == 8:           # nvml prints an 8-digit domain, sysfs a 4-digit one
-            bus = bus[4:]
+        pr = torch.cuda.get_device_properties(index)
+        bus = f"{pr.pci_domain_id:04x}:{pr.pci_bus_id:02x}:{pr.pci_device_id:02x}.0"
+        rep["pci"] = bus
         node = int(open(f"/sys/bus/pci/devices/{bus}/numa_node").read())
+        rep["node"] = node
         if node < 0:
-            return None
+            return rep
         cpus = set()
         for part in open(f"/sys/devices/system/node/node{node}/cpulist").read().strip().split(","):
             a, _, b = part.partition("-")
             cpus.update(range(int(a), int(b or a) + 1))
         cpus &= os.sched_getaffinity(0)
-        if not cpus:
-            return None
-        os.sched_setaffinity(0, cpus)
-        return node
-    except Exception:
-        return None
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            rep["cpus_bound"] = len(cpus)
+    except Exception as e:
+        rep["error"] = repr(e)[:120]
+    return rep
 
 
 def main():
@@ -247,8 +293,6 @@ def main():
         except Exception:
             cpu_base = {"error": (cpu_proc_out[1] or "")[-300:]}
 
-    numa = bind_to_gpu_numa_node(local_rank)   # before any pinned allocation: first touch decides where the pages live
-
     import torch
     import torch.distributed as dist
 
@@ -256,6 +300,7 @@ def main():
     from radet_b200 import functional as F
     from radet_b200 import plugin as P
 
+    numa = bind_to_gpu_numa_node(local_rank)   # before any pinned allocation: first touch decides where the pages live
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
@@ -402,124 +447,179 @@ def main():
     with torch.cuda.stream(lanes[0]["main"]):
         step(sets[0], nxt=nxt_of(0), lane=0)
     launches_per_step = _lib.launch_count() - l0
-    for i in range(max(3, min(args.warmup, 20), U)):      # eager warm-up on every lane's streams (allocates its workspaces)
+    for i in range(max(3, U)):      # eager warm-up on every lane's streams (allocates its workspaces)
         with torch.cuda.stream(lanes[i % U]["main"]):
             step(sets[i % R], nxt=nxt_of(i % R), lane=i % U)
         torch.cuda.synchronize()
 
-    # ---- CUDA graphs: one per input set (the C ABI only enqueues, so the whole step is capturable)
+    # ---- CUDA graphs.  Step i works on input set i % R on lane i % U (R is a multiple of U, so a set always meets the same
+    # lane: its workspaces and its hand-over buffers are only ever touched from one stream).  A lane's consecutive steps
+    # are captured into ONE graph (`per_lane` = R / U steps, plus shorter ones for remainders), so a block of K steps
+    # costs the host ~K / per_lane graph launches instead of K, spread over U streams that never wait for each other.
     use_graph = not args.no_graph
-    graphs, outs = [], []
-    if use_graph:
-        # one memory pool per lane: graphs of one lane replay back to back on its stream and may share intermediates,
-        # graphs of different lanes run concurrently and must not
-        lane_pools = [torch.cuda.graph_pool_handle() for _ in range(U)]
-        for r_, s in enumerate(sets):
+    per_lane = R // U
+    lane_graphs, lane_outs = {}, {}
+    lane_pools = [torch.cuda.graph_pool_handle() for _ in range(U)] if use_graph else None
+
+    def lane_graph(l, n):
+        """Graph of the first n (<= per_lane) steps of lane l: sets l, l + U, ..."""
+        key = (l, n)
+        if key not in lane_graphs:
             g = torch.cuda.CUDAGraph()
             keep = []
-            with torch.cuda.graph(g, pool=lane_pools[r_ % U], stream=lanes[r_ % U]["main"]):
-                step(s, keep, nxt=nxt_of(r_), lane=r_ % U)
-            graphs.append(g)
-            outs.append(keep)
+            with torch.cuda.graph(g, pool=lane_pools[l], stream=lanes[l]["main"]):
+                for k in range(n):
+                    r = l + k * U
+                    step(sets[r], keep, nxt=nxt_of(r), lane=l)
+            lane_graphs[key], lane_outs[key] = g, keep
+        return lane_graphs[key]
 
-        def run(i, one_lane=False):
-            with torch.cuda.stream(lanes[0 if one_lane else i % U]["main"]):
-                graphs[i % R].replay()
-    else:
-        def run(i, one_lane=False):
+    def lane_plan(K):
+        """[(lane, [graphs...])]: step i of a K-step block runs on lane i % U."""
+        plan = []
+        for l in range(U):
+            n = K // U + (1 if l < K % U else 0)
+            seq = [lane_graph(l, per_lane)] * (n // per_lane)
+            if n % per_lane:
+                seq.append(lane_graph(l, n % per_lane))
+            plan.append(seq)
+        return plan
+
+    def enqueue_block(K, one_lane=False):
+        """Enqueue K steps (no synchronisation).  Returns the number of graph launches."""
+        if not use_graph:
             with torch.cuda.stream(lanes[0]["main"]):
-                step(sets[i % R], nxt=nxt_of(i % R))
+                for i in range(K):
+                    step(sets[i % R], nxt=nxt_of(i % R))
+            return K * launches_per_step
+        plan = lane_plan(K)
+        n = 0
+        if one_lane:
+            with torch.cuda.stream(lanes[0]["main"]):
+                for seq in plan:
+                    for g in seq:
+                        g.replay()
+                        n += 1
+            return n
+        for j in range(max(len(seq) for seq in plan)):     # round-robin over the lanes
+            for l, seq in enumerate(plan):
+                if j < len(seq):
+                    with torch.cuda.stream(lanes[l]["main"]):
+                        seq[j].replay()
+                    n += 1
+        return n
+
+    host_group = dist.new_group(backend="gloo") if world > 1 else None   # host-only rendezvous (a NCCL barrier would wait for the gated stream)
 
     def barrier():
-        if world > 1:
-            dist.barrier()
         torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier(group=host_group)
 
-    sampler = ClockSampler(local_rank) if rank == 0 else None
-    for i in range(args.warmup):
-        run(i)
-    # keep the GPU under load long enough for the clock sampler to see it (not timed)
-    t_load = time.perf_counter()
-    i = 0
-    while time.perf_counter() - t_load < 0.6:
-        run(i)
-        i += 1
-        if i % 256 == 0:
-            torch.cuda.synchronize()
-    host_enqueue_us = [0.0]
+    flush_buf = torch.empty(2 * L2_BYTES, dtype=torch.uint8, device=dev)
+    gate_flag = torch.zeros(1, dtype=torch.int32).pin_memory()          # device-visible at the same address (UVA)
+    gate_np = gate_flag.numpy()
+    lib_ = _lib.load()
+    host_enqueue_us = []
+    gated = [False]
 
-    def timed(n, one_lane=False):
-        """ms for n steps: events on the current stream, every lane's stream forked from / joined into it."""
+    def timed_block(K, one_lane=False):
+        """Device milliseconds of one K-step block (CUDA events on the current stream; every lane forks from it after
+        the first event and joins before the second).  The block is enqueued completely behind a device-side gate
+        that the host opens after a cross-rank rendezvous, so host launch stalls stay outside the window."""
+        plan_launches = K if not use_graph else sum(len(seq) for seq in lane_plan(K))
+        use_gate = use_graph and not args.no_gate and plan_launches <= 96      # deep queues: let the device start at once instead
         barrier()
         cur = torch.cuda.current_stream()
+        flush_buf.zero_()                                                      # L2 holds nothing of the inputs when the block starts
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        if use_gate:
+            gate_np[0] = 0
+            rc = lib_.radet_stream_gate(ctypes.c_void_p(gate_flag.data_ptr()), 2_000_000_000, ctypes.c_void_p(cur.cuda_stream))
+            assert rc == 0, rc
         e0.record()
         for ln in lanes:
             ln["main"].wait_stream(cur)
         th0 = time.perf_counter()
-        for i in range(n):
-            run(i, one_lane)
-        host_enqueue_us[0] = (time.perf_counter() - th0) * 1e6 / n
+        enqueue_block(K, one_lane)
         for ln in lanes:
             cur.wait_stream(ln["main"])
         e1.record()
-        barrier()
-        ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+        host_us = (time.perf_counter() - th0) * 1e6 / K
+        if use_gate:
+            if world > 1:
+                dist.barrier(group=host_group)                                 # every rank has its block queued
+            gate_np[0] = 1
+        gated[0] = use_gate
+        torch.cuda.synchronize()
+        if not one_lane:
+            host_enqueue_us.append(host_us)
+        return e0.elapsed_time(e1)
+
+    def timed(K, reps, one_lane=False):
+        """Median block time over `reps` repeats, max over ranks of every repeat; returns (median_ms, all_ms)."""
+        ms = torch.tensor([timed_block(K, one_lane) for _ in range(reps)], dtype=torch.float64, device=dev)
         if world > 1:
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
-        return float(ms.item())
+        v = sorted(ms.tolist())
+        return v[len(v) // 2], v
 
-    one_lane_ms = timed(min(args.steps, 500), one_lane=True) / min(args.steps, 500) if U > 1 else None
-    t_clk0 = time.perf_counter()
-    ms_total = timed(args.steps)
-    t_clk1 = time.perf_counter()
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    if args.warmup:
+        enqueue_block(args.warmup)
+    torch.cuda.synchronize()
+    # keep the GPU under load long enough for the clock sampler to see it (not timed)
+    t_load = time.perf_counter()
+    while time.perf_counter() - t_load < 0.6:
+        enqueue_block(4 * R)
+        torch.cuda.synchronize()
+    reps = max(1, args.repeats)
+    tstream = torch.cuda.Stream(device=dev)        # non-blocking: the gate must not hold the legacy default stream
+    with torch.cuda.stream(tstream):
+        timed_block(args.steps)                                                # builds the block's graphs; untimed
+        one_lane_ms = timed(min(args.steps, 512), 3, one_lane=True)[0] / min(args.steps, 512) if U > 1 else None
+        host_enqueue_us.clear()
+        t_clk0 = time.perf_counter()
+        ms_total, ms_all = timed(args.steps, reps)
+        t_clk1 = time.perf_counter()
+    host_us_all = torch.tensor([float(np.median(host_enqueue_us))], dtype=torch.float64, device=dev)
+    if world > 1:
+        gathered = [torch.zeros_like(host_us_all) for _ in range(world)]
+        dist.all_gather(gathered, host_us_all)
+        host_us_ranks = [float(t.item()) for t in gathered]
+    else:
+        host_us_ranks = [float(host_us_all.item())]
 
     # overlapped replays must leave exactly what one-at-a-time replays leave (no scratch shared between lanes)
     overlap_check = None
     if use_graph and U > 1 and (len(stages) == 3 or os.environ.get("RADET_BENCH_DEBUG")):
         def flat(keep):
             ts = []
-            for t in keep[0]:
-                if isinstance(t, torch.Tensor):
-                    ts.append(t.clone())
-                elif isinstance(t, (tuple, list)):
-                    ts += [x.clone() for grp in t for x in grp]
+            for rec in keep:
+                for t in rec:
+                    if isinstance(t, torch.Tensor):
+                        ts.append(t.clone())
+                    elif isinstance(t, (tuple, list)):
+                        ts += [x.clone() for grp in t for x in grp]
             return ts
-        for i in range(2 * R):
-            run(i)
+        for l in range(U):
+            lane_graph(l, per_lane)
+        for _ in range(2):
+            enqueue_block(R)
         torch.cuda.synchronize()
-        got = [flat(k) for k in outs]
-        for i in range(R):
-            run(i, one_lane=True)
+        got = [flat(lane_outs[(l, per_lane)]) for l in range(U)]
+        for l in range(U):
+            with torch.cuda.stream(lanes[0]["main"]):
+                lane_graphs[(l, per_lane)].replay()
             torch.cuda.synchronize()
-            want = flat(outs[i])
-            if os.environ.get("RADET_BENCH_DEBUG"):
-                si = sets[i]
-                truth = F.loss_fwd_bwd(geom, wl.C, si["cls"], si["bbox"], si["iou"], si["counts"], si["boxes"], si["labels"],
-                                       si["abuf"][0], si["abuf"][1], lcfg, gt_offsets=si["off"])
-                torch.cuda.synchronize()
-                tl = [truth[0]] + [x for grp in truth[1] for x in grp]
-                for k, (a, b) in enumerate(zip(got[i], want)):
-                    if not torch.equal(a, b):
-                        bad = (a != b).nonzero()
-                        msg = f"set {i} output #{k} shape {tuple(a.shape)}: {bad.shape[0]} differ; first {bad[:3].tolist()}"
-                        if 2 <= k < 2 + len(tl):
-                            t = tl[k - 2]
-                            j = tuple(bad[0].tolist())
-                            msg += (f" overlapped_wrong={int((a != t).sum())} serial_wrong={int((b != t).sum())} "
-                                    f"vals ov={a[j].item():.6g} ser={b[j].item():.6g} truth={t[j].item():.6g}")
-                            if a.dim() == 4:
-                                bb, cc, yy, xx = j
-                                near = {dc: t[bb, cc + dc, yy, xx].item() for dc in (-8, -1, 1, 8) if 0 <= cc + dc < a.shape[1]}
-                                msg += f" truth at other planes {near}"
-                        print(msg, file=sys.stderr)
-            for k, (a, b) in enumerate(zip(got[i], want)):
+            want = flat(lane_outs[(l, per_lane)])
+            for k, (a, b) in enumerate(zip(got[l], want)):
                 if not torch.equal(a, b):
                     bad = (a != b).nonzero()
-                    raise RuntimeError(f"overlapped replay of input set {i} differs from its serial replay: output #{k} "
+                    raise RuntimeError(f"overlapped replay of lane {l} differs from its serial replay: output #{k} "
                                        f"shape {tuple(a.shape)}, {bad.shape[0]} elements, first at {bad[0].tolist()}: "
                                        f"{a[tuple(bad[0])].item()} vs {b[tuple(bad[0])].item()}")
-        overlap_check = f"outputs of {R} sets after overlapped replays bit-identical to one-at-a-time replays"
+        overlap_check = f"outputs of {R} sets after overlapped replays bit-identical to one-lane-at-a-time replays"
         del got
     ms_per_step = ms_total / args.steps
     value = world * B * args.steps / (ms_total * 1e-3)
@@ -604,13 +704,41 @@ def main():
                 "note": f"(8C+52) B/point x {B * Ppts} points; at this batch the launch moves {loss_bytes / 1e6:.1f} MB "
                         "(latency-bound regime, SURVEY 8d); see roofline_large for the bandwidth-bound regime"}
 
-    # ---- the same kernel in the bandwidth-bound regime (cfg5-shaped: 1280x960, C=30, B=16 -> ~120 MB per launch)
-    roofline_large = None
-    if rank == 0:
-        try:
-            roofline_large = large_roofline(F, _lib, dev, peak_gbs)
-        except Exception as e:  # never lose the headline line to the auxiliary measurement
-            roofline_large = {"error": repr(e)}
+    # ---- the other BASELINE.json configs at their per-GPU shapes (cfg5 is the bandwidth-bound regime of the loss kernel:
+    # 1280x960, C=30, B=16 -> ~120 MB per launch), measured on rank 0 with graph replays over rotating sets
+    side = {}
+    if rank == 0 and not args.no_side_configs:
+        for name in ("cfg5", "cfg3", "cfg4"):
+            try:
+                side[name] = side_config(name, F, dev, peak_gbs)
+            except Exception as e:  # never lose the headline line to an auxiliary measurement
+                side[name] = {"error": repr(e)}
+    roofline_large = side.get("cfg5")
+
+    # ---- the one collective north_star names: the opt-in FCOS-style reduce_mean of the loss normalisers over NCCL
+    sync_cost = None
+    if world > 1:
+        def loss_only(s, group):
+            return F.loss_fwd_bwd(geom, wl.C, s["cls"], s["bbox"], s["iou"], s["counts"], s["boxes"], s["labels"], s["idx"], s["w"],
+                                  lcfg, gt_offsets=s["off"], sync_group=group)
+        res = {}
+        for tag, group in (("local", None), ("synced", dist.group.WORLD)):
+            for i in range(5):
+                loss_only(sets[i % R], group)
+            torch.cuda.synchronize()
+            dist.barrier(group=host_group)
+            ea, eb = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            ea.record()
+            for i in range(100):
+                loss_only(sets[i % R], group)
+            eb.record()
+            torch.cuda.synchronize()
+            t = torch.tensor([ea.elapsed_time(eb) * 10.0], dtype=torch.float64, device=dev)     # us per call
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            res[tag] = float(t.item())
+        sync_cost = {"loss_us_local": res["local"], "loss_us_sync_num_pos": res["synced"], "allreduce_bytes": 16,
+                     "note": "eager calls (host-launch-bound); RADetHead(sync_num_pos=True): loss phase 1 -> NCCL all-reduce of the two "
+                             "fp64 normalisers -> phase 2; default (reference behaviour, radet_head.py:254-259) is rank-local"}
 
     # ---- e2e: plugin API, pinned host buffers, H2D + D2H inside the timed region
     e2e = None
@@ -619,66 +747,82 @@ def main():
 
     clocks = sampler.stop(t_clk0, t_clk1) if sampler else None
     if world > 1:
-        dist.barrier()
+        dist.barrier(group=host_group)
     if rank == 0:
         pairs = float(np.mean([s["pairs"] for s in sets]))
+        launch = ("cuda_graph" if use_graph else "eager") + (
+            ", 1 stream" if args.serial else
+            ", assign->loss and decode+NMS branches of one batch forked on streams" if args.no_prefetch else
+            f", 3 branches per step: assign(batch i+{U}) || loss fwd+bwd(batch i) || decode+NMS(batch i) "
+            f"(assignment runs ahead like the reference's DataLoader workers); {U} lanes (streams) in flight, each replaying "
+            f"graphs of up to {per_lane} consecutive steps")
         out = {
-            "metric": "images/s (assign + loss fwd/bwd + decode/vote-NMS)", "value": value, "unit": "images/s", "n_gpus": world,
+            "metric": METRIC, "value": value, "unit": "images/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": wl.name, "images_per_gpu": B, "points_per_image": Ppts, "classes": wl.C,
-                       "launch": ("cuda_graph" if use_graph else "eager") + (
-                           ", 1 stream" if args.serial else
-                           ", assign->loss and decode+NMS branches of one batch forked on streams" if args.no_prefetch else
-                           f", 3 branches per step: assign(batch i+{U}) || loss fwd+bwd(batch i) || decode+NMS(batch i) "
-                           f"(assignment runs ahead like the reference's DataLoader workers); {U} step graphs in flight "
-                           f"(round-robin over {U} streams)"),
-                       "steps_in_flight": U, "ms_per_step_one_in_flight": one_lane_ms, "overlap_check": overlap_check,
-                       "host_enqueue_us_per_step": host_enqueue_us[0],
-                       "l2": f"{R} rotating input sets, {R * per_set / 1e6:.0f} MB total > L2 ({L2_BYTES / 1e6:.0f} MB)",
-                       "parallelism": f"images sharded over {world} rank(s), no data-path collective",
-                       "numa_node_of_rank0": numa},
+            "config": bench_config(wl, B, Ppts),
+            "run": {"launch": launch, "steps_in_flight": U, "ms_per_step_one_in_flight": one_lane_ms, "overlap_check": overlap_check,
+                    "timing": f"median of {reps} blocks of {args.steps} steps, each block CUDA-event timed on the device "
+                              f"(max over ranks per block){', enqueued behind a device-side gate' if gated[0] else ''}; "
+                              f"L2 flushed before every block",
+                    "block_ms": ms_all, "host_enqueue_us_per_step_by_rank": host_us_ranks,
+                    "rotation": f"{R} rotating input sets, {R * per_set / 1e6:.0f} MB total > L2 ({L2_BYTES / 1e6:.0f} MB)",
+                    "parallelism": f"images sharded over {world} rank(s), no data-path collective", "numa": numa},
             "point_gt_pairs_per_s": world * pairs / (stage_us["assign(pairs+resolve)"] * 1e-6),
             "point_gt_pairs_per_s_train_path": world * pairs / ((stage_us["assign(pairs+resolve)"] + stage_us["loss(pos+dense)"]) * 1e-6),
             "stage_us": stage_us, "gpu_launches": launches_per_step * args.steps, "launches_per_step": launches_per_step,
-            "roofline": roofline, "roofline_large": roofline_large, "cpu_baseline": cpu_base, "e2e": e2e, "clocks": clocks,
+            "roofline": roofline, "roofline_large": roofline_large, "other_configs": {k: v for k, v in side.items() if k != "cfg5"},
+            "sync_num_pos": sync_cost, "cpu_baseline": cpu_base, "e2e": e2e, "clocks": clocks,
         }
         print(json.dumps(out))
     if world > 1:
         dist.destroy_process_group()
 
 
-def large_roofline(F, _lib, dev, peak_gbs):
-    """loss_dense_kernel and the assignment at cfg5 scale (per-GPU share), synthetic random tensors of that shape."""
+def side_config(name, F, dev, peak_gbs):
+    """One of BASELINE.json's other configs at its per-GPU shape: stage times (CUDA events around graph replays over
+    rotating input sets > L2), images/s, point-GT pairs/s and the HBM roofline fractions of the assignment and the loss."""
     import torch
 
-    wl = syn.WORKLOADS["cfg5"]
+    wl = syn.WORKLOADS[name]
     B, C = wl.B, wl.C
     geom = F.Geometry()
     shapes = geom.level_shapes(wl.H, wl.W)
     Ppts = geom.num_points(shapes)
     g = torch.Generator(device=dev).manual_seed(0)
-    R = 3   # 3 x ~120 MB > L2
+    per_set = B * Ppts * (C + 5) * 4 * 2
+    R = max(3, int(np.ceil(2.2 * L2_BYTES / per_set)))
     sets = []
     rs = np.random.RandomState(0)
+    real = name != "cfg5"          # 1280x960 mask generation is slow on the host: two real images tiled over the batch
     for r in range(R):
-        counts = [int(c) for c in rs.randint(wl.g_lo, wl.g_hi + 1, B)]
-        imgs = [syn.make_image(np.random.RandomState(50 + r * B + i), wl.H, wl.W, C, counts[i]) for i in range(2)]
-        # boxes/masks: two real synthetic images tiled over the batch (mask generation at 1280x960 is slow on the host)
-        counts = [imgs[i % 2].gt_bboxes.shape[0] for i in range(B)]
+        if real:
+            imgs = syn.make_batch(wl, B, r * B)
+        else:
+            cnt = [int(c) for c in rs.randint(wl.g_lo, wl.g_hi + 1, 2)]
+            two = [syn.make_image(np.random.RandomState(50 + r * B + i), wl.H, wl.W, C, cnt[i]) for i in range(2)]
+            imgs = [two[i % 2] for i in range(B)]
+        counts = [im.gt_bboxes.shape[0] for im in imgs]
         off = F.offsets_of(counts, dev)
-        boxes = torch.from_numpy(np.concatenate([imgs[i % 2].gt_bboxes for i in range(B)])).to(dev)
-        labels = torch.from_numpy(np.concatenate([imgs[i % 2].gt_labels for i in range(B)])).to(dev)
-        grids = torch.from_numpy(np.concatenate([syn.sample_grid(imgs[i % 2].masks) for i in range(B)])).to(dev)
+        boxes = torch.from_numpy(np.concatenate([im.gt_bboxes for im in imgs])).to(dev)
+        labels = torch.from_numpy(np.concatenate([im.gt_labels for im in imgs])).to(dev)
+        grids = torch.from_numpy(np.concatenate([syn.sample_grid(im.masks) for im in imgs])).to(dev)
         gh, gw = grids.shape[1:]
         bits = F.pack_masks(grids, 1, gh, gw)
         seeds = torch.arange(B, dtype=torch.int32, device=dev) + 1000 * r
         idx, w, _ = F.assign(geom, shapes, counts, boxes, bits, (gh, gw), seeds=seeds, gt_offsets=off)
-        cls = [torch.randn((B, C, h, w_), device=dev, generator=g) - 4.6 for h, w_ in shapes]
-        bbox = [torch.relu(torch.randn((B, 4, h, w_), device=dev, generator=g) + 1) for h, w_ in shapes]
-        iou = [torch.randn((B, 1, h, w_), device=dev, generator=g) for h, w_ in shapes]
+        if real:     # SURVEY 8d head outputs (logits boosted at the positives), so ~1000 candidates per image survive
+            ho = syn.make_head_outputs(wl, imgs, list(idx.cpu().numpy()), seed_base=wl.cfg_id * 100 + 7 * r)
+            T = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)
+            cls, bbox, iou = [T(m) for m in ho.cls], [T(m) for m in ho.bbox], [T(m) for m in ho.iou]
+        else:
+            cls = [torch.randn((B, C, h, w_), device=dev, generator=g) - 4.6 for h, w_ in shapes]
+            bbox = [torch.relu(torch.randn((B, 4, h, w_), device=dev, generator=g) + 1) for h, w_ in shapes]
+            iou = [torch.randn((B, 1, h, w_), device=dev, generator=g) for h, w_ in shapes]
         sets.append(dict(counts=counts, off=off, boxes=boxes, labels=labels, bits=bits, seeds=seeds, idx=idx, w=w, cls=cls, bbox=bbox,
-                         iou=iou, gh=gh, gw=gw, pairs=sum(counts) * Ppts))
+                         iou=iou, gh=gh, gw=gw, pairs=sum(counts) * Ppts,
+                         shp=torch.tensor([[wl.H, wl.W]] * B, dtype=torch.int32, device=dev),
+                         sf=torch.ones((B, 4), dtype=torch.float32, device=dev)))
     lcfg = F.LossConfig()
 
     def timeit(fn, iters=60):
@@ -686,11 +830,12 @@ def large_roofline(F, _lib, dev, peak_gbs):
             fn(sets[i % R])
         torch.cuda.synchronize()
         gs, keepalive = [], []
+        pool = torch.cuda.graph_pool_handle()
         for s in sets:   # graph replays: no Python/ctypes time between the launches
-            g = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(g):
+            gr = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(gr, pool=pool):
                 keepalive.append(fn(s))
-            gs.append(g)
+            gs.append(gr)
         for i in range(R):
             gs[i].replay()
         torch.cuda.synchronize()
@@ -702,19 +847,34 @@ def large_roofline(F, _lib, dev, peak_gbs):
         torch.cuda.synchronize()
         return a.elapsed_time(b) * 1e3 / iters
 
-    t_loss = timeit(lambda s: F.loss_fwd_bwd(geom, C, s["cls"], s["bbox"], s["iou"], s["counts"], s["boxes"], s["labels"], s["idx"], s["w"],
-                                             lcfg, gt_offsets=s["off"]))
-    t_assign = timeit(lambda s: F.assign(geom, shapes, s["counts"], s["boxes"], s["bits"], (s["gh"], s["gw"]), seeds=s["seeds"],
-                                         gt_offsets=s["off"]))
-    loss_bytes = B * Ppts * (8 * C + 52)
-    gavg = float(np.mean([sum(s["counts"]) for s in sets])) / B
-    assign_bytes = B * (12 * Ppts + gavg * (16 + sets[0]["gh"] * ((sets[0]["gw"] + 31) // 32) * 4))   # idx i64 + w f32 out; boxes + bit masks in
-    return {"workload": wl.name + " (per-GPU share)", "loss_fwd_bwd": {"us": t_loss, "algorithmic_bytes": loss_bytes,
-                                                                        "achieved_GBps": loss_bytes / t_loss / 1e3,
-                                                                        "frac": loss_bytes / t_loss / 1e3 / peak_gbs},
-            "assign": {"us": t_assign, "algorithmic_bytes": assign_bytes, "achieved_GBps": assign_bytes / t_assign / 1e3,
-                       "frac": assign_bytes / t_assign / 1e3 / peak_gbs,
-                       "point_gt_pairs_per_s": float(np.mean([s["pairs"] for s in sets])) / (t_assign * 1e-6)}}
+    out = {"workload": wl.name + " (per-GPU share)", "images": B, "points_per_image": Ppts, "classes": C}
+    pairs = float(np.mean([s["pairs"] for s in sets]))
+    if name != "cfg4":
+        t_loss = timeit(lambda s: F.loss_fwd_bwd(geom, C, s["cls"], s["bbox"], s["iou"], s["counts"], s["boxes"], s["labels"], s["idx"],
+                                                 s["w"], lcfg, gt_offsets=s["off"]))
+        t_assign = timeit(lambda s: F.assign(geom, shapes, s["counts"], s["boxes"], s["bits"], (s["gh"], s["gw"]), seeds=s["seeds"],
+                                             gt_offsets=s["off"]))
+        loss_bytes = B * Ppts * (8 * C + 52)
+        gavg = float(np.mean([sum(s["counts"]) for s in sets])) / B
+        # 36 P + G (24 + P0) B per image with bit-packed masks (P0/8); labels/targets are fused into the loss,
+        # so what the assignment itself moves is idx i64 + w f32 out (12 P) and boxes + bit masks in
+        assign_bytes = B * (12 * Ppts + gavg * (16 + sets[0]["gh"] * ((sets[0]["gw"] + 31) // 32) * 4))
+        out["loss_fwd_bwd"] = {"us": t_loss, "algorithmic_bytes": loss_bytes, "achieved_GBps": loss_bytes / t_loss / 1e3,
+                               "frac": loss_bytes / t_loss / 1e3 / peak_gbs}
+        out["assign"] = {"us": t_assign, "algorithmic_bytes": assign_bytes, "achieved_GBps": assign_bytes / t_assign / 1e3,
+                         "frac": assign_bytes / t_assign / 1e3 / peak_gbs, "point_gt_pairs_per_s": pairs / (t_assign * 1e-6)}
+        out["train_path_images_per_s"] = B / ((t_assign + t_loss) * 1e-6)
+        out["point_gt_pairs_per_s_train_path"] = pairs / ((t_assign + t_loss) * 1e-6)
+    if name != "cfg3":
+        for typ in (("vote", "nms") if name == "cfg4" else ("vote",)):
+            dcfg = F.DetectConfig(score_thr=wl.score_thr, nms_pre=wl.nms_pre, max_per_img=wl.max_per_img, nms_type=typ, **NMS_CFG)
+            nums = []
+            t_det = timeit(lambda s: nums.append(F.get_bboxes(geom, C, s["cls"], s["bbox"], s["iou"], s["shp"], s["sf"], dcfg,
+                                                              rescale=True)[2]) or nums[-1])
+            scan_bytes = B * Ppts * (C + 5) * 4
+            out[f"get_bboxes_{typ}"] = {"us": t_det, "images_per_s": B / (t_det * 1e-6), "scan_bytes": scan_bytes,
+                                        "scan_GBps": scan_bytes / t_det / 1e3, "mean_dets_per_image": float(nums[-1].float().mean())}
+    return out
 
 
 def run_e2e(args, wl, B, host_sets, dev, P, F, world):
@@ -749,7 +909,7 @@ def run_e2e(args, wl, B, host_sets, dev, P, F, world):
         pipes[0].fill(views, [im.gt_bboxes for im in batch], [im.gt_labels for im in batch], [syn.sample_grid(im.masks) for im in batch],
                       [im.seed for im in batch], ho.cls, ho.bbox, ho.iou)
         arenas.append(buf)
-    n = max(10, min(args.steps, 1000))
+    n = max(20, min(args.steps, 1000))
     sink = 0.0
     for i in range(2 * NP):
         sink += float(pipes[i % NP].run(arenas[i % len(arenas)])["losses"][0])
@@ -772,28 +932,46 @@ def run_e2e(args, wl, B, host_sets, dev, P, F, world):
                 kk = int(nd[b_])
                 if not (torch.equal(res["dets"][b_, :kk], want["dets"][b_, :kk]) and torch.equal(res["labels"][b_, :kk], want["labels"][b_, :kk])):
                     raise RuntimeError(f"e2e: pipelined batch {j} differs from its serial run in the detections of image {b_}")
-    if world > 1:
-        dist.barrier()
-    torch.cuda.synchronize()
-    t0 = time.perf_counter()
-    for i in range(n + NP - 1):
-        if i < n:
-            pipes[i % NP].launch(arenas[i % len(arenas)])         # copy + graph of batch i overlap the batches before it
-        j = i - (NP - 1)
-        if j >= 0:
-            res = pipes[j % NP].wait()                             # results of batch j are on the host now
-            sink += float(res["losses"][0]) + float(res["num"][0])
-    torch.cuda.synchronize()
-    dt = sync_max(time.perf_counter() - t0)
+
+    def e2e_block(resident):
+        nonlocal sink
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for i in range(n + NP - 1):
+            if i < n:
+                pipes[i % NP].launch(arenas[i % len(arenas)], maps_resident=resident)   # copy + graph of batch i overlap the batches before it
+            j = i - (NP - 1)
+            if j >= 0:
+                res = pipes[j % NP].wait()                         # results of batch j are on the host now
+                sink += float(res["losses"][0]) + float(res["num"][0])
+        torch.cuda.synchronize()
+        return sync_max(time.perf_counter() - t0)
+
+    reps = 7
+    dts = sorted(e2e_block(False) for _ in range(reps))
+    dt = dts[reps // 2]
     h2d_mean = float(np.mean([pipes[0].used_bytes(a) for a in arenas]))
     out = {"value": world * B * n / dt, "unit": "images/s", "h2d_bytes_per_step": int(h2d_mean),
            "d2h_bytes_per_step": int(pipes[0].d2h_bytes), "steps": n, "ms_per_step": 1e3 * dt / n,
            "h2d_GBps_per_gpu": h2d_mean * n / dt / 1e9,
            "pipelined_check": f"{4 * NP * len(arenas)} pipelined batches bit-identical to their serial runs (losses, detections)",
-           "timing": "host wall clock between device synchronisations (max over ranks)",
+           "timing": f"median of {reps} blocks of {n} batches, host wall clock between device synchronisations (max over ranks)",
            "api": "plugin.GraphedHotPath.launch/wait: pinned host arena -> H2D -> CUDA graph (seed | pack+assign+loss fwd/bwd | "
                   f"decode+vote-NMS) -> D2H of losses/detections; {NP} instances in flight; the step is bound by the "
                   "host->device copy of the head outputs (h2d_GBps_per_gpu against the PCIe link)"}
+    # deployment shape: the head outputs are produced on the device by the conv towers; only GT / seeds / mask grids are host-fed
+    for pi in pipes:           # every instance's device arena holds one batch's maps (the arenas rotate below as before)
+        pi.run(arenas[0])
+    dts = sorted(e2e_block(True) for _ in range(reps))
+    pipes[0].launch(arenas[0], maps_resident=True)
+    pipes[0].wait()
+    out["maps_resident"] = {"value": world * B * n / dts[reps // 2], "unit": "images/s", "ms_per_step": 1e3 * dts[reps // 2] / n,
+                            "h2d_bytes_per_step": int(pipes[0].last_h2d_bytes), "d2h_bytes_per_step": int(pipes[0].d2h_bytes),
+                            "note": "same API with launch(maps_resident=True): cls/bbox/iou maps already in the device arena (where "
+                                    "the conv towers write them in deployment); GT boxes, labels, seeds and mask grids come from "
+                                    "pinned host memory every step, losses and detections go back"}
 
     # ---------------- eager plugin calls
     pin = lambda a: torch.from_numpy(np.ascontiguousarray(a)).pin_memory()

@@ -80,6 +80,10 @@ const char* radet_version(void);
 /* number of kernel launches enqueued by this library in this process so far (bench.py's gpu_launches) */
 uint64_t radet_launch_count(void);
 int64_t radet_num_points(const radet_grid_t* grid);
+/* Measurement aid (bench.py): holds `stream` until *flag != 0 (flag: int32 in pinned, device-mapped host memory; the
+ * host opens the gate with a plain store) or until max_wait_ns have passed.  Work enqueued behind it starts the moment
+ * the gate opens, so host launch latency stays outside a CUDA-event timing window.  Not counted by radet_launch_count. */
+int radet_stream_gate(const int32_t* flag, int64_t max_wait_ns, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Visible-mask hand-off (replaces the [G,H,W] uint8 `distance_maps.to_ndarray()` input of

@@ -46,6 +46,7 @@ _SIGS = {
     "radet_version": (c_char_p, []),
     "radet_launch_count": (c_uint64, []),
     "radet_num_points": (c_int64, [POINTER(Grid)]),
+    "radet_stream_gate": (c_int32, [c_void_p, c_int64, c_void_p]),
     "radet_pack_masks": (c_int32, [c_void_p, c_int64, c_int32, c_int32, c_int32, c_int32, c_int32, c_void_p, c_void_p, c_void_p]),
     "radet_mt19937_uniforms": (c_int32, [c_void_p, c_int32, c_int32, c_void_p, c_void_p]),
     "radet_mt19937_seed": (c_int32, [c_void_p, c_int32, c_void_p, c_void_p]),

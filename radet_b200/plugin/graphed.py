@@ -72,7 +72,8 @@ class GraphedHotPath:
         self._graph = None
         self._stream = torch.cuda.Stream(device=self.dev)
         self._side = [torch.cuda.Stream(device=self.dev) for _ in range(2)]
-        self._done = torch.cuda.Event()
+        with torch.cuda.device(self.dev):
+            self._done = torch.cuda.Event()
         self.grads = None
 
     # ------------------------------------------------------------------ arenas
@@ -147,10 +148,12 @@ class GraphedHotPath:
 
     def capture(self):
         """Warm up eagerly (workspaces, lazy module loading), then capture the step."""
-        self._dev_arena.zero_()
-        self._dviews["img_shapes"][:] = torch.tensor([self.H, self.W], dtype=torch.int32, device=self.dev)
-        self._dviews["scale_factors"].fill_(1.0)
+        self._stream.wait_stream(torch.cuda.current_stream(self.dev))    # the arena may have been allocated on the caller's stream
         with torch.cuda.stream(self._stream):
+            # initialise the arena on the stream the warm-up runs on (side streams do not order against the caller's)
+            self._dev_arena.zero_()
+            self._dviews["img_shapes"][:] = torch.tensor([self.H, self.W], dtype=torch.int32, device=self.dev)
+            self._dviews["scale_factors"].fill_(1.0)
             for _ in range(2):
                 self._body()
             self._stream.synchronize()
@@ -180,16 +183,33 @@ class GraphedHotPath:
         moff = self._layout["mask_grids"][0]
         return min(self.arena_bytes, _align(moff + n_gt * self.gh * self.gw))
 
-    def launch(self, host_arena: torch.Tensor):
-        """Enqueue: H2D of the used part of the arena, the graph, D2H of the results.  Returns immediately."""
+    def launch(self, host_arena: torch.Tensor, maps_resident: bool = False):
+        """Enqueue: H2D of the used part of the arena, the graph, D2H of the results.  Returns immediately.
+
+        maps_resident=True is the deployment shape: the head outputs (cls / bbox / iou maps) are already in the device
+        arena (written there by the conv towers, `device_views()`), so only the ground truth, the seeds and the mask
+        grids cross the bus (two copies: the small fields in front of the maps, the used mask grids behind them)."""
         if self._graph is None:
             self.capture()
         n = self.used_bytes(host_arena)
         with torch.cuda.stream(self._stream):
-            self._dev_arena[:n].copy_(host_arena[:n], non_blocking=True)
+            if maps_resident:
+                head = self._layout["cls0"][0]
+                moff = self._layout["mask_grids"][0]
+                self._dev_arena[:head].copy_(host_arena[:head], non_blocking=True)
+                if n > moff:
+                    self._dev_arena[moff:n].copy_(host_arena[moff:n], non_blocking=True)
+                n = head + max(0, n - moff)
+            else:
+                self._dev_arena[:n].copy_(host_arena[:n], non_blocking=True)
             self._graph.replay()
             self._done.record(self._stream)
         self.last_h2d_bytes = n
+
+    def device_views(self) -> Dict[str, torch.Tensor]:
+        """Views into the device arena (e.g. `cls0`, `bbox0`, `iou0`, ...: where a model writes its head outputs for
+        `launch(..., maps_resident=True)`)."""
+        return self._dviews
 
     def wait(self):
         """Block until the last launch has finished; returns the pinned result block (valid until the next launch)
