@@ -130,13 +130,15 @@ int radet_mt19937_seed(const uint32_t* seeds, int32_t batch, uint32_t* mt_states
  *   points_weight      f32   [B,P]                                           (label_assignment.py:199)
  *   consumed           int32 [B]    doubles drawn from the stream; -1 if `uniforms` ran out, -2 if an adaptive
  *                                   positive_num exceeded 32 (outputs invalid in both cases)
+ *   weight_sums        f64   [B]    optional (NULL = skip): sum of points_weight over the points with index >= 0 of each
+ *                                   image (0 for an image without ground truth) -- radet_loss_cfg_t.weight_sums
  * workspace: radet_assign_workspace_bytes(). */
 size_t radet_assign_workspace_bytes(const radet_grid_t* grid, int32_t batch);
 int radet_assign(const radet_grid_t* grid, int32_t batch, const int32_t* gt_offsets, const int32_t* gt_offsets_host,
                  const float* gt_bboxes, const uint32_t* mask_bits, int32_t mask_h, int32_t mask_w, int32_t mask_step,
                  const double* uniforms, int32_t n_uniform, const uint32_t* seeds, uint32_t* mt_states,
                  int32_t positive_num, int32_t balance_sample, int64_t* points_to_gt_index, float* points_weight,
-                 int32_t* consumed, void* workspace, size_t workspace_bytes, void* stream);
+                 int32_t* consumed, double* weight_sums, void* workspace, size_t workspace_bytes, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Target gather + TBLR encode.  Replaces RADetHead.get_targets / _get_target_single
@@ -171,6 +173,11 @@ typedef struct {
   float w_cls, w_bbox, w_iou;         /* loss_weight of the three terms (1, 2, 1) */
   float eps;                          /* GIoULoss.eps (1e-6); iou target uses bbox_overlaps default 1e-6 */
   float avg_extra;                    /* num_imgs */
+  /* Optional (NULL = compute it): per-image sum of points_weight over the points with points_to_gt_index >= 0 in images
+   * that have ground truth, double[batch] on the device -- what radet_assign(weight_sums=...) writes next to the
+   * assignment.  num_pos (radet_head.py:254) is the sum of these; with it the dense pass does not have to wait for
+   * its own reduction over the index / weight arrays.  Must match the arrays passed; ignored unless phases == 3. */
+  const double* weight_sums;
 } radet_loss_cfg_t;
 /* phases: RADET_LOSS_PHASE_NORMALIZERS computes num_pos / sum(wq) into workspace doubles [0] and [1];
  * RADET_LOSS_PHASE_DENSE consumes them.  Pass both (3) for the reference behaviour (rank-local normalisers,

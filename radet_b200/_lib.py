@@ -33,7 +33,7 @@ class Maps(Structure):
 
 class LossCfg(Structure):
     _fields_ = [("gamma", c_float), ("alpha", c_float), ("w_cls", c_float), ("w_bbox", c_float), ("w_iou", c_float),
-                ("eps", c_float), ("avg_extra", c_float)]
+                ("eps", c_float), ("avg_extra", c_float), ("weight_sums", c_void_p)]
 
 
 class DetectCfg(Structure):
@@ -53,7 +53,7 @@ _SIGS = {
     "radet_assign_workspace_bytes": (c_size_t, [POINTER(Grid), c_int32]),
     "radet_assign": (c_int32, [POINTER(Grid), c_int32, c_void_p, POINTER(c_int32), c_void_p, c_void_p, c_int32, c_int32, c_int32,
                                c_void_p, c_int32, c_void_p, c_void_p, c_int32, c_int32, c_void_p, c_void_p, c_void_p,
-                               c_void_p, c_size_t, c_void_p]),
+                               c_void_p, c_void_p, c_size_t, c_void_p]),
     "radet_get_targets": (c_int32, [POINTER(Grid), c_int32, c_int32, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                                     c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     "radet_loss_workspace_bytes": (c_size_t, [POINTER(Grid), c_int32, c_int32]),

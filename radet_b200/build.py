@@ -12,7 +12,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB_DIR = os.path.join(HERE, "lib")
 LIB = os.path.join(LIB_DIR, "libradet_b200.so")
-SOURCES = ["capi.cu", "assign.cu", "loss.cu", "detect.cu", "nms_list.cu"]
+SOURCES = ["capi.cu", "assign.cu", "loss.cu", "loss_fused.cu", "detect.cu", "nms_list.cu"]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-Xcompiler", "-fPIC",
          "--expt-relaxed-constexpr"]
@@ -29,7 +29,7 @@ def build(force=False, verbose=False):
     os.makedirs(LIB_DIR, exist_ok=True)
     obj_dir = os.path.join(HERE, "build")
     os.makedirs(obj_dir, exist_ok=True)
-    headers = [os.path.join(CSRC, "common.cuh"), os.path.join(HERE, "..", "include", "radet_b200.h"), __file__]
+    headers = [os.path.join(CSRC, "common.cuh"), os.path.join(CSRC, "loss_common.cuh"), os.path.join(HERE, "..", "include", "radet_b200.h"), __file__]
     objs, procs = [], []
     for src in SOURCES:
         s = os.path.join(CSRC, src)

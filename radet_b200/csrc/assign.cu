@@ -422,7 +422,8 @@ assign_resolve_kernel(GridDev grid, const int* __restrict__ gt_offsets, const fl
                       const double* __restrict__ uniforms, int n_uniform, const uint32_t* __restrict__ seeds,
                       uint32_t* __restrict__ mt_states, uint32_t* __restrict__ g_list, uint16_t* __restrict__ g_own,
                       int list_in_smem, int64_t* __restrict__ out_idx, float* __restrict__ out_w,
-                      int* __restrict__ consumed, int state_writeback, long long* __restrict__ dbg) {
+                      int* __restrict__ consumed, double* __restrict__ weight_sums, int state_writeback,
+                      long long* __restrict__ dbg) {
 #define RESOLVE_DBG(k) do { if (dbg && lane == 0) dbg[(int64_t)blockIdx.x * 16 + (k)] = clock64(); } while (0)
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
@@ -458,7 +459,10 @@ assign_resolve_kernel(GridDev grid, const int* __restrict__ gt_offsets, const fl
       idx[p] = -1;
       wt[p] = 1.0f;
     }
-    if (tid == 0) consumed[b] = 0;
+    if (tid == 0) {
+      consumed[b] = 0;
+      if (weight_sums) weight_sums[b] = 0.0;
+    }
     return;
   }
   area_ranks(gt_bboxes + 4 * (int64_t)g0, G, s_area, s_rank2gt);
@@ -786,6 +790,7 @@ assign_resolve_kernel(GridDev grid, const int* __restrict__ gt_offsets, const fl
     // (a GT sampling from its fallback set has only such points)
     const float pro = (mult && ((S->F[r >> 5] >> (r & 31)) & 1u)) ? 1e-8f : 1.0f;
     int running = 0;
+    double wsum = 0.0;                                    // sum of the weights written for this GT (weight_sums)
     for (int base = 0; base < M; base += 32) {
       const int e = base + lane;
       const bool mine = e < M && own[e] == (uint16_t)r;
@@ -798,9 +803,24 @@ assign_resolve_kernel(GridDev grid, const int* __restrict__ gt_offsets, const fl
           if (selpos[j] == mpos) cnt = selcnt[j];
         const int p = (int)list[e];
         idx[p] = cnt > 0 ? gt1 : 0;          // label_assignment.py:193-194
-        wt[p] = __fmul_rn((float)cnt, pro);  // :195-196, :127-128
+        const float wv = __fmul_rn((float)cnt, pro);
+        wt[p] = wv;                          // :195-196, :127-128
+        wsum += (double)wv;
       }
       running += __popc(ball);
+    }
+    if (weight_sums) {                                    // the sampling is over: its pre-tempered stream buffer is free
+      wsum = warp_sum(wsum);
+      if (lane == 0) reinterpret_cast<double*>(s_xbuf)[r] = wsum;
+    }
+  }
+  if (weight_sums) {
+    __syncthreads();
+    if (tid == 0) {
+      double tot = 0.0;
+      for (int r = 0; r < G; ++r)
+        if (s_nr[r] != 0) tot += reinterpret_cast<double*>(s_xbuf)[r];
+      weight_sums[b] = tot;
     }
   }
   if (wid == 1) RESOLVE_DBG(5);
@@ -863,7 +883,8 @@ extern "C" int radet_assign(const radet_grid_t* grid, int32_t batch, const int32
                             const float* gt_bboxes, const uint32_t* mask_bits, int32_t mask_h, int32_t mask_w,
                             int32_t mask_step, const double* uniforms, int32_t n_uniform, const uint32_t* seeds,
                             uint32_t* mt_states, int32_t positive_num, int32_t balance_sample, int64_t* points_to_gt_index,
-                            float* points_weight, int32_t* consumed, void* workspace, size_t workspace_bytes, void* stream) {
+                            float* points_weight, int32_t* consumed, double* weight_sums, void* workspace, size_t workspace_bytes,
+                            void* stream) {
   GridDev g;
   int rc = make_grid_dev(grid, &g);
   if (rc != RADET_OK) return rc;
@@ -927,7 +948,7 @@ extern "C" int radet_assign(const radet_grid_t* grid, int32_t batch, const int32
                                                                    states_arg,                                            \
                                                                    g_list, g_own, list_in_smem ? 1 : 0,                  \
                                                                    points_to_gt_index, points_weight, consumed,          \
-                                                                   seeds ? 0 : 1,                                       \
+                                                                   weight_sums, seeds ? 0 : 1,                          \
                                                                    static_cast<long long*>(g_debug_buf));               \
     RADET_LAUNCH_CHECK();                                                                                                \
   } while (0)

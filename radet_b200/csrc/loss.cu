@@ -16,32 +16,11 @@
 //
 // Algorithmic traffic: (8C + 52) B/point  (C logits read + C grads written + 16 B bbox + 4 B iou read, 20 B grads
 // written, 8 B index + 4 B weight read).
-#include "common.cuh"
+#include "loss_common.cuh"
 
 namespace radet {
 
-struct MapsDev {
-  const float* cls[RADET_MAX_LEVELS];
-  const float* bbox[RADET_MAX_LEVELS];
-  const float* iou[RADET_MAX_LEVELS];
-};
-struct GradsDev {
-  float* cls[RADET_MAX_LEVELS];
-  float* bbox[RADET_MAX_LEVELS];
-  float* iou[RADET_MAX_LEVELS];
-};
-
 // ------------------------------------------------------------------------------------------------ targets
-// radet_head.py:373-392 + tblr_bbox_coder.py:71-114.  label: C for idx<0; gt_labels[idx-1] with python negative
-// indexing for idx==0 (last GT).  target: ((d / (scale*stride)) / 0.125), order T,B,L,R.
-__device__ __forceinline__ int64_t label_of(int64_t idx, int G, const int64_t* __restrict__ gt_labels, int C) {
-  if (G <= 0 || idx < 0) return C;
-  int64_t k = idx - 1;
-  if (k < 0) k += G;
-  if (k >= G) k = G - 1;
-  return gt_labels[k];
-}
-
 __global__ void get_targets_kernel(GridDev grid, int B, int C, const int* __restrict__ gt_offsets,
                                    const float* __restrict__ gt_bboxes, const int64_t* __restrict__ gt_labels,
                                    const int64_t* __restrict__ pidx, const float* __restrict__ pw,
@@ -79,99 +58,6 @@ __global__ void get_targets_kernel(GridDev grid, int B, int C, const int* __rest
     anchors[row] = make_float4(cx - half, cy - half, cx + half, cy + half);
   }
 }
-
-// ------------------------------------------------------------------------------------------------ box terms
-struct BoxTerms {
-  float iou, giou;
-  float d[4];  // d giou / d (T, B, L, R)
-};
-
-// split of torch.max / torch.min gradients at ties (0.5 each), clamp(min=0) passes the gradient at 0
-__device__ __forceinline__ float sel_gt(float a, float b) { return a > b ? 1.f : (a == b ? 0.5f : 0.f); }
-
-template <bool kGrad>
-__device__ __forceinline__ BoxTerms box_terms(float cx, float cy, float s, float T, float Bt, float L, float R,
-                                              float tT, float tB, float tL, float tR, float eps_iou, float eps_giou) {
-  // decode (tblr_bbox_coder.py:154-166): loc = (v*normalizer)*side = v*s with s = normalizer*side (= stride for
-  // the shipped 1/8 x 8*stride, where both scalings are exact); no clamp in training
-  const float px1 = cx - L * s, py1 = cy - T * s, px2 = cx + R * s, py2 = cy + Bt * s;
-  const float tx1 = cx - tL, ty1 = cy - tT, tx2 = cx + tR, ty2 = cy + tB;
-  const float wp = px2 - px1, hp = py2 - py1;
-  const float area_p = wp * hp, area_t = (tx2 - tx1) * (ty2 - ty1);
-  const float ltx = fmaxf(px1, tx1), lty = fmaxf(py1, ty1), rbx = fminf(px2, tx2), rby = fminf(py2, ty2);
-  const float iw_raw = rbx - ltx, ih_raw = rby - lty;
-  const float iw = fmaxf(iw_raw, 0.f), ih = fmaxf(ih_raw, 0.f);
-  const float ov = iw * ih;
-  const float union_raw = area_p + area_t - ov;
-  BoxTerms o;
-  // IoU target: bbox_overlaps(..., eps=1e-6) (radet_head.py:267)
-  o.iou = ov / fmaxf(union_raw, eps_iou);
-  // GIoU: bbox_overlaps(mode='giou', eps=GIoULoss.eps) (iou_loss.py:96)
-  const float uni = fmaxf(union_raw, eps_giou);
-  const float iou_g = ov / uni;
-  const float elx = fminf(px1, tx1), ely = fminf(py1, ty1), erx = fmaxf(px2, tx2), ery = fmaxf(py2, ty2);
-  const float ew_raw = erx - elx, eh_raw = ery - ely;
-  const float ew = fmaxf(ew_raw, 0.f), eh = fmaxf(eh_raw, 0.f);
-  const float ea_raw = ew * eh;
-  const float ea = fmaxf(ea_raw, eps_giou);
-  o.giou = iou_g - (ea - uni) / ea;
-  if (kGrad) {
-    const float pw_ = iw_raw >= 0.f ? 1.f : 0.f, ph_ = ih_raw >= 0.f ? 1.f : 0.f;
-    // d ov / d (px1, py1, px2, py2)
-    const float dov[4] = {-pw_ * sel_gt(px1, tx1) * ih, -ph_ * sel_gt(py1, ty1) * iw, pw_ * sel_gt(tx2, px2) * ih,
-                          ph_ * sel_gt(ty2, py2) * iw};
-    const float dap[4] = {-hp, -wp, hp, wp};
-    const float up = sel_gt(union_raw, eps_giou);
-    const float pew = ew_raw >= 0.f ? 1.f : 0.f, peh = eh_raw >= 0.f ? 1.f : 0.f;
-    const float ep = sel_gt(ea_raw, eps_giou);
-    const float dea[4] = {-ep * pew * sel_gt(tx1, px1) * eh, -ep * peh * sel_gt(ty1, py1) * ew,
-                          ep * pew * sel_gt(px2, tx2) * eh, ep * peh * sel_gt(py2, ty2) * ew};
-    const float inv_u = 1.f / uni, inv_e = 1.f / ea;
-    const float u_over_e = uni * inv_e;
-    float dz[4];
-#pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      const float dun = up * (dap[k] - dov[k]);
-      const float diou = (dov[k] - iou_g * dun) * inv_u;
-      dz[k] = diou + (dun - u_over_e * dea[k]) * inv_e;
-    }
-    // chain to (T,B,L,R): py1 = cy - T s, py2 = cy + B s, px1 = cx - L s, px2 = cx + R s
-    o.d[0] = -s * dz[1];
-    o.d[1] = s * dz[3];
-    o.d[2] = -s * dz[0];
-    o.d[3] = s * dz[2];
-  }
-  return o;
-}
-
-__device__ __forceinline__ void point_target(int64_t idx, int G, const float* __restrict__ gtb, float cx, float cy,
-                                             float& tT, float& tB, float& tL, float& tR) {
-  // decoded target distances in pixels: encode/decode scalings are exact powers of two, so decode(encode(d)) = d
-  tT = tB = tL = tR = 0.f;
-  if (idx > 0) {
-    const int k = (int)((idx - 1) < (int64_t)(G - 1) ? (idx - 1) : (int64_t)(G - 1));
-    const float4 gb = *reinterpret_cast<const float4*>(gtb + 4 * (int64_t)k);
-    tT = cy - gb.y;
-    tB = gb.w - cy;
-    tL = cx - gb.x;
-    tR = gb.z - cx;
-  }
-}
-
-__device__ __forceinline__ float bce_logits(float x, float z) {  // torch: max(x,0) - x*z + log1p(exp(-|x|))
-  return fmaxf(x, 0.f) - x * z + log1pf(expf(-fabsf(x)));
-}
-__device__ __forceinline__ float sigmoidf_(float x) { return 1.0f / (1.0f + expf(-x)); }
-
-// workspace layout (doubles): [0..7] final sums / normalisers, then block partials
-constexpr int kPosThreads = 256;
-constexpr int kPosPerThread = 4;
-constexpr int kNormSlots = 8;   // S0 num_pos, S1 sum wq, S2 sum wq(1-giou), S3 sum w*bce, S4 sum pred, S5 sum iou logit
-struct LossWs {
-  double norm[kNormSlots];
-  unsigned int counter_pos, counter_dense;
-  unsigned int pad[2];
-};
 
 __global__ void __launch_bounds__(kPosThreads)
 loss_pos_kernel(GridDev grid, int B, MapsDev maps, const int* __restrict__ gt_offsets,
@@ -295,46 +181,6 @@ struct DenseTable {
   int uoff[RADET_MAX_LEVELS + 1];  // unit (4-point group) offsets per level over the whole batch
   int upl[RADET_MAX_LEVELS];       // units per (image, level) plane
 };
-
-// Sigmoid focal loss and its derivative for one logit (mmcv sigmoid_focal_loss semantics; restated from
-// focal_loss.py:10-41 because the mmcv op is not in the reference tree).  Tolerance parity (not bit parity), so the
-// transcendental part is kept to ~28 instructions per element (at 70+ the kernel is issue-bound, not HBM-bound):
-// one ex2.approx, one rcp.approx and one lg2.approx:
-//     e = exp(-|z|),  inv = 1/(1+e),  log1p(e) = -ln(inv).
-// The target case is folded into the non-target one by symmetry: with z = -x,
-//     FL_target(x) = alpha * sigmoid(z)^gamma * softplus(z),  dFL_target/dx = -d/dz[...],
-// so a single expression  m = coef * s^gamma,  loss = m * softplus(z),  dloss/dz = m * (s + gamma * (1-s) * softplus(z))
-// with s = sigmoid(z) serves both (coef = alpha for the target class, 1-alpha otherwise).
-__device__ __forceinline__ float ex2_approx(float x) {
-  float y;
-  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
-  return y;
-}
-__device__ __forceinline__ float rcp_approx(float x) {
-  float y;
-  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
-  return y;
-}
-__device__ __forceinline__ float lg2_approx(float x) {
-  float y;
-  asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
-  return y;
-}
-template <bool kGamma2>
-__device__ __forceinline__ void focal_elem(float x, bool is_t, float gamma, float alpha, float& loss, float& grad) {
-  const float z = is_t ? -x : x;
-  const float e = ex2_approx(fabsf(z) * -1.4426950408889634f);   // exp(-|z|) in (0, 1]
-  const float inv = rcp_approx(1.0f + e);                         // 1/(1+e) in [0.5, 1)
-  // softplus(z) = max(z,0) + log1p(e) = max(z,0) - ln(inv): one lg2.approx (absolute error ~1e-7 on a term that is
-  // only tiny where the whole element is negligible: its gradient carries the factor s^2 ~ e^2)
-  const float sp = fmaf(-0.6931471805599453f, lg2_approx(inv), fmaxf(z, 0.f));
-  const float s = z >= 0.f ? inv : e * inv;       // sigmoid(z)
-  const float coef = is_t ? alpha : 1.f - alpha;
-  const float m = coef * (kGamma2 ? s * s : ex2_approx(gamma * -1.4426950408889634f * (sp - z)));   // s^gamma = exp(-gamma*softplus(-z))
-  loss = m * sp;
-  const float g = m * fmaf(kGamma2 ? fmaf(-2.f, s, 2.f) : gamma * (1.f - s), sp, s);
-  grad = is_t ? -g : g;
-}
 
 constexpr int kDG = 2;   // class planes per load group (pairs ping-pong between two register sets)
 
@@ -859,8 +705,6 @@ static int dense_plan(const GridDev& g, int B, int C, DenseTable* tab, int* cc, 
 // Tiles of the TMA-pipelined dense kernel; false when some level is not 16-byte tileable (h*w % 4 != 0) or the
 // development override RADET_DENSE_IMPL=reg is set.
 static bool tile_plan(const GridDev& g, int B, TileTable* tt, int* blocks) {
-  static const char* impl = getenv("RADET_DENSE_IMPL");
-  if (impl && impl[0] == 'r') return false;
   int t = 0;
   for (int l = 0; l < g.num_levels; ++l) {
     const int hw = g.h[l] * g.w[l];
@@ -878,20 +722,31 @@ static bool tile_plan(const GridDev& g, int B, TileTable* tt, int* blocks) {
   return true;
 }
 
+// workspace: LossWs | loss_pos partials | dense partials (two-launch path) | fused-kernel partials
+static void loss_ws_layout(const GridDev& g, int batch, int num_classes, int dblk, size_t* off_pos, size_t* off_dense, size_t* off_fused,
+                           size_t* total) {
+  const int64_t n = (int64_t)batch * g.off[g.num_levels];
+  const int64_t pos_blocks = (n + kPosThreads * kPosPerThread - 1) / (kPosThreads * kPosPerThread);
+  const int64_t dense_blocks = dblk > (int)(kSMs * 8) ? dblk : (int)(kSMs * 8);   // either two-launch kernel's partial-sum slots
+  size_t o = align_up(sizeof(LossWs), 256);
+  *off_pos = o;
+  o += align_up((size_t)pos_blocks * 6 * 8, 256);
+  *off_dense = o;
+  o += align_up((size_t)dense_blocks * 8, 256);
+  *off_fused = o;
+  o += fused_part_bytes(g, batch, num_classes);
+  *total = o;
+}
+
 extern "C" size_t radet_loss_workspace_bytes(const radet_grid_t* grid, int32_t batch, int32_t num_classes) {
   GridDev g;
   if (make_grid_dev(grid, &g) != RADET_OK || batch <= 0 || num_classes <= 0) return 0;
   DenseTable tab;
   int cc, nj, dblk;
   if (dense_plan(g, batch, num_classes, &tab, &cc, &nj, &dblk) != RADET_OK) return 0;
-  const int64_t n = (int64_t)batch * g.off[g.num_levels];
-  const int64_t pos_blocks = (n + kPosThreads * kPosPerThread - 1) / (kPosThreads * kPosPerThread);
-  TileTable tt;
-  int tma_blocks = 0;
-  tile_plan(g, batch, &tt, &tma_blocks);
-  const int64_t dense_blocks = dblk > (int)(kSMs * 8) ? dblk : (int)(kSMs * 8);   // either kernel's partial-sum slots
-  (void)tma_blocks;
-  return align_up(sizeof(LossWs), 256) + align_up((size_t)pos_blocks * 6 * 8, 256) + align_up((size_t)dense_blocks * 8, 256);
+  size_t a, b, c, total;
+  loss_ws_layout(g, batch, num_classes, dblk, &a, &b, &c, &total);
+  return total;
 }
 
 extern "C" int radet_loss_fwd_bwd(const radet_grid_t* grid, int32_t batch, int32_t num_classes, const radet_maps_t* maps,
@@ -929,24 +784,38 @@ extern "C" int radet_loss_fwd_bwd(const radet_grid_t* grid, int32_t batch, int32
   int cc, nj, dblk;
   rc = dense_plan(g, batch, num_classes, &tab, &cc, &nj, &dblk);
   if (rc != RADET_OK) return rc;
+  // RADET_LOSS_IMPL: "fused" = the experimental single-launch kernel (loss_fused.cu); "reg" = the register-pipelined dense
+  // kernel even where the TMA one applies.  Default: loss_pos_kernel + loss_dense_tma_kernel (see DESIGN.md section 4 for the
+  // measurements behind that choice).
+  const char* impl = getenv("RADET_LOSS_IMPL");
   TileTable tt;
   int tma_blocks = 0;
   const bool use_tma = tile_plan(g, batch, &tt, &tma_blocks);
   if (use_tma && tma_blocks > dblk) dblk = tma_blocks;       // partial-sum slots (workspace_bytes sizes for the max)
   unsigned char* wsb = static_cast<unsigned char*>(workspace);
   LossWs* ws = reinterpret_cast<LossWs*>(wsb);
+  size_t off_pos, off_dense, off_fused, total_ws;
+  loss_ws_layout(g, batch, num_classes, dblk, &off_pos, &off_dense, &off_fused, &total_ws);
   const int64_t n = (int64_t)batch * g.off[g.num_levels];
   const int64_t pos_blocks = (n + kPosThreads * kPosPerThread - 1) / (kPosThreads * kPosPerThread);
-  double* pos_part = reinterpret_cast<double*>(wsb + align_up(sizeof(LossWs), 256));
-  double* dense_part = reinterpret_cast<double*>(wsb + align_up(sizeof(LossWs), 256) + align_up((size_t)pos_blocks * 6 * 8, 256));
+  double* pos_part = reinterpret_cast<double*>(wsb + off_pos);
+  double* dense_part = reinterpret_cast<double*>(wsb + off_dense);
   cudaStream_t st = (cudaStream_t)stream;
+  if (impl && impl[0] == 'f') {
+    // single launch: normalisers, positive terms, dense pass and the three losses (or only one of the two phases).
+    // Shapes it does not take (a plane size that is not a multiple of 4, unaligned index / weight arrays) fall through.
+    const bool with_p1 = (phases & RADET_LOSS_PHASE_NORMALIZERS) != 0, with_items = (phases & RADET_LOSS_PHASE_DENSE) != 0;
+    rc = launch_loss_fused(g, batch, num_classes, md, gd, gt_offsets, gt_bboxes, gt_labels, points_to_gt_index, points_weight, *cfg,
+                           grad_scale, ws, wsb + off_fused, with_p1, with_items, losses, cfg->weight_sums, st);
+    if (rc != RADET_E_UNSUPPORTED) return rc;
+  }
   if (phases & RADET_LOSS_PHASE_NORMALIZERS) {
     loss_pos_kernel<<<(unsigned)pos_blocks, kPosThreads, 0, st>>>(g, batch, md, gt_offsets, gt_bboxes, points_to_gt_index,
                                                                   points_weight, *cfg, ws, pos_part, gd);
     RADET_LAUNCH_CHECK();
   }
   if (!(phases & RADET_LOSS_PHASE_DENSE)) return RADET_OK;
-  if (use_tma) {
+  if (use_tma && !(impl && impl[0] == 'r')) {
     if (cfg->gamma == 2.0f)
       loss_dense_tma_kernel<true><<<(unsigned)tma_blocks, kTmaThreads, 0, st>>>(g, tt, batch, num_classes, md, gd, gt_offsets, gt_labels,
                                                                                   points_to_gt_index, points_weight, *cfg, grad_scale,

@@ -117,10 +117,11 @@ def assign(geom: Geometry, level_shapes, gt_counts: Sequence[int], gt_bboxes: to
            mask_hw: Tuple[int, int], *, uniforms: Optional[torch.Tensor] = None, seeds: Optional[torch.Tensor] = None,
            mt_states: Optional[torch.Tensor] = None, positive_num: int = 10, balance_sample: bool = True,
            gt_offsets: Optional[Tuple[np.ndarray, torch.Tensor]] = None, out=None, adapt_positive_num: bool = False,
-           multiply_samplepro_for_weight: bool = False):
+           multiply_samplepro_for_weight: bool = False, weight_sums: Optional[torch.Tensor] = None):
     """Batched LabelAssignment (label_assignment.py:136-201).  Returns points_to_gt_index int64 [B,P],
     points_weight f32 [B,P], consumed int32 [B] (written into `out` = (idx, w, consumed) when given; -1 = the uniforms
-    ran out, -2 = an adaptive positive_num above 32)."""
+    ran out, -2 = an adaptive positive_num above 32).  weight_sums (optional float64 [B], written): per-image sum of the
+    weights of the points with index >= 0 -- hand it to loss_fwd_bwd(weight_sums=...) together with idx / w."""
     _require_cuda(gt_bboxes, "gt_bboxes")
     dev = gt_bboxes.device
     off_h, off_d = gt_offsets if gt_offsets is not None else offsets_of(gt_counts, dev)
@@ -145,11 +146,13 @@ def assign(geom: Geometry, level_shapes, gt_counts: Sequence[int], gt_bboxes: to
         n_uniform = uniforms.shape[1]
     if seeds is not None and seeds.dtype != torch.int32:
         seeds = seeds.to(torch.int32)
+    if weight_sums is not None and (weight_sums.dtype != torch.float64 or weight_sums.numel() != B or not weight_sums.is_cuda):
+        raise RadetError("assign(weight_sums=...): need a CUDA float64 [B] tensor")
     check(lib.radet_assign(ctypes.byref(grid), B, _ptr(off_d), off_h.ctypes.data_as(ctypes.POINTER(ctypes.c_int32)),
                            _ptr(gt_bboxes.contiguous()), _ptr(mask_bits), mask_hw[0], mask_hw[1], geom.mask_step,
                            _ptr(uniforms), n_uniform, _ptr(seeds), _ptr(mt_states), positive_num,
                            int(bool(balance_sample)) | (2 if adapt_positive_num else 0) | (4 if multiply_samplepro_for_weight else 0),
-                           _ptr(idx), _ptr(w), _ptr(consumed), _ptr(ws), ws.numel(), _stream()), "radet_assign")
+                           _ptr(idx), _ptr(w), _ptr(consumed), _ptr(weight_sums), _ptr(ws), ws.numel(), _stream()), "radet_assign")
     return idx, w, consumed
 
 
@@ -178,10 +181,11 @@ class LossConfig:
     def __init__(self, gamma=2.0, alpha=0.25, w_cls=1.0, w_bbox=2.0, w_iou=1.0, eps=1e-6):
         self.gamma, self.alpha, self.w_cls, self.w_bbox, self.w_iou, self.eps = gamma, alpha, w_cls, w_bbox, w_iou, eps
 
-    def c_struct(self, avg_extra):
+    def c_struct(self, avg_extra, weight_sums=None):
         c = _lib.LossCfg()
         c.gamma, c.alpha, c.w_cls, c.w_bbox, c.w_iou, c.eps, c.avg_extra = (self.gamma, self.alpha, self.w_cls, self.w_bbox,
                                                                               self.w_iou, self.eps, float(avg_extra))
+        c.weight_sums = None if weight_sums is None else weight_sums.data_ptr()
         return c
 
 
@@ -196,12 +200,14 @@ def _check_maps(cls, bbox, iou, level_shapes, B, C):
 
 def loss_fwd_bwd(geom: Geometry, num_classes: int, cls, bbox, iou, gt_counts, gt_bboxes, gt_labels, idx, w,
                  cfg: LossConfig, want_grads=True, grad_scale: Optional[torch.Tensor] = None, gt_offsets=None,
-                 sync_group=None):
+                 sync_group=None, weight_sums: Optional[torch.Tensor] = None):
     """Fused RADetHead.loss forward+backward (radet_head.py:173-288).  Returns losses f32[4]
     (loss_cls, loss_bbox, loss_iou, num_pos) and (grad_cls, grad_bbox, grad_iou) lists (or None).
 
     sync_group: opt-in FCOS/ATSS-style reduce_mean of the two normalisers over that process group (NOT the
-    reference behaviour of RADetHead, which keeps them rank-local)."""
+    reference behaviour of RADetHead, which keeps them rank-local).
+    weight_sums: optional float64 [B] written by assign(weight_sums=...) for these idx / w: the dense pass then starts
+    without waiting for its own reduction over them."""
     B = cls[0].shape[0]
     level_shapes = tuple(tuple(t.shape[-2:]) for t in cls)
     _check_maps(cls, bbox, iou, level_shapes, B, num_classes)
@@ -234,7 +240,9 @@ def loss_fwd_bwd(geom: Geometry, num_classes: int, cls, bbox, iou, gt_counts, gt
     losses = torch.empty((4,), dtype=torch.float32, device=dev)
     nws = lib.radet_loss_workspace_bytes(ctypes.byref(grid), B, num_classes)
     ws = _workspace(("loss", B, P, num_classes), nws, dev)
-    ccfg = cfg.c_struct(avg_extra=B)
+    if weight_sums is not None and (weight_sums.dtype != torch.float64 or weight_sums.numel() != B or not weight_sums.is_cuda):
+        raise RadetError("loss_fwd_bwd(weight_sums=...): need a CUDA float64 [B] tensor")
+    ccfg = cfg.c_struct(avg_extra=B, weight_sums=weight_sums if sync_group is None else None)
 
     def run(phases):
         check(lib.radet_loss_fwd_bwd(ctypes.byref(grid), B, num_classes, ctypes.byref(maps), _ptr(off_d),
@@ -274,6 +282,7 @@ class HeadLossFunction(torch.autograd.Function):
         losses, grads = loss_fwd_bwd(geom, num_classes, cls, bbox, iou, gt_counts, gt_bboxes, gt_labels, idx, w, cfg,
                                      want_grads=need, sync_group=sync_group)
         ctx.geom, ctx.num_classes, ctx.grads, ctx.nlev = geom, num_classes, grads, nlev
+        ctx.applied = None            # upstream factors already folded into ctx.grads (after the first backward)
         return losses[0], losses[1], losses[2], losses[3]
 
     @staticmethod
@@ -284,8 +293,15 @@ class HeadLossFunction(torch.autograd.Function):
         z = lambda g, ref: torch.zeros((), dtype=torch.float32, device=ref.device) if g is None else g.reshape(()).float()
         ref = grads[0][0]
         up = torch.stack([z(g_cls, ref), z(g_bbox, ref), z(g_iou, ref)])
-        scale_grads(ctx.geom, ctx.num_classes, grads, up)   # exits early on the device when upstream == (1,1,1)
-        return (None,) * 10 + tuple(grads[0]) + tuple(grads[1]) + tuple(grads[2])
+        if ctx.applied is None:       # first backward: rescale the forward's buffers in place (no extra memory, no copy)
+            scale_grads(ctx.geom, ctx.num_classes, grads, up)   # exits early on the device when upstream == (1,1,1)
+            ctx.applied = up
+            return (None,) * 10 + tuple(grads[0]) + tuple(grads[1]) + tuple(grads[2])
+        # re-entrant use (retain_graph=True, autograd.grad twice, checkpointing): the buffers already carry the first call's
+        # factors and were handed out; return fresh tensors scaled by the ratio instead of compounding in place
+        ratio = up / ctx.applied
+        out = [[t * ratio[k] for t in grads[k]] for k in range(3)]
+        return (None,) * 10 + tuple(out[0]) + tuple(out[1]) + tuple(out[2])
 
 
 def head_loss(geom, num_classes, cfg, cls, bbox, iou, gt_counts, gt_bboxes, gt_labels, idx, w, sync_group=None):
@@ -439,12 +455,31 @@ class DetectConfig:
                    cluster_score=nms.get("cluster_score", "cls"), vote_score=nms.get("vote_score", "iou"),
                    iou_enable=nms.get("iou_enable", False), sigma=nms.get("sigma", 0.025))
 
+    def with_max_per_img(self, n):
+        import copy
+        c = copy.copy(self)
+        c.max_per_img = int(n)
+        return c
+
     def c_struct(self, rescale):
         c = _lib.DetectCfg()
         c.score_thr, c.nms_pre, c.max_per_img, c.nms_mode = self.score_thr, self.nms_pre, self.max_per_img, self.nms_mode
         c.iou_threshold, c.cluster_score_mode, c.vote_score_mode = self.iou_threshold, self.cs_mode, self.vs_mode
         c.iou_enable, c.sigma, c.rescale = int(self.iou_enable), self.sigma, int(bool(rescale))
         return c
+
+
+def _check_image_info(img_shapes, scale_factors, B, rescale):
+    _require_cuda(img_shapes, "img_shapes")
+    if img_shapes.dtype != torch.int32 or tuple(img_shapes.shape) != (B, 2) or not img_shapes.is_contiguous():
+        raise RadetError(f"img_shapes must be a contiguous int32 [{B},2] (h,w) tensor, got {img_shapes.dtype} {tuple(img_shapes.shape)}")
+    if scale_factors is None:
+        if rescale:
+            raise RadetError("rescale=True needs scale_factors")
+        return
+    _require_cuda(scale_factors, "scale_factors")
+    if scale_factors.dtype != torch.float32 or tuple(scale_factors.shape) != (B, 4) or not scale_factors.is_contiguous():
+        raise RadetError(f"scale_factors must be a contiguous float32 [{B},4] tensor, got {scale_factors.dtype} {tuple(scale_factors.shape)}")
 
 
 def get_bboxes(geom: Geometry, num_classes: int, cls, bbox, iou, img_shapes: torch.Tensor, scale_factors: torch.Tensor,
@@ -454,6 +489,10 @@ def get_bboxes(geom: Geometry, num_classes: int, cls, bbox, iou, img_shapes: tor
     B = cls[0].shape[0]
     level_shapes = tuple(tuple(t.shape[-2:]) for t in cls)
     _check_maps(cls, bbox, iou, level_shapes, B, num_classes)
+    _check_image_info(img_shapes, scale_factors, B, rescale)
+    if cfg.max_per_img <= 0:     # the reference reads max_num <= 0 as "no cap" (vote_wrapper.py:39-42)
+        cap = int(_lib.load().radet_candidates_capacity(ctypes.byref(geom.grid(level_shapes)), num_classes, cfg.nms_pre))
+        cfg = cfg.with_max_per_img(min(cap, 4096))
     dev = cls[0].device
     cls = [t.contiguous() for t in cls]
     bbox = [t.contiguous() for t in bbox]
@@ -480,6 +519,7 @@ def get_candidates(geom: Geometry, num_classes: int, cls, bbox, iou, img_shapes:
     B = cls[0].shape[0]
     level_shapes = tuple(tuple(t.shape[-2:]) for t in cls)
     _check_maps(cls, bbox, iou, level_shapes, B, num_classes)
+    _check_image_info(img_shapes, scale_factors, B, rescale)
     dev = cls[0].device
     cls = [t.contiguous() for t in cls]
     bbox = [t.contiguous() for t in bbox]

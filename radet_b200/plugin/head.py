@@ -65,7 +65,8 @@ class RADetHead(nn.Module):
                  bbox_coder=dict(type='TBLRBBoxCoder', normalizer=1 / 8), reg_decoded_bbox=False,
                  loss_cls=dict(type='FocalLoss', use_sigmoid=True, gamma=2.0, alpha=0.25, loss_weight=1.0),
                  loss_bbox=dict(type='GIoULoss', loss_weight=2.0), train_cfg=None, test_cfg=None,
-                 regress_ranges=F.REGRESS_RANGES, sync_num_pos=False, results_device='reference'):
+                 regress_ranges=F.REGRESS_RANGES, sync_num_pos=False, results_device='reference',
+                 label_assignment=dict(positive_num=10, neg_threshold=0.2, adapt_positive_num=False, balance_sample=True)):
         super().__init__()
         if conv_cfg is not None:
             raise NotImplementedError("conv_cfg (DCN etc.) is outside the implemented surface")
@@ -104,6 +105,10 @@ class RADetHead(nn.Module):
                                      w_bbox=self.loss_bbox.loss_weight, w_iou=self.loss_iou.loss_weight, eps=self.loss_bbox.eps)
         self.sync_num_pos = sync_num_pos       # opt-in FCOS-style reduce_mean; False = reference behaviour
         self.results_device = results_device   # 'reference': vote branches return CPU tensors like radet_head.py:150-158
+        # the assignment the head runs itself when the loader hands over mask grids (PackVisibleMaskGrid) instead of
+        # assigned indices; the defaults are the shipped pipeline's (configs/base/datasets/bop_detection.py:19-32)
+        self.label_assignment_cfg = dict(label_assignment)
+        self._assigner = None
         self._init_layers()
 
     # ------------------------------------------------------------------ layers (atss_head.py:52-98)
@@ -144,8 +149,35 @@ class RADetHead(nn.Module):
         iou_pred = self.atss_centerness(reg_feat)
         return cls_score, bbox_pred, iou_pred
 
+    def assigner(self):
+        if self._assigner is None:
+            from .pipelines import LabelAssignment
+            self._assigner = LabelAssignment(strides=self.strides, regress_ranges=self.geom.regress_ranges,
+                                             anchor_generator_cfg=dict(type='AnchorGenerator', ratios=[1.0],
+                                                                       octave_base_scale=int(self.geom.anchor_scale),
+                                                                       scales_per_octave=1, strides=list(self.strides)),
+                                             **self.label_assignment_cfg)
+        return self._assigner
+
+    def assign_from_mask_grids(self, img_metas, gt_bboxes, mask_grids, seeds):
+        """The loader handed over PackVisibleMaskGrid's sample grids: run LabelAssignment for the whole batch here, on the
+        training GPU (label_assignment.py:136-201; one launch pair for all images instead of ~25 ms of numpy per image in
+        a worker).  seeds: per-image int tensors / ints (np.random.seed(seed) right before each image)."""
+        shapes = [(int(m['img_shape'][0]), int(m['img_shape'][1])) for m in img_metas]
+        dev = self.atss_cls.weight.device
+        sd = torch.as_tensor([int(torch.as_tensor(s).reshape(-1)[0]) for s in seeds], dtype=torch.int64).to(dev, non_blocking=True)
+        with torch.cuda.device(dev):
+            idx, w, consumed = self.assigner().assign_batch(shapes, gt_bboxes, mask_grids, seeds=sd)
+        return idx, w
+
     def forward_train(self, x, img_metas, gt_bboxes, gt_labels=None, points_to_gt_index=None, points_weight=None,
                       gt_bboxes_ignore=None, proposal_cfg=None, **kwargs):
+        from .pipelines import is_mask_grid_handoff
+        if is_mask_grid_handoff(points_to_gt_index):          # PackVisibleMaskGrid in the pipeline: assign here, batched
+            points_to_gt_index, points_weight = self.assign_from_mask_grids(img_metas, gt_bboxes, points_to_gt_index, points_weight)
+        elif points_to_gt_index is None and gt_labels is not None:
+            raise RadetError("RADetHead.forward_train needs points_to_gt_index / points_weight: either the reference's assigned "
+                             "indices (LabelAssignment in the pipeline) or PackVisibleMaskGrid's mask grids + seeds under the same keys")
         outs = self(x)
         if gt_labels is None:
             loss_inputs = outs + (gt_bboxes, img_metas)
@@ -225,6 +257,7 @@ class RADetHead(nn.Module):
         dcfg = F.DetectConfig.from_test_cfg(cfg)
         dev = cls_scores[0].device
         B = len(img_metas)
+        assert B == cls_scores[0].shape[0], "one img_meta per image of the batch (atss_head.py:369 loops over img_metas)"
         shp = np.asarray([[m['img_shape'][0], m['img_shape'][1]] for m in img_metas], np.int32)
         sf = np.asarray([np.broadcast_to(np.asarray(m.get('scale_factor', 1.0), np.float32), (4,)) for m in img_metas], np.float32)
         shp_d = torch.from_numpy(shp).to(dev, non_blocking=True)

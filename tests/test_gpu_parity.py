@@ -921,6 +921,38 @@ def test_standalone_focal_other_gamma():
         np.testing.assert_allclose(x.grad.cpu().numpy(), g, rtol=1e-4, atol=1e-6 * float(np.abs(g).max()))
 
 
+def _fused_loss(wl, cls, bbox, iou, counts, boxes, labels, idx, w, **kw):
+    """The experimental single-launch kernel (loss_fused.cu) through the development switch."""
+    import os
+    os.environ["RADET_LOSS_IMPL"] = "fused"
+    try:
+        return F.loss_fwd_bwd(GEOM, wl.C, cls, bbox, iou, counts, boxes, labels, idx, w, F.LossConfig(), **kw)
+    finally:
+        del os.environ["RADET_LOSS_IMPL"]
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("key", ["small", "cfg1", "cfg3b2"])
+def test_loss_single_launch_variant_vs_oracle(key):
+    wl, batch, idx_l, w_l, ho = _head_inputs(key)
+    cls, bbox, iou = _to_dev(ho)
+    counts, boxes, labels = _gt_dev(batch)
+    idx = torch.from_numpy(np.stack(idx_l)).to(DEV)
+    w = torch.from_numpy(np.stack(w_l)).to(DEV)
+    losses, grads = _fused_loss(wl, cls, bbox, iou, counts, boxes, labels, idx, w)
+    o32 = orc.head_loss(ho.cls, ho.bbox, ho.iou, [b.gt_bboxes for b in batch], [b.gt_labels for b in batch], idx_l, w_l, wl.C, wl.H, wl.W)
+    losses = losses.cpu().numpy()
+    for i, k in enumerate(("loss_cls", "loss_bbox", "loss_iou")):
+        assert abs(losses[i] - o32[k]) <= 1e-5 * abs(o32[k]), (k, losses[i], o32[k])
+    assert losses[3] == o32["num_pos"]
+    _check_grads(grads[0], o32["grad_cls"], 1e-4, 1e-6)
+    _check_grads(grads[1], o32["grad_bbox"], 1e-4, 1e-6)
+    _check_grads(grads[2], o32["grad_iou"], 1e-4, 1e-6)
+    # forward only, and a second call on the same workspace (the control block re-arms itself)
+    l2, g2 = _fused_loss(wl, cls, bbox, iou, counts, boxes, labels, idx, w, want_grads=False)
+    assert g2 is None and torch.equal(l2.cpu(), torch.from_numpy(losses))
+
+
 @pytest.mark.gpu
 def test_loss_two_phase_normaliser_sync_path():
     """sync_num_pos: radet_loss_fwd_bwd(phases=1) -> reduce_mean of the two normalisers -> phases=2.  In a single process
