@@ -271,13 +271,17 @@ def get_targets(gt_bboxes_list, gt_labels_list, idx_list, w_list, num_classes, H
 # --------------------------------------------------------------------------- loss (floating point: torch CPU)
 def head_loss(cls_maps, bbox_maps, iou_maps, gt_bboxes_list, gt_labels_list, idx_list, w_list, num_classes,
               H, W, strides=STRIDES, gamma=2.0, alpha=0.25, w_cls=1.0, w_bbox=2.0, w_iou=1.0, eps=1e-6,
-              dtype="float32", need_grad=True):
+              dtype="float32", need_grad=True, normalizers=None):
     """RADetHead.loss (radet_head.py:173-288) with FocalLoss (focal_loss.py:10-41 py version, mmcv op absent),
     GIoULoss (iou_loss.py:82-98,319-354; bbox_overlaps iou2d_calculator.py:107-159) and
     CrossEntropyLoss(use_sigmoid) (cross_entropy_loss.py:58-91).
 
     Inputs are numpy NCHW maps per level.  Returns dict of python floats and (if need_grad) the gradients of
     (loss_cls + loss_bbox + loss_iou) w.r.t. every map, as numpy arrays in the same NCHW layout.
+
+    normalizers=(num_pos, sum_wq): the opt-in FCOS/ATSS-style variant in which the two normalisers are the reduce_mean
+    over the ranks (core/utils/dist_utils.py:63-69, atss_head.py:278,296) while the `num_pos > 0` branch (:261) stays
+    rank-local; None = RADetHead's own behaviour (rank-local, :254-259).  `sum_wq` (local) is part of the result.
     """
     import torch
     import torch.nn.functional as F
@@ -305,7 +309,8 @@ def head_loss(cls_maps, bbox_maps, iou_maps, gt_bboxes_list, gt_labels_list, idx
     pt = (1 - ps) * onehot + ps * (1 - onehot)
     fw = (alpha * onehot + (1 - alpha) * (1 - onehot)) * pt.pow(gamma)
     fl = F.binary_cross_entropy_with_logits(flat_cls, onehot, reduction="none") * fw
-    loss_cls = w_cls * (fl * wts.view(-1, 1)).sum() / (num_pos + B)                        # :256-259
+    n_norm = num_pos if normalizers is None else torch.tensor(float(normalizers[0]), dtype=td)
+    loss_cls = w_cls * (fl * wts.view(-1, 1)).sum() / (n_norm + B)                         # :256-259
 
     def decode(anc, tblr):                                                                 # tblr_bbox_coder.py:117-172
         loc = tblr * 0.125
@@ -337,14 +342,17 @@ def head_loss(cls_maps, bbox_maps, iou_maps, gt_bboxes_list, gt_labels_list, idx
         dt = decode(ancs[pos], tgs[pos])
         iou_tg = overlaps(dp, dt, "iou").detach()                                          # :267
         wq = iou_tg.clamp(min=1e-12) * pw                                                  # :272
-        loss_bbox = w_bbox * ((1 - overlaps(dp, dt, "giou")) * wq).sum() / wq.sum()        # :269-274
+        sum_wq = float(wq.sum())
+        q_norm = wq.sum() if normalizers is None else torch.tensor(float(normalizers[1]), dtype=td)
+        loss_bbox = w_bbox * ((1 - overlaps(dp, dt, "giou")) * wq).sum() / q_norm          # :269-274
         bce = F.binary_cross_entropy_with_logits(flat_iou[pos], iou_tg, reduction="none")
-        loss_iou = w_iou * (bce * pw).sum() / pw.sum()                                     # :275-278
+        loss_iou = w_iou * (bce * pw).sum() / (pw.sum() if normalizers is None else n_norm)   # :275-278
     else:
+        sum_wq = 0.0
         loss_bbox = flat_box[pos].sum()                                                    # :280-281
         loss_iou = flat_iou[pos].sum()
     out = dict(loss_cls=float(loss_cls.detach()), loss_bbox=float(loss_bbox.detach()), loss_iou=float(loss_iou.detach()),
-               num_pos=float(num_pos))
+               num_pos=float(num_pos), sum_wq=sum_wq)
     if need_grad:
         (loss_cls + loss_bbox + loss_iou).backward()
         z = lambda t: np.zeros(t.shape, np.dtype(dtype)) if t.grad is None else t.grad.numpy()

@@ -389,7 +389,8 @@ constexpr int kTmaThreads = kTmaWarps * 32;
 
 template <bool kGamma2>
 __global__ void __launch_bounds__(kTmaThreads, 8)
-loss_dense_tma_kernel(GridDev grid, TileTable tt, int B, int C, MapsDev maps, GradsDev grads,
+loss_dense_tma_kernel(GridDev grid, TileTable tt, int nch /* class chunks per tile */, int cc /* classes per chunk */, int B, int C,
+                      MapsDev maps, GradsDev grads,
                       const int* __restrict__ gt_offsets, const int64_t* __restrict__ gt_labels,
                       const int64_t* __restrict__ pidx, const float* __restrict__ pw, radet_loss_cfg_t cfg,
                       const float* __restrict__ grad_scale, LossWs* __restrict__ ws, double* __restrict__ partials,
@@ -408,7 +409,7 @@ loss_dense_tma_kernel(GridDev grid, TileTable tt, int B, int C, MapsDev maps, Gr
   __syncthreads();
   const int P = grid.off[grid.num_levels];
   const int tiles_per_image = tt.toff[grid.num_levels];
-  const int total_tiles = B * tiles_per_image;
+  const int total_items = B * tiles_per_image * nch;   // (tile, class chunk); small batches split the classes to fill the SMs
   const double num_pos = ws->norm[0], sum_wq = ws->norm[1];
   const bool has_pos = ws->norm[6] > 0.0;                                        // radet_head.py:261
   const float gs_cls = grad_scale ? grad_scale[0] : 1.f, gs_box = grad_scale ? grad_scale[1] : 1.f,
@@ -422,7 +423,9 @@ loss_dense_tma_kernel(GridDev grid, TileTable tt, int B, int C, MapsDev maps, Gr
   uint64_t* full = &s_full[wid][0];
   float lsum = 0.f;
   unsigned fills = 0;                                   // planes this warp has pushed through its ring so far
-  for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+  for (int it = blockIdx.x; it < total_items; it += gridDim.x) {
+    const int t = it / nch, ch = it - t * nch;
+    const int c0 = ch * cc, cn = min(cc, C - c0);                    // planes c0 .. c0 + cn - 1
     const int b = t / tiles_per_image, r = t - b * tiles_per_image;
     int l = 0;
 #pragma unroll
@@ -432,9 +435,9 @@ loss_dense_tma_kernel(GridDev grid, TileTable tt, int B, int C, MapsDev maps, Gr
     const int npts = min(128, hw - q_warp);                          // multiple of 4; <= 0: nothing for this warp
     if (npts <= 0) continue;                                          // warp-uniform
     const uint32_t bytes = (uint32_t)npts * 4u;
-    const float* src = maps.cls[l] + (int64_t)b * C * hw + q_warp;
+    const float* src = maps.cls[l] + ((int64_t)b * C + c0) * hw + q_warp;
     if (lane == 0) {                                                  // prologue: the first planes
-      const int n0 = min(kTmaStages, C);
+      const int n0 = min(kTmaStages, cn);
       for (int c = 0; c < n0; ++c) {
         const unsigned st = (fills + c) % kTmaStages;
         mbar_expect_tx(&full[st], bytes);
@@ -460,11 +463,11 @@ loss_dense_tma_kernel(GridDev grid, TileTable tt, int B, int C, MapsDev maps, Gr
     }
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
-      lab[i] = (int)label_of(idx[i], G, gt_labels + g0, C);
+      lab[i] = (int)label_of(idx[i], G, gt_labels + g0, C) - c0;      // relative to the chunk
       kw[i] = k_cls * w[i];
     }
-    float* dst = want_grad ? grads.cls[l] + (int64_t)b * C * hw + q0 : nullptr;
-    for (int c = 0; c < C; ++c, ++fills) {
+    float* dst = want_grad ? grads.cls[l] + ((int64_t)b * C + c0) * hw + q0 : nullptr;
+    for (int c = 0; c < cn; ++c, ++fills) {
       const unsigned st = fills % kTmaStages;
       mbar_wait(&full[st], (fills / kTmaStages) & 1u);
       float4 xv = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -482,13 +485,13 @@ loss_dense_tma_kernel(GridDev grid, TileTable tt, int B, int C, MapsDev maps, Gr
       // enough: neither a barrier nor an mbarrier arrive waits for a shared-memory read still in flight, and under
       // load (other kernels' CTAs on the SM) the bulk copy was observed to overwrite the stage before the read.
       __syncwarp();
-      if (lane == 0 && c + kTmaStages < C) {
+      if (lane == 0 && c + kTmaStages < cn) {
         mbar_expect_tx(&full[st], bytes);
         tma_bulk_g2s(ring + st * 128, src + (int64_t)(c + kTmaStages) * hw, bytes, &full[st]);
       }
     }
     // regression / IoU gradient planes: zero except at the positives parked by loss_pos_kernel (rescaled in place)
-    if (want_grad && active) {
+    if (want_grad && active && ch == 0) {
       const bool anypos = G > 0 && (idx[0] >= 0 || idx[1] >= 0 || idx[2] >= 0 || idx[3] >= 0);
 #pragma unroll
       for (int kk = 0; kk < 5; ++kk) {
@@ -704,7 +707,7 @@ static int dense_plan(const GridDev& g, int B, int C, DenseTable* tab, int* cc, 
 
 // Tiles of the TMA-pipelined dense kernel; false when some level is not 16-byte tileable (h*w % 4 != 0) or the
 // development override RADET_DENSE_IMPL=reg is set.
-static bool tile_plan(const GridDev& g, int B, TileTable* tt, int* blocks) {
+static bool tile_plan(const GridDev& g, int B, int C, TileTable* tt, int* nch, int* cc, int* blocks) {
   int t = 0;
   for (int l = 0; l < g.num_levels; ++l) {
     const int hw = g.h[l] * g.w[l];
@@ -716,9 +719,25 @@ static bool tile_plan(const GridDev& g, int B, TileTable* tt, int* blocks) {
   for (int l = g.num_levels; l <= RADET_MAX_LEVELS; ++l) tt->toff[l] = t;
   for (int l = g.num_levels; l < RADET_MAX_LEVELS; ++l) tt->tpl[l] = 0;
   const int64_t total = (int64_t)B * t;
-  if (total > (1ll << 30)) return false;
+  if (total * C > (1ll << 30)) return false;
   const int64_t slots = (int64_t)kSMs * 8;
-  *blocks = (int)(total < slots ? total : slots);
+  // Class chunks (RADET_DENSE_CTAS = target CTA count, development switch): a small batch has too few tiles to occupy
+  // the SMs and every warp then walks all C planes one after the other; splitting the classes over `nch` CTAs per
+  // tile shortens that chain (cfg2 alone: 22.3 -> 18.5 us at 3 chunks, 17.7 us at 5).  It is OFF by default: under the
+  // step scheduler the kernel shares the SMs with other steps, and the extra CTAs (each re-reading the
+  // tile's indices / weights) cost the neighbours more than the shorter chain gains (583 k -> 550 k / 524 k images/s).
+  int64_t want = 0;
+  if (const char* e = getenv("RADET_DENSE_CTAS")) {
+    const long v = atol(e);
+    if (v > 0) want = v;
+  }
+  int64_t n = total > 0 ? (want + total - 1) / total : 1;
+  if (n > (C + 1) / 2) n = (C + 1) / 2;             // at least two planes per chunk
+  if (n < 1) n = 1;
+  *cc = (int)((C + n - 1) / n);
+  *nch = (C + *cc - 1) / *cc;
+  const int64_t items = total * *nch;
+  *blocks = (int)(items < slots ? items : slots);
   return true;
 }
 
@@ -789,8 +808,8 @@ extern "C" int radet_loss_fwd_bwd(const radet_grid_t* grid, int32_t batch, int32
   // measurements behind that choice).
   const char* impl = getenv("RADET_LOSS_IMPL");
   TileTable tt;
-  int tma_blocks = 0;
-  const bool use_tma = tile_plan(g, batch, &tt, &tma_blocks);
+  int tma_blocks = 0, nch = 1, tcc = 1;
+  const bool use_tma = tile_plan(g, batch, num_classes, &tt, &nch, &tcc, &tma_blocks);
   if (use_tma && tma_blocks > dblk) dblk = tma_blocks;       // partial-sum slots (workspace_bytes sizes for the max)
   unsigned char* wsb = static_cast<unsigned char*>(workspace);
   LossWs* ws = reinterpret_cast<LossWs*>(wsb);
@@ -817,11 +836,11 @@ extern "C" int radet_loss_fwd_bwd(const radet_grid_t* grid, int32_t batch, int32
   if (!(phases & RADET_LOSS_PHASE_DENSE)) return RADET_OK;
   if (use_tma && !(impl && impl[0] == 'r')) {
     if (cfg->gamma == 2.0f)
-      loss_dense_tma_kernel<true><<<(unsigned)tma_blocks, kTmaThreads, 0, st>>>(g, tt, batch, num_classes, md, gd, gt_offsets, gt_labels,
+      loss_dense_tma_kernel<true><<<(unsigned)tma_blocks, kTmaThreads, 0, st>>>(g, tt, nch, tcc, batch, num_classes, md, gd, gt_offsets, gt_labels,
                                                                                   points_to_gt_index, points_weight, *cfg, grad_scale,
                                                                                   ws, dense_part, losses);
     else
-      loss_dense_tma_kernel<false><<<(unsigned)tma_blocks, kTmaThreads, 0, st>>>(g, tt, batch, num_classes, md, gd, gt_offsets, gt_labels,
+      loss_dense_tma_kernel<false><<<(unsigned)tma_blocks, kTmaThreads, 0, st>>>(g, tt, nch, tcc, batch, num_classes, md, gd, gt_offsets, gt_labels,
                                                                                    points_to_gt_index, points_weight, *cfg, grad_scale,
                                                                                    ws, dense_part, losses);
     RADET_LAUNCH_CHECK();

@@ -250,6 +250,27 @@ class RADetHead(nn.Module):
         sizes = [num_imgs * n for n in num_level_anchors]
         return list(lab.split(sizes)), list(tg.split(sizes)), list(wt.split(sizes)), list(anc.split(sizes))
 
+    # ------------------------------------------------------------------ single image / TTA surface
+    def _get_bboxes_single(self, cls_scores, bbox_preds, centernesses, mlvl_anchors, img_shape, scale_factor, cfg, rescale=False,
+                           with_nms=True):
+        """RADetHead._get_bboxes_single (radet_head.py:55-169) for ONE image: per-level maps [C,h,w] / [4,h,w] / [1,h,w].
+        `mlvl_anchors` is accepted for signature parity and ignored (the priors are closed-form in the kernels)."""
+        meta = dict(img_shape=tuple(img_shape), scale_factor=scale_factor)
+        return self.get_bboxes([t.unsqueeze(0) for t in cls_scores], [t.unsqueeze(0) for t in bbox_preds],
+                               [t.unsqueeze(0) for t in centernesses], [meta], cfg=cfg, rescale=rescale, with_nms=with_nms)[0]
+
+    def aug_test_bboxes(self, feats, img_metas, rescale=False):
+        """dense_test_mixins.py:38-97.  In the reference this path cannot run for RADetHead: its with_nms=False rows are
+        [n, 9] (box, score, prior; radet_head.py:165-169), while `merge_aug_bboxes` -> `bbox_mapping_back` views its input as
+        (-1, 4) boxes and `bbox_flip` asserts `shape[-1] % 4 == 0` (core/bbox/transforms.py:5-17,46-58).  The per-augmentation candidates are available from
+        `get_bboxes(..., with_nms=False)`; merging them is left to the caller."""
+        raise NotImplementedError("test-time augmentation is not functional for RADetHead in the reference either "
+                                  "(bbox_mapping_back rejects the [n,9] candidate rows); use get_bboxes(with_nms=False) per "
+                                  "augmentation and merge the rows yourself")
+
+    def aug_test(self, feats, img_metas, rescale=False):
+        return self.aug_test_bboxes(feats, img_metas, rescale=rescale)
+
     # ------------------------------------------------------------------ get_bboxes (atss_head.py:326-387, radet_head.py:55-169)
     def get_bboxes(self, cls_scores, bbox_preds, centernesses, img_metas, cfg=None, rescale=False, with_nms=True):
         cfg = self.test_cfg if cfg is None else cfg

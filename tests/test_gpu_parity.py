@@ -973,3 +973,84 @@ def test_loss_two_phase_normaliser_sync_path():
     out = head.loss(cls, bbox, iou, [T(b.gt_bboxes) for b in batch], [T(b.gt_labels) for b in batch], [T(i) for i in idx_l],
                     [T(x) for x in w_l], syn.img_metas(batch))
     assert abs(float(out["loss_cls"]) - float(l1[0])) <= 1e-7 * abs(float(l1[0]))
+
+
+@pytest.mark.gpu
+def test_forward_train_assigns_from_mask_grids():
+    """PackVisibleMaskGrid in the loader + RADetHead.forward_train on the trainer's GPU == the stock flow
+    (LabelAssignment in the worker with np.random.seed(seed) before each image, then RADetHead.loss)."""
+    wl, batch = hp.head_case("cfg1")
+    head = P.build_head(dict(type="RADetHead", num_classes=wl.C, in_channels=8, feat_channels=8, stacked_convs=1,
+                             norm_cfg=dict(type="GN", num_groups=4, requires_grad=True))).to(DEV)
+    head.init_weights()
+    shapes = GEOM.level_shapes(wl.H, wl.W)
+    g = torch.Generator(device=DEV).manual_seed(3)
+    feats = [torch.randn((len(batch), 8, h, w), device=DEV, generator=g) for h, w in shapes]
+    metas = syn.img_metas(batch)
+    pack = P.PackVisibleMaskGrid(seed_key="seed")
+    T = lambda a: torch.from_numpy(np.ascontiguousarray(a))
+    grids, seeds = [], []
+    for im in batch:                                   # what a DataLoader worker + DefaultFormatBundle hand over (CPU tensors)
+        r = pack(dict(img_shape=(im.H, im.W, 3), gt_bboxes=im.gt_bboxes, gt_labels=im.gt_labels, distance_maps=im.masks, seed=im.seed))
+        grids.append(T(r["points_to_gt_index"]))
+        seeds.append(T(r["points_weight"]))
+    gtb, gtl = [T(im.gt_bboxes).to(DEV) for im in batch], [T(im.gt_labels).to(DEV) for im in batch]
+    losses = head.forward_train(feats, metas, gtb, gtl, grids, seeds)
+    # the stock flow: assignment by the oracle (= the reference's LabelAssignment, tests/test_reference_live.py) seeded per image
+    a = [orc.assign_image_seeded(im.gt_bboxes, im.masks, im.H, im.W, im.seed) for im in batch]
+    want = head.forward_train(feats, metas, gtb, gtl, [T(x[0]).to(DEV) for x in a], [T(x[1]).to(DEV) for x in a])
+    for k in ("loss_cls", "loss_bbox", "loss_iou"):
+        assert torch.equal(losses[k], want[k]), k
+    (losses["loss_cls"] + losses["loss_bbox"] + losses["loss_iou"]).backward()
+    assert all(p.grad is not None and torch.isfinite(p.grad).all() for p in head.atss_cls.parameters())
+
+
+def _forked_label_assignment(q):
+    from radet_b200._lib import RadetError
+    la = P.LabelAssignment(anchor_generator_cfg=dict(type="AnchorGenerator", ratios=[1.0], octave_base_scale=8, scales_per_octave=1,
+                                                     strides=[8, 16, 32, 64, 128]), neg_threshold=0.2, balance_sample=True)
+    try:
+        la(dict(img_shape=(64, 64, 3), gt_bboxes=np.zeros((0, 4), np.float32), gt_labels=np.zeros(0, np.int64),
+                distance_maps=np.zeros((0, 64, 64), np.uint8)))
+        q.put("ran")
+    except RadetError as e:
+        q.put("refused: " + str(e)[:60])
+    except Exception as e:  # noqa: BLE001
+        q.put("other: " + repr(e)[:80])
+
+
+@pytest.mark.gpu
+def test_label_assignment_refuses_forked_dataloader_workers():
+    """mmcv's default DataLoader workers are forked from a process that already uses CUDA: the GPU pipeline step must say so
+    instead of dying in `Cannot re-initialize CUDA in forked subprocess`."""
+    import multiprocessing as mp
+    torch.zeros(1, device=DEV)                          # the parent has initialised CUDA
+    ctx = mp.get_context("fork")
+    q = ctx.Queue()
+    p = ctx.Process(target=_forked_label_assignment, args=(q,))
+    p.start()
+    msg = q.get(timeout=60)
+    p.join(timeout=30)
+    assert msg.startswith("refused: LabelAssignment.__call__ runs on the GPU"), msg
+
+
+@pytest.mark.gpu
+def test_head_loss_backward_is_reentrant():
+    """a second backward through the fused loss node (retain_graph) must not compound the upstream factor."""
+    wl, batch, idx_l, w_l, ho = _head_inputs("small")
+    cls, bbox, iou = _to_dev(ho)
+    for t in cls + bbox + iou:
+        t.requires_grad_()
+    counts, boxes, labels = _gt_dev(batch)
+    idx = torch.from_numpy(np.stack(idx_l)).to(DEV)
+    w = torch.from_numpy(np.stack(w_l)).to(DEV)
+    out, _ = F.head_loss(GEOM, wl.C, F.LossConfig(), cls, bbox, iou, counts, boxes, labels, idx, w)
+    total = 3.0 * out["loss_cls"] + 0.5 * out["loss_bbox"] + 2.0 * out["loss_iou"]
+    g1 = torch.autograd.grad(total, cls + bbox + iou, retain_graph=True)
+    g1 = [t.clone() for t in g1]
+    g2 = torch.autograd.grad(total, cls + bbox + iou, retain_graph=True)
+    for a, b in zip(g1, g2):
+        assert torch.allclose(a, b, rtol=1e-6, atol=0), "second backward returned differently scaled gradients"
+    g3 = torch.autograd.grad(2.0 * total, cls + bbox + iou)
+    for a, b in zip(g1, g3):
+        assert torch.allclose(2.0 * a, b, rtol=1e-6, atol=0)

@@ -139,3 +139,45 @@ def test_install_into_reference_registries():
         R_HEADS.register_module(name="RADetHead", force=True, module=ref_head)
         R_PIPELINES.register_module(name="LabelAssignment", force=True, module=RefLA)
         rops.vote_nms, rops.global_vote_nms, rops.cluster_nms = v0, g0, c0
+
+
+def test_pack_visible_mask_grid_is_cpu_only_and_collect_compatible():
+    """the worker-side step ships the stride-8 sample grid + a seed under the reference's own Collect keys."""
+    from radet_b200.plugin.pipelines import is_mask_grid_handoff
+
+    im = syn.make_batch(syn.WORKLOADS["cfg1"], 1)[0]
+    step = P.build_from_cfg(dict(type="PackVisibleMaskGrid"), P.PIPELINES)
+    np.random.seed(5)
+    res = step(dict(img_shape=(im.H, im.W, 3), gt_bboxes=im.gt_bboxes, gt_labels=im.gt_labels, distance_maps=im.masks))
+    np.random.seed(5)
+    want_seed = int(np.random.randint(0, 2 ** 31 - 1))                 # one legacy randint from the global generator
+    assert res["points_to_gt_index"].dtype == np.uint8 and res["points_to_gt_index"].shape == (im.gt_bboxes.shape[0], 60, 80)
+    assert np.array_equal(res["points_to_gt_index"], im.masks[:, ::8, ::8])
+    assert res["points_weight"].dtype == np.int64 and res["points_weight"].tolist() == [want_seed]
+    # after DefaultFormatBundle's to_tensor (formating.py:218-223) the head recognises the hand-off
+    as_tensors = [torch.from_numpy(res["points_to_gt_index"])]
+    assert is_mask_grid_handoff(as_tensors) and not is_mask_grid_handoff([torch.zeros(6400, dtype=torch.int64)])
+    assert not is_mask_grid_handoff(None)
+    # an explicit per-image seed from the results dict; empty images; graded maps are refused
+    res = P.PackVisibleMaskGrid(seed_key="assign_seed")(dict(img_shape=(im.H, im.W, 3), gt_bboxes=np.zeros((0, 4), np.float32),
+                                                             distance_maps=np.zeros((0, im.H, im.W), np.uint8), assign_seed=123))
+    assert res["points_to_gt_index"].shape == (0, 60, 80) and res["points_weight"].tolist() == [123]
+    graded = im.masks.copy()
+    graded[0][graded[0] > 0] = 1
+    graded[0, :, : im.W // 2][graded[0, :, : im.W // 2] > 0] = 2
+    if (graded[0, ::8, ::8] == 1).any() and (graded[0, ::8, ::8] == 2).any():
+        with pytest.raises(NotImplementedError, match="graded"):
+            step(dict(img_shape=(im.H, im.W, 3), gt_bboxes=im.gt_bboxes, gt_labels=im.gt_labels, distance_maps=graded))
+    with pytest.raises(NotImplementedError):
+        P.build_from_cfg(dict(ASSIGN_CFG, neg_threshold=0.0), P.PIPELINES)      # reference semantics at 0 differ (ADVICE r1)
+
+
+def test_head_refuses_training_without_an_assignment():
+    head = P.build_head(HEAD_CFG)
+    assert head.label_assignment_cfg == dict(positive_num=10, neg_threshold=0.2, adapt_positive_num=False, balance_sample=True)
+    la = head.assigner()
+    assert isinstance(la, P.LabelAssignment) and la.positive_num == 10 and la.balance_sample
+    with pytest.raises(Exception, match="points_to_gt_index"):
+        head.forward_train([torch.zeros(1, 8, 4, 4)] * 5, [dict(img_shape=(32, 32, 3))], [torch.zeros(0, 4)], [torch.zeros(0)])
+    with pytest.raises(NotImplementedError, match="test-time augmentation"):
+        head.aug_test([], [])

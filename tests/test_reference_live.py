@@ -201,3 +201,30 @@ def test_get_targets_live(shim):
             assert np.array_equal(lab[l].numpy(), olab[l]), (wl.name, l)
             assert np.array_equal(tg[l].numpy().view(np.uint32), otg[l].view(np.uint32)), (wl.name, l)
             assert np.array_equal(wt[l].numpy(), owt[l]) and np.array_equal(anc[l].numpy(), oanc[l])
+
+
+def test_mask_grid_handoff_equals_the_stock_pipeline(shim):
+    """`PackVisibleMaskGrid` (CPU, in the worker) ships exactly the pixels the reference's LabelAssignment reads,
+    in a form the reference's own formatting code accepts; the assignment computed from (grid, seed) equals what the
+    UNMODIFIED reference step returns when `np.random.seed(seed)` precedes it."""
+    import torch
+    from radet.datasets.pipelines.formating import to_tensor
+
+    from radet_b200 import plugin as P
+    from radet_b200.plugin.pipelines import is_mask_grid_handoff
+
+    la = shim.build_reference_assigner()
+    pack = P.PackVisibleMaskGrid(seed_key="seed")
+    rs = np.random.RandomState(99)
+    for i in range(6):
+        wl = _random_workload(rs, 300 + i)
+        for im in syn.make_batch(wl):
+            r = pack(dict(img_shape=(im.H, im.W, 3), gt_bboxes=im.gt_bboxes, gt_labels=im.gt_labels,
+                          distance_maps=shim.BitmapMasksStandIn(im.masks), seed=im.seed))
+            grid_t, seed_t = to_tensor(r["points_to_gt_index"]), to_tensor(r["points_weight"])      # DefaultFormatBundle, formating.py:218-223
+            assert grid_t.dtype == torch.uint8 and seed_t.dtype == torch.int64 and is_mask_grid_handoff([grid_t])
+            np.random.seed(int(seed_t[0]))
+            ref = la(dict(img_shape=(im.H, im.W, 3), gt_bboxes=im.gt_bboxes, gt_labels=im.gt_labels,
+                          distance_maps=shim.BitmapMasksStandIn(im.masks)))
+            idx, w, _ = orc.assign_image_seeded(im.gt_bboxes, grid_t.numpy(), im.H, im.W, int(seed_t[0]), grid_step=8)
+            assert np.array_equal(idx, ref["points_to_gt_index"]) and np.array_equal(w, ref["points_weight"]), wl.name
