@@ -419,8 +419,8 @@ loss_dense_tma_kernel(GridDev grid, TileTable tt, int nch /* class chunks per ti
   const float k_iou = has_pos ? gs_iou * cfg.w_iou / (float)num_pos : gs_iou;
   const bool want_grad = grads.cls[0] != nullptr;
   const float gamma = cfg.gamma, alpha = cfg.alpha;
-  float* ring = &s_ring[wid][0][0];
-  uint64_t* full = &s_full[wid][0];
+  const float* ring = &s_ring[wid][0][0];
+  const uint32_t ring_s = smem_u32(ring), full_s = smem_u32(&s_full[wid][0]);   // shared-window addresses, computed once
   float lsum = 0.f;
   unsigned fills = 0;                                   // planes this warp has pushed through its ring so far
   for (int it = blockIdx.x; it < total_items; it += gridDim.x) {
@@ -435,13 +435,14 @@ loss_dense_tma_kernel(GridDev grid, TileTable tt, int nch /* class chunks per ti
     const int npts = min(128, hw - q_warp);                          // multiple of 4; <= 0: nothing for this warp
     if (npts <= 0) continue;                                          // warp-uniform
     const uint32_t bytes = (uint32_t)npts * 4u;
-    const float* src = maps.cls[l] + ((int64_t)b * C + c0) * hw + q_warp;
+    const float* nsrc = maps.cls[l] + ((int64_t)b * C + c0) * hw + q_warp;   // lane 0: next plane to request
+    int issued = 0;
     if (lane == 0) {                                                  // prologue: the first planes
       const int n0 = min(kTmaStages, cn);
-      for (int c = 0; c < n0; ++c) {
-        const unsigned st = (fills + c) % kTmaStages;
-        mbar_expect_tx(&full[st], bytes);
-        tma_bulk_g2s(ring + st * 128, src + (int64_t)c * hw, bytes, &full[st]);
+      for (; issued < n0; ++issued, nsrc += hw) {
+        const unsigned st = (fills + issued) % kTmaStages;
+        mbar_expect_tx_s(full_s + st * 8u, bytes);
+        tma_bulk_g2s_s(ring_s + st * 512u, nsrc, bytes, full_s + st * 8u);
       }
     }
     // per-lane setup for its 4 points (index -> label, weight) while the ring fills
@@ -450,44 +451,51 @@ loss_dense_tma_kernel(GridDev grid, TileTable tt, int nch /* class chunks per ti
     const int g0 = gt_offsets[b], G = gt_offsets[b + 1] - g0;
     const int64_t pbase = (int64_t)b * P + grid.off[l] + q0;
     int idx[4], lab[4];
-    float w[4], kw[4];
+    float wt[4], wn[4];                                              // alpha w and (1 - alpha) w of the four points
+    {
+      longlong2 a01 = make_longlong2(-1, -1), a23 = make_longlong2(-1, -1);
+      float4 wv = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (active) {                                                   // P and every level size are multiples of 4: aligned vectors
+        a01 = *reinterpret_cast<const longlong2*>(pidx + pbase);
+        a23 = *reinterpret_cast<const longlong2*>(pidx + pbase + 2);
+        wv = *reinterpret_cast<const float4*>(pw + pbase);
+      }
+      const int64_t v[4] = {a01.x, a01.y, a23.x, a23.y};
+      const float w[4] = {wv.x, wv.y, wv.z, wv.w};
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      idx[i] = -1;
-      w[i] = 0.f;
-      if (active) {
-        const int64_t v = pidx[pbase + i];
-        idx[i] = v < 0 ? -1 : (int)(v > (int64_t)G ? (int64_t)G : v);
-        w[i] = pw[pbase + i];
+      for (int i = 0; i < 4; ++i) {
+        idx[i] = v[i] < 0 ? -1 : (int)(v[i] > (int64_t)G ? (int64_t)G : v[i]);
+        lab[i] = (int)label_of(idx[i], G, gt_labels + g0, C) - c0;    // relative to the chunk
+        wt[i] = alpha * w[i];
+        wn[i] = (1.f - alpha) * w[i];
       }
     }
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      lab[i] = (int)label_of(idx[i], G, gt_labels + g0, C) - c0;      // relative to the chunk
-      kw[i] = k_cls * w[i];
-    }
-    float* dst = want_grad ? grads.cls[l] + ((int64_t)b * C + c0) * hw + q0 : nullptr;
+    float* dst = want_grad ? grads.cls[l] + ((int64_t)b * C + c0) * hw + q0 : nullptr;   // next plane to store
+    const float* rp0 = ring + 4 * lane;
     for (int c = 0; c < cn; ++c, ++fills) {
       const unsigned st = fills % kTmaStages;
-      mbar_wait(&full[st], (fills / kTmaStages) & 1u);
-      float4 xv = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (active) xv = *reinterpret_cast<const float4*>(ring + st * 128 + 4 * lane);
+      mbar_wait_s(full_s + st * 8u, (fills / kTmaStages) & 1u);
       if (active) {
-        float lo_, gr_;
+        const float4 xv = *reinterpret_cast<const float4*>(rp0 + st * 128);
         float4 gv;
-        focal_elem<kGamma2>(xv.x, lab[0] == c, gamma, alpha, lo_, gr_); lsum = fmaf(w[0], lo_, lsum); gv.x = kw[0] * gr_;
-        focal_elem<kGamma2>(xv.y, lab[1] == c, gamma, alpha, lo_, gr_); lsum = fmaf(w[1], lo_, lsum); gv.y = kw[1] * gr_;
-        focal_elem<kGamma2>(xv.z, lab[2] == c, gamma, alpha, lo_, gr_); lsum = fmaf(w[2], lo_, lsum); gv.z = kw[2] * gr_;
-        focal_elem<kGamma2>(xv.w, lab[3] == c, gamma, alpha, lo_, gr_); lsum = fmaf(w[3], lo_, lsum); gv.w = kw[3] * gr_;
-        if (dst) stg_stream4(dst + (int64_t)c * hw, gv);
+        gv.x = focal_acc<kGamma2>(xv.x, lab[0] == c, wt[0], wn[0], k_cls, gamma, lsum);
+        gv.y = focal_acc<kGamma2>(xv.y, lab[1] == c, wt[1], wn[1], k_cls, gamma, lsum);
+        gv.z = focal_acc<kGamma2>(xv.z, lab[2] == c, wt[2], wn[2], k_cls, gamma, lsum);
+        gv.w = focal_acc<kGamma2>(xv.w, lab[3] == c, wt[3], wn[3], k_cls, gamma, lsum);
+        if (dst) {
+          stg_stream4(dst, gv);
+          dst += hw;
+        }
       }
       // Refill the stage only AFTER the values have been consumed.  Issuing the copy right behind the LDS is not
       // enough: neither a barrier nor an mbarrier arrive waits for a shared-memory read still in flight, and under
       // load (other kernels' CTAs on the SM) the bulk copy was observed to overwrite the stage before the read.
       __syncwarp();
-      if (lane == 0 && c + kTmaStages < cn) {
-        mbar_expect_tx(&full[st], bytes);
-        tma_bulk_g2s(ring + st * 128, src + (int64_t)(c + kTmaStages) * hw, bytes, &full[st]);
+      if (lane == 0 && issued < cn) {
+        mbar_expect_tx_s(full_s + st * 8u, bytes);
+        tma_bulk_g2s_s(ring_s + st * 512u, nsrc, bytes, full_s + st * 8u);
+        nsrc += hw;
+        ++issued;
       }
     }
     // regression / IoU gradient planes: zero except at the positives parked by loss_pos_kernel (rescaled in place)
@@ -707,7 +715,8 @@ static int dense_plan(const GridDev& g, int B, int C, DenseTable* tab, int* cc, 
 
 // Tiles of the TMA-pipelined dense kernel; false when some level is not 16-byte tileable (h*w % 4 != 0) or the
 // development override RADET_DENSE_IMPL=reg is set.
-static bool tile_plan(const GridDev& g, int B, int C, TileTable* tt, int* nch, int* cc, int* blocks) {
+static bool tile_plan(const GridDev& g, int B, int C, const void* pidx, const void* pw, TileTable* tt, int* nch, int* cc, int* blocks) {
+  if ((reinterpret_cast<uintptr_t>(pidx) | reinterpret_cast<uintptr_t>(pw)) & 15) return false;   // 128-bit index / weight loads
   int t = 0;
   for (int l = 0; l < g.num_levels; ++l) {
     const int hw = g.h[l] * g.w[l];
@@ -809,7 +818,7 @@ extern "C" int radet_loss_fwd_bwd(const radet_grid_t* grid, int32_t batch, int32
   const char* impl = getenv("RADET_LOSS_IMPL");
   TileTable tt;
   int tma_blocks = 0, nch = 1, tcc = 1;
-  const bool use_tma = tile_plan(g, batch, num_classes, &tt, &nch, &tcc, &tma_blocks);
+  const bool use_tma = tile_plan(g, batch, num_classes, points_to_gt_index, points_weight, &tt, &nch, &tcc, &tma_blocks);
   if (use_tma && tma_blocks > dblk) dblk = tma_blocks;       // partial-sum slots (workspace_bytes sizes for the max)
   unsigned char* wsb = static_cast<unsigned char*>(workspace);
   LossWs* ws = reinterpret_cast<LossWs*>(wsb);
@@ -820,6 +829,16 @@ extern "C" int radet_loss_fwd_bwd(const radet_grid_t* grid, int32_t batch, int32
   double* pos_part = reinterpret_cast<double*>(wsb + off_pos);
   double* dense_part = reinterpret_cast<double*>(wsb + off_dense);
   cudaStream_t st = (cudaStream_t)stream;
+  const bool hybrid = impl && impl[0] == 'h';   // "hybrid": loss_pos_kernel, then the ticketed streaming kernel for the dense pass
+  if (hybrid && phases == RADET_LOSS_PHASE_ALL) {
+    loss_pos_kernel<<<(unsigned)pos_blocks, kPosThreads, 0, st>>>(g, batch, md, gt_offsets, gt_bboxes, points_to_gt_index,
+                                                                  points_weight, *cfg, ws, pos_part, gd);
+    RADET_LAUNCH_CHECK();
+    rc = launch_loss_fused(g, batch, num_classes, md, gd, gt_offsets, gt_bboxes, gt_labels, points_to_gt_index, points_weight, *cfg,
+                           grad_scale, ws, wsb + off_fused, false, true, losses, nullptr, st);
+    if (rc != RADET_E_UNSUPPORTED) return rc;
+    phases = RADET_LOSS_PHASE_DENSE;
+  }
   if (impl && impl[0] == 'f') {
     // single launch: normalisers, positive terms, dense pass and the three losses (or only one of the two phases).
     // Shapes it does not take (a plane size that is not a multiple of 4, unaligned index / weight arrays) fall through.

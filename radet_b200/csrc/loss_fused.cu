@@ -85,29 +85,6 @@ __device__ __forceinline__ void wait_flag(const unsigned* flag) {
 __device__ __forceinline__ void st_relaxed_u32(unsigned* p, unsigned v) {   // after a __threadfence(): fence + relaxed store = release
   asm volatile("st.relaxed.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
-// shared-memory mbarrier / bulk-copy helpers on precomputed 32-bit shared addresses (no cvta in the loop)
-__device__ __forceinline__ void mbar_expect_tx_s(uint32_t bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void tma_bulk_g2s_s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
-  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src),
-               "r"(bytes), "r"(bar)
-               : "memory");
-}
-__device__ __forceinline__ void mbar_wait_s(uint32_t bar, uint32_t phase) {
-  asm volatile(
-      "{\n"
-      ".reg .pred p;\n"
-      "WAIT_%=:\n"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
-      "@p bra DONE_%=;\n"
-      "bra WAIT_%=;\n"
-      "DONE_%=:\n"
-      "}\n" ::"r"(bar),
-      "r"(phase)
-      : "memory");
-}
-
 // Fixed-order partial sum of p[first], p[first + stride], ...: up to 16 loads are issued before the first addition
 // (one L2 round trip for the usual few hundred to few thousand partial sums); the combination order is fixed, so the
 // value depends only on (n, first, stride).
@@ -129,23 +106,6 @@ __device__ __forceinline__ double strided_sum(const double* p, unsigned n, unsig
 // ... by one warp (lane-strided, then an xor tree): the same result whichever warp evaluates it
 __device__ __forceinline__ double warp_sum_array(const double* p, unsigned n, int lane) {
   return warp_sum(strided_sum(p, n, (unsigned)lane, 32u));
-}
-
-// Sigmoid focal loss of one logit, accumulated, and its gradient (see focal_elem in loss_common.cuh for the derivation).
-// wt = alpha * w, wn = (1 - alpha) * w of the point; the sign that the target class puts on the gradient travels in A.
-template <bool kGamma2>
-__device__ __forceinline__ float focal_acc(float x, bool is_t, float wt, float wn, float k_cls, float gamma, float& lsum) {
-  const float z = is_t ? -x : x;
-  const float wl = is_t ? -wt : wn;
-  const float e = ex2_approx(fabsf(z) * -1.4426950408889634f);   // exp(-|z|) in (0, 1]
-  const float inv = rcp_approx(1.0f + e);                         // 1/(1+e) in [0.5, 1)
-  const float sp = fmaf(-0.6931471805599453f, lg2_approx(inv), fmaxf(z, 0.f));   // softplus(z)
-  const float s = z >= 0.f ? inv : e * inv;                       // sigmoid(z)
-  const float u = kGamma2 ? s * s : ex2_approx(gamma * -1.4426950408889634f * (sp - z));   // s^gamma
-  const float A = wl * u;
-  lsum = fmaf(fabsf(A), sp, lsum);
-  const float h = fmaf(kGamma2 ? fmaf(-2.f, s, 2.f) : gamma * (1.f - s), sp, s);
-  return (A * h) * k_cls;
 }
 
 template <bool kGamma2, int CG, int D>
