@@ -693,9 +693,11 @@ def main():
     peak_gbs = float(peaks.get("hbm_gbs", 6650.0))
     peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650 GB/s"
     traffic = None   # dram bytes per launch of the same kernel from the committed `ncu --set full` capture, if it matches this shape
-    tj = os.path.join(ROOT, "profiles", "r1_traffic.json")
-    if os.path.exists(tj) and wl.name.startswith("cfg2") and B == 8:
-        traffic = json.load(open(tj)).get("loss_dense_kernel@cfg2_B8")
+    for tj in ("r2_traffic.json", "r1_traffic.json"):
+        tj = os.path.join(ROOT, "profiles", tj)
+        if os.path.exists(tj) and wl.name.startswith("cfg2") and B == 8:
+            traffic = json.load(open(tj)).get("loss_dense_kernel@cfg2_B8")
+            break
     loss_bytes = B * Ppts * (8 * wl.C + 52)
     ach = loss_bytes / (stage_us["loss_dense_kernel"] * 1e-6) / 1e9
     roofline = {"bound": "hbm", "kernel": "loss_dense_kernel", "achieved": ach, "peak": peak_gbs, "unit": "GB/s", "frac": ach / peak_gbs,
