@@ -141,6 +141,14 @@ int radet_assign(const radet_grid_t* grid, int32_t batch, const int32_t* gt_offs
                  int32_t* consumed, double* weight_sums, void* workspace, size_t workspace_bytes, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
+ * AnchorGenerator.grid_anchors / valid_flags for ONE image (core/anchor/anchor_generator.py:206-271, 273-298;
+ * ratios=[1], one square prior of side anchor_scale * stride centred on (x*s, y*s) per cell).  The kernels of the hot
+ * path compute priors in closed form; this entry serves AnchorHead.get_anchors (anchor_head.py:142-170).
+ *   anchors     f32 [P,4]   optional   x1,y1,x2,y2, level-major / row-major
+ *   valid_flags u8  [P]     optional   1 for cells inside ceil(pad_h / stride) x ceil(pad_w / stride) */
+int radet_grid_priors(const radet_grid_t* grid, int32_t pad_h, int32_t pad_w, float* anchors, uint8_t* valid_flags, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
  * Target gather + TBLR encode.  Replaces RADetHead.get_targets / _get_target_single
  * (models/dense_heads/radet_head.py:290-369, 373-392) and TBLRBBoxCoder.encode
  * (core/bbox/coder/tblr_bbox_coder.py:29-46, 71-114): target = (distance / prior side) / normalizer.

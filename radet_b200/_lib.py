@@ -54,6 +54,7 @@ _SIGS = {
     "radet_assign": (c_int32, [POINTER(Grid), c_int32, c_void_p, POINTER(c_int32), c_void_p, c_void_p, c_int32, c_int32, c_int32,
                                c_void_p, c_int32, c_void_p, c_void_p, c_int32, c_int32, c_void_p, c_void_p, c_void_p,
                                c_void_p, c_void_p, c_size_t, c_void_p]),
+    "radet_grid_priors": (c_int32, [POINTER(Grid), c_int32, c_int32, c_void_p, c_void_p, c_void_p]),
     "radet_get_targets": (c_int32, [POINTER(Grid), c_int32, c_int32, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                                     c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     "radet_loss_workspace_bytes": (c_size_t, [POINTER(Grid), c_int32, c_int32]),

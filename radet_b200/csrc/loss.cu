@@ -21,6 +21,27 @@
 namespace radet {
 
 // ------------------------------------------------------------------------------------------------ targets
+// AnchorGenerator.grid_anchors / valid_flags (anchor_generator.py:206-298) for one image: priors [P,4] and, optionally, the
+// flags of the cells inside ceil(pad_shape / stride).  The hot path never materialises them; this serves get_anchors().
+__global__ void grid_priors_kernel(GridDev grid, int pad_h, int pad_w, float4* __restrict__ anchors, uint8_t* __restrict__ flags) {
+  const int P = grid.off[grid.num_levels];
+  const int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= P) return;
+  const int l = level_of(grid, p);
+  const int q = p - grid.off[l];
+  const int y = q / grid.w[l], x = q - y * grid.w[l];
+  const int s = grid.stride[l];
+  if (anchors) {
+    const float cx = (float)(x * s), cy = (float)(y * s);
+    const float half = 0.5f * (grid.anchor_scale * (float)s);
+    anchors[p] = make_float4(cx - half, cy - half, cx + half, cy + half);
+  }
+  if (flags) {
+    const int vh = min((pad_h + s - 1) / s, grid.h[l]), vw = min((pad_w + s - 1) / s, grid.w[l]);
+    flags[p] = (y < vh && x < vw) ? 1 : 0;
+  }
+}
+
 __global__ void get_targets_kernel(GridDev grid, int B, int C, const int* __restrict__ gt_offsets,
                                    const float* __restrict__ gt_bboxes, const int64_t* __restrict__ gt_labels,
                                    const int64_t* __restrict__ pidx, const float* __restrict__ pw,
@@ -669,6 +690,19 @@ extern "C" int radet_get_targets(const radet_grid_t* grid, int32_t batch, int32_
   get_targets_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
       g, batch, num_classes, gt_offsets, gt_bboxes, gt_labels, points_to_gt_index, points_weight, labels,
       reinterpret_cast<float4*>(bbox_targets), weights, reinterpret_cast<float4*>(anchors));
+  RADET_LAUNCH_CHECK();
+  return RADET_OK;
+}
+
+extern "C" int radet_grid_priors(const radet_grid_t* grid, int32_t pad_h, int32_t pad_w, float* anchors, uint8_t* valid_flags,
+                                 void* stream) {
+  GridDev g;
+  int rc = make_grid_dev(grid, &g);
+  if (rc != RADET_OK) return rc;
+  if (!anchors && !valid_flags) return RADET_E_BADARG;
+  if (valid_flags && (pad_h <= 0 || pad_w <= 0)) return RADET_E_BADARG;
+  const int P = g.off[g.num_levels];
+  grid_priors_kernel<<<(P + 255) / 256, 256, 0, (cudaStream_t)stream>>>(g, pad_h, pad_w, reinterpret_cast<float4*>(anchors), valid_flags);
   RADET_LAUNCH_CHECK();
   return RADET_OK;
 }

@@ -156,6 +156,28 @@ def assign(geom: Geometry, level_shapes, gt_counts: Sequence[int], gt_bboxes: to
     return idx, w, consumed
 
 
+# ------------------------------------------------------------------------------------------------ priors
+def grid_priors(geom: Geometry, level_shapes, device, pad_shape=None, want_anchors=True):
+    """AnchorGenerator.grid_anchors / valid_flags of one image on the device: (anchors f32 [P,4] or None, flags u8 [P] or None)."""
+    device = torch.device(device)
+    if device.type != "cuda":
+        raise RadetError("grid_priors runs on a CUDA device (radet_b200 has no CPU path)")
+    grid = geom.grid(level_shapes)
+    P = geom.num_points(level_shapes)
+    with torch.cuda.device(device):
+        anc = torch.empty((P, 4), dtype=torch.float32, device=device) if want_anchors else None
+        flg = torch.empty((P,), dtype=torch.uint8, device=device) if pad_shape is not None else None
+        ph, pw_ = (int(pad_shape[0]), int(pad_shape[1])) if pad_shape is not None else (0, 0)
+        check(_lib.load().radet_grid_priors(ctypes.byref(grid), ph, pw_, _ptr(anc), _ptr(flg), _stream()), "radet_grid_priors")
+    return anc, flg
+
+
+def release_workspaces():
+    """Drop the cached per-(configuration, stream) workspaces (they are kept for the life of the process otherwise: a stream
+    that goes away leaves its scratch behind)."""
+    _WS.clear()
+
+
 # ------------------------------------------------------------------------------------------------ targets
 def get_targets(geom: Geometry, level_shapes, num_classes: int, gt_counts, gt_bboxes, gt_labels, idx, w,
                 with_anchors=True, gt_offsets=None):

@@ -67,12 +67,22 @@ class AnchorGenerator:
     def num_levels(self):
         return len(self.strides)
 
+    def _geometry(self):
+        from .. import functional as F
+        return F.Geometry(strides=[sw for sw, _ in self.strides], regress_ranges=[(0.0, 0.0)] * len(self.strides),
+                          anchor_scale=self.anchor_scale)
+
     def grid_anchors(self, featmap_sizes, device='cuda'):
-        """anchor_generator.py:206-271 (host arithmetic on small integers: exact; returned on `device`)."""
+        """anchor_generator.py:206-271.  On a CUDA device: one launch of `radet_grid_priors`; a CPU device is only served for
+        the docstring KAT / host-side shape checks (small-integer arithmetic, exact either way)."""
         assert self.num_levels == len(featmap_sizes)
+        sizes = [(int(h), int(w)) for h, w in featmap_sizes]
+        if torch.device(device).type == 'cuda':
+            from .. import functional as F
+            flat = F.grid_priors(self._geometry(), sizes, torch.device(device))[0]
+            return list(flat.split([h * w for h, w in sizes]))
         out = []
-        for (h, w), (s, _) in zip(featmap_sizes, self.strides):
-            h, w = int(h), int(w)
+        for (h, w), (s, _) in zip(sizes, self.strides):
             xs = np.tile(np.arange(w, dtype=np.float32) * s, h)
             ys = np.repeat(np.arange(h, dtype=np.float32) * s, w)
             half = np.float32(0.5 * self.anchor_scale * s)
@@ -82,8 +92,13 @@ class AnchorGenerator:
 
     def valid_flags(self, featmap_sizes, pad_shape, device='cuda'):
         """anchor_generator.py:273-298."""
+        sizes = [(int(h), int(w)) for h, w in featmap_sizes]
+        if torch.device(device).type == 'cuda':
+            from .. import functional as F
+            flags = F.grid_priors(self._geometry(), sizes, torch.device(device), pad_shape=pad_shape[:2], want_anchors=False)[1]
+            return list(flags.bool().split([h * w for h, w in sizes]))
         flags = []
-        for (fh, fw), (sw, sh) in zip(featmap_sizes, self.strides):
+        for (fh, fw), (sw, sh) in zip(sizes, self.strides):
             h, w = pad_shape[:2]
             vh, vw = min(int(np.ceil(h / sh)), int(fh)), min(int(np.ceil(w / sw)), int(fw))
             f = np.zeros((int(fh), int(fw)), bool)

@@ -1054,3 +1054,19 @@ def test_head_loss_backward_is_reentrant():
     g3 = torch.autograd.grad(2.0 * total, cls + bbox + iou)
     for a, b in zip(g1, g3):
         assert torch.allclose(2.0 * a, b, rtol=1e-6, atol=0)
+
+
+@pytest.mark.gpu
+def test_grid_priors_on_the_device():
+    """AnchorGenerator.grid_anchors / valid_flags (anchor_generator.py:206-298) through radet_grid_priors == the oracle's priors."""
+    ag = P.build_anchor_generator(dict(type="AnchorGenerator", ratios=[1.0], octave_base_scale=8, scales_per_octave=1,
+                                       strides=[8, 16, 32, 64, 128]))
+    for H, W in ((480, 640), (100, 100), (333, 500)):
+        sizes = GEOM.level_shapes(H, W)
+        anc = ag.grid_anchors(sizes, device=DEV)
+        want = orc.grid_anchors(H, W)
+        assert len(anc) == 5 and all(a.is_cuda for a in anc)
+        assert np.array_equal(torch.cat(anc).cpu().numpy(), want)
+        flags = ag.valid_flags(sizes, (H - 40, W - 90, 3), device=DEV)
+        ref = ag.valid_flags(sizes, (H - 40, W - 90, 3), device="cpu")
+        assert all(torch.equal(f.cpu(), r) for f, r in zip(flags, ref))
