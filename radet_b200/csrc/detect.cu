@@ -237,6 +237,31 @@ detect_bin_kernel(BinParams p) {
   u64 kth = 0ull;
   if (p.nms_pre > 0 && nl > p.nms_pre) kth = radix_select_kth(src, nl, p.nms_pre, s_hist, s_misc);  // radet_head.py:112-122
   const int hw = g.h[l] * g.w[l];
+  // Class binning.  A global atomic with a return value per candidate is a ~1 us round trip on every thread's serial
+  // path (10 candidates per thread on the finest level); instead the CTA counts its candidates per class in shared
+  // memory, reserves one range per class with ONE global atomic each, and hands out the slots from shared memory.
+  // (The order inside a bin is irrelevant: class_nms_kernel sorts by key.)
+  constexpr int kBinClasses = 1024;
+  __shared__ int s_ccnt[kBinClasses], s_cbase[kBinClasses];
+  const bool local = p.C <= kBinClasses;
+  if (local) {
+    for (int c = tid; c < p.C; c += kBinThreads) s_ccnt[c] = 0;
+    __syncthreads();
+    for (int i = tid; i < nl; i += kBinThreads) {
+      const u64 key = src[i];
+      if (key < kth) continue;
+      const unsigned flat = 0xffffffffu - (unsigned)(key & 0xffffffffull);
+      atomicAdd(&s_ccnt[flat % (unsigned)p.C], 1);
+    }
+    __syncthreads();
+    for (int c = tid; c < p.C; c += kBinThreads) {
+      const int n = s_ccnt[c];
+      s_cbase[c] = n ? atomicAdd(&p.class_counts[b * p.C + c], n) : 0;
+      s_ccnt[c] = 0;
+    }
+    __syncthreads();
+  }
+#pragma unroll 4
   for (int i = tid; i < nl; i += kBinThreads) {
     const u64 key = src[i];
     if (key < kth) continue;
@@ -250,7 +275,7 @@ detect_bin_kernel(BinParams p) {
       cs = p.cs_mode == 0 ? __fmul_rn(S, ctr) : ctr;                            // vote_wrapper.py:14-21
     }
     const unsigned ord = ((unsigned)l << kOrdLevelShift) | flat;
-    const int slot = atomicAdd(&p.class_counts[b * p.C + c], 1);
+    const int slot = local ? s_cbase[c] + atomicAdd(&s_ccnt[c], 1) : atomicAdd(&p.class_counts[b * p.C + c], 1);
     if (slot < p.class_cap)
       p.bins[((int64_t)b * p.C + c) * p.class_cap + slot] = ((u64)float_order_key(cs) << 32) | (u64)(0xffffffffu - ord);
   }
