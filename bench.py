@@ -52,6 +52,7 @@ def parse():
     ap.add_argument("--stages", default="assign,loss,detect", help="development aid: run only these stages of the step")
     ap.add_argument("--inflight", type=int, default=8, help="steps in flight: every lane (stream) replays graphs of consecutive steps, "
                     "the assignment running this many batches ahead (1 = one step at a time)")
+    ap.add_argument("--no-weight-sums", action="store_true", help="do not hand the assignment's per-image weight sums to the loss (classic kernel order)")
     ap.add_argument("--no-gate", action="store_true", help="do not hold the timed block behind a device-side gate")
     ap.add_argument("--no-side-configs", action="store_true", help="skip the cfg3/cfg4/cfg5 side measurements")
     ap.add_argument("--no-prefetch", action="store_true", help="assignment and loss of the same batch in sequence (no one-batch-ahead assignment)")
@@ -352,16 +353,20 @@ def main():
     for s in sets:   # assignment buffers of every input set (double-buffered hand-off, see step())
         s["abuf"] = (torch.empty((B, Ppts), dtype=torch.int64, device=dev), torch.empty((B, Ppts), dtype=torch.float32, device=dev),
                      torch.empty((B,), dtype=torch.int32, device=dev))
+        s["wsum"] = torch.zeros((B,), dtype=torch.float64, device=dev)   # per-image weight sums, handed to the loss with idx / w
 
     def do_assign(s, out=None, states=None):
         bits = F.pack_masks(s["grids"], 1, gh, gw)
+        ws_ = None if args.no_weight_sums else s["wsum"]
         if states is not None:
-            return F.assign(geom, shapes, s["counts"], s["boxes"], bits, (gh, gw), mt_states=states, gt_offsets=s["off"], out=out)
-        return F.assign(geom, shapes, s["counts"], s["boxes"], bits, (gh, gw), seeds=s["seeds"], gt_offsets=s["off"], out=out)
+            return F.assign(geom, shapes, s["counts"], s["boxes"], bits, (gh, gw), mt_states=states, gt_offsets=s["off"], out=out,
+                            weight_sums=ws_)
+        return F.assign(geom, shapes, s["counts"], s["boxes"], bits, (gh, gw), seeds=s["seeds"], gt_offsets=s["off"], out=out,
+                        weight_sums=ws_)
 
     def do_loss(s, idx, w):
         losses, grads = F.loss_fwd_bwd(geom, wl.C, s["cls"], s["bbox"], s["iou"], s["counts"], s["boxes"], s["labels"], idx, w, lcfg,
-                                       gt_offsets=s["off"])
+                                       gt_offsets=s["off"], weight_sums=None if args.no_weight_sums else s["wsum"])
         F.scale_grads(geom, wl.C, grads, up_ones)            # what autograd's backward of the three losses launches
         return losses, grads
 
@@ -633,22 +638,30 @@ def main():
         torch.cuda.synchronize()
         gs, keepalive = [], []
         if use_graph:
+            # one graph = the stage applied to all R rotating sets, one call after the other: the gap between two graph
+            # launches (several us) is paid once per R calls, so the figure is the stage's launch-to-launch time in a stream
             stage_pool = torch.cuda.graph_pool_handle()
-            for s in sets:
-                g = torch.cuda.CUDAGraph()
-                with torch.cuda.graph(g, pool=stage_pool):
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g, pool=stage_pool):
+                for s in sets:
                     keepalive.append(fn(s))
-                gs.append(g)
-            call = lambda i: gs[i % R].replay()
-        else:
-            call = lambda i: fn(sets[i % R])
+            n_rep = max(1, iters // R)
+            g.replay()
+            torch.cuda.synchronize()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            for i in range(n_rep):
+                g.replay()
+            b.record()
+            torch.cuda.synchronize()
+            return a.elapsed_time(b) * 1e3 / (n_rep * R)   # us
         for i in range(R):
-            call(i)
+            fn(sets[i % R])
         torch.cuda.synchronize()
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         a.record()
         for i in range(iters):
-            call(i)
+            fn(sets[i % R])
         b.record()
         torch.cuda.synchronize()
         return a.elapsed_time(b) * 1e3 / iters   # us
@@ -656,7 +669,8 @@ def main():
     pre = []
     for s in sets:
         bits = F.pack_masks(s["grids"], 1, gh, gw)
-        idx, w, _ = F.assign(geom, shapes, s["counts"], s["boxes"], bits, (gh, gw), seeds=s["seeds"], gt_offsets=s["off"])
+        idx, w, _ = F.assign(geom, shapes, s["counts"], s["boxes"], bits, (gh, gw), seeds=s["seeds"], gt_offsets=s["off"],
+                             weight_sums=s["wsum"])
         s["bits"], s["idx"], s["w"] = bits, idx, w
         s["grads"] = F.loss_fwd_bwd(geom, wl.C, s["cls"], s["bbox"], s["iou"], s["counts"], s["boxes"], s["labels"], idx, w, lcfg,
                                     gt_offsets=s["off"])[1]
@@ -681,7 +695,11 @@ def main():
         "assign(pairs+resolve)": time_stage(lambda s: F.assign(geom, shapes, s["counts"], s["boxes"], s["bits"], (gh, gw), seeds=s["seeds"],
                                                                gt_offsets=s["off"])),
         "loss(pos+dense)": time_stage(lambda s: F.loss_fwd_bwd(geom, wl.C, s["cls"], s["bbox"], s["iou"], s["counts"], s["boxes"],
-                                                              s["labels"], s["idx"], s["w"], lcfg, gt_offsets=s["off"])),
+                                                              s["labels"], s["idx"], s["w"], lcfg, gt_offsets=s["off"],
+                                                              weight_sums=None if args.no_weight_sums else s["wsum"])),
+        "loss(pos+dense), no weight sums": time_stage(lambda s: F.loss_fwd_bwd(geom, wl.C, s["cls"], s["bbox"], s["iou"], s["counts"],
+                                                                              s["boxes"], s["labels"], s["idx"], s["w"], lcfg,
+                                                                              gt_offsets=s["off"])),
         "loss_dense_kernel": time_stage(dense_only),
         "get_bboxes(select+nms)": time_stage(lambda s: F.get_bboxes(geom, wl.C, s["cls"], s["bbox"], s["iou"], s["shp"], s["sf"], dcfg,
                                                                     rescale=True)),
@@ -812,7 +830,8 @@ def side_config(name, F, dev, peak_gbs):
         gh, gw = grids.shape[1:]
         bits = F.pack_masks(grids, 1, gh, gw)
         seeds = torch.arange(B, dtype=torch.int32, device=dev) + 1000 * r
-        idx, w, _ = F.assign(geom, shapes, counts, boxes, bits, (gh, gw), seeds=seeds, gt_offsets=off)
+        wsum = torch.zeros((B,), dtype=torch.float64, device=dev)
+        idx, w, _ = F.assign(geom, shapes, counts, boxes, bits, (gh, gw), seeds=seeds, gt_offsets=off, weight_sums=wsum)
         if real:     # SURVEY 8d head outputs (logits boosted at the positives), so ~1000 candidates per image survive
             ho = syn.make_head_outputs(wl, imgs, list(idx.cpu().numpy()), seed_base=wl.cfg_id * 100 + 7 * r)
             T = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)
@@ -822,7 +841,7 @@ def side_config(name, F, dev, peak_gbs):
             bbox = [torch.relu(torch.randn((B, 4, h, w_), device=dev, generator=g) + 1) for h, w_ in shapes]
             iou = [torch.randn((B, 1, h, w_), device=dev, generator=g) for h, w_ in shapes]
         sets.append(dict(counts=counts, off=off, boxes=boxes, labels=labels, bits=bits, seeds=seeds, idx=idx, w=w, cls=cls, bbox=bbox,
-                         iou=iou, gh=gh, gw=gw, pairs=sum(counts) * Ppts,
+                         iou=iou, gh=gh, gw=gw, pairs=sum(counts) * Ppts, wsum=wsum,
                          shp=torch.tensor([[wl.H, wl.W]] * B, dtype=torch.int32, device=dev),
                          sf=torch.ones((B, 4), dtype=torch.float32, device=dev)))
     lcfg = F.LossConfig()
@@ -831,29 +850,30 @@ def side_config(name, F, dev, peak_gbs):
         for i in range(3):
             fn(sets[i % R])
         torch.cuda.synchronize()
-        gs, keepalive = [], []
+        keepalive = []
         pool = torch.cuda.graph_pool_handle()
-        for s in sets:   # graph replays: no Python/ctypes time between the launches
-            gr = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(gr, pool=pool):
+        gr = torch.cuda.CUDAGraph()   # one graph = the call on every rotating set, back to back (no Python/ctypes time, one graph-launch gap per R calls)
+        with torch.cuda.graph(gr, pool=pool):
+            for s in sets:
                 keepalive.append(fn(s))
-            gs.append(gr)
-        for i in range(R):
-            gs[i].replay()
+        gr.replay()
         torch.cuda.synchronize()
+        n_rep = max(1, iters // R)
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         a.record()
-        for i in range(iters):
-            gs[i % R].replay()
+        for i in range(n_rep):
+            gr.replay()
         b.record()
         torch.cuda.synchronize()
-        return a.elapsed_time(b) * 1e3 / iters
+        return a.elapsed_time(b) * 1e3 / (n_rep * R)
 
     out = {"workload": wl.name + " (per-GPU share)", "images": B, "points_per_image": Ppts, "classes": C}
     pairs = float(np.mean([s["pairs"] for s in sets]))
     if name != "cfg4":
         t_loss = timeit(lambda s: F.loss_fwd_bwd(geom, C, s["cls"], s["bbox"], s["iou"], s["counts"], s["boxes"], s["labels"], s["idx"],
-                                                 s["w"], lcfg, gt_offsets=s["off"]))
+                                                 s["w"], lcfg, gt_offsets=s["off"], weight_sums=s["wsum"]))
+        t_loss_nohint = timeit(lambda s: F.loss_fwd_bwd(geom, C, s["cls"], s["bbox"], s["iou"], s["counts"], s["boxes"], s["labels"],
+                                                        s["idx"], s["w"], lcfg, gt_offsets=s["off"]))
         t_assign = timeit(lambda s: F.assign(geom, shapes, s["counts"], s["boxes"], s["bits"], (s["gh"], s["gw"]), seeds=s["seeds"],
                                              gt_offsets=s["off"]))
         loss_bytes = B * Ppts * (8 * C + 52)
@@ -862,7 +882,10 @@ def side_config(name, F, dev, peak_gbs):
         # so what the assignment itself moves is idx i64 + w f32 out (12 P) and boxes + bit masks in
         assign_bytes = B * (12 * Ppts + gavg * (16 + sets[0]["gh"] * ((sets[0]["gw"] + 31) // 32) * 4))
         out["loss_fwd_bwd"] = {"us": t_loss, "algorithmic_bytes": loss_bytes, "achieved_GBps": loss_bytes / t_loss / 1e3,
-                               "frac": loss_bytes / t_loss / 1e3 / peak_gbs}
+                               "frac": loss_bytes / t_loss / 1e3 / peak_gbs,
+                               "note": "radet_loss_fwd_bwd with the assignment's per-image weight sums handed over (what forward_train / "
+                                       "GraphedHotPath do); us_without_weight_sums = the same call without them",
+                               "us_without_weight_sums": t_loss_nohint, "frac_without_weight_sums": loss_bytes / t_loss_nohint / 1e3 / peak_gbs}
         out["assign"] = {"us": t_assign, "algorithmic_bytes": assign_bytes, "achieved_GBps": assign_bytes / t_assign / 1e3,
                          "frac": assign_bytes / t_assign / 1e3 / peak_gbs, "point_gt_pairs_per_s": pairs / (t_assign * 1e-6)}
         out["train_path_images_per_s"] = B / ((t_assign + t_loss) * 1e-6)

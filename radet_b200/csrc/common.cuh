@@ -22,6 +22,29 @@ extern void* g_debug_buf;  // optional device buffer for phase timestamps (devel
 constexpr int kWarp = 32;
 constexpr unsigned kFull = 0xffffffffu;
 
+// Programmatic dependent launch (sm_90+).  A kernel launched with launch_after_trigger() may start once every CTA of the
+// preceding kernel in the stream has executed griddep_launch_dependents() (or exited); it must execute griddep_wait()
+// before it reads or overwrites anything the preceding kernel touches (the wait returns when that grid has completed and
+// its writes are visible).  Both instructions are no-ops for kernels launched the ordinary way.
+__device__ __forceinline__ void griddep_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;"); }
+__device__ __forceinline__ void griddep_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_after_trigger(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, bool programmatic,
+                                        Args&&... args) {
+  cudaLaunchConfig_t lc{};
+  lc.gridDim = grid;
+  lc.blockDim = block;
+  lc.dynamicSmemBytes = smem;
+  lc.stream = st;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  lc.attrs = at;
+  lc.numAttrs = programmatic ? 1u : 0u;
+  return cudaLaunchKernelEx(&lc, kernel, static_cast<KArgs>(args)...);
+}
+
 // Device-side copy of the grid with prefix offsets (passed by value as a kernel parameter).
 struct GridDev {
   int num_levels;

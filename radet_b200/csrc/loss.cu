@@ -80,33 +80,80 @@ __global__ void get_targets_kernel(GridDev grid, int B, int C, const int* __rest
   }
 }
 
+// "Overlapped" order (radet_loss_fwd_bwd): loss_pos_kernel zero-fills the regression / IoU gradient planes itself and leaves
+// the positives' un-normalised gradient values in a compact list; the dense kernel, running next to it, writes the
+// normalised values into the planes at its end.  Unused (all null) in the classic order.
+struct PosList {
+  int* plist;                        // scratch [n]: flat (image, point) index of every positive of the batch (-1: skip) ...
+  float* pvals;                      // scratch [5n]: ... and its five un-normalised gradient values (T, B, L, R, IoU logit)
+};
+
+constexpr int kPosGroups = kPosPerThread / 4;   // a thread scans kPosGroups groups of 4 consecutive points, kPosThreads * 4 apart
+
 __global__ void __launch_bounds__(kPosThreads)
 loss_pos_kernel(GridDev grid, int B, MapsDev maps, const int* __restrict__ gt_offsets,
                 const float* __restrict__ gt_bboxes, const int64_t* __restrict__ pidx, const float* __restrict__ pw,
-                radet_loss_cfg_t cfg, LossWs* __restrict__ ws, double* __restrict__ partials, GradsDev grads) {
-  // Phase 1: every thread scans kPosPerThread consecutive points and the CTA compacts the (sparse, spatially
-  // clustered) positives into shared memory.  Phase 2: one positive per thread -- IoU target, GIoU and BCE terms and
-  // their gradients, evaluated ONCE here.  The un-normalised gradient values are parked in the gradient planes
-  // themselves at the positives' cells; the dense kernel (next in the stream) rescales those cells while it
-  // zero-fills the rest of the regression / IoU planes.
+                radet_loss_cfg_t cfg, LossWs* __restrict__ ws, double* __restrict__ partials, GradsDev grads, PosList fin,
+                unsigned long long* dbg) {
+#define PDBG(k) do { if (dbg && threadIdx.x == 0) { unsigned long long t__; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t__)); dbg[((size_t)50000 + blockIdx.x) * 8 + (k)] = t__; } } while (0)
+  PDBG(0);
+  // Phase 1: every thread scans kPosPerThread points (groups of 4 consecutive ones) and the CTA compacts the (sparse,
+  // spatially clustered) positives into shared memory.  Phase 2: one positive per thread -- IoU target, GIoU and BCE terms
+  // and their gradients, evaluated ONCE here.
+  //   Classic order: the un-normalised gradient values are parked in the gradient planes themselves at the positives' cells;
+  //   the dense kernel (next in the stream) rescales those cells while it zero-fills the rest of the regression / IoU planes.
+  //   Overlapped order (fin.plist): this kernel zero-fills the planes itself and the un-normalised values go to a compact
+  //   list; the dense kernel writes the normalised values into the planes once both kernels' class-plane work is done.
+  // CTAs are small (128 threads) so that a whole grid of them fits NEXT to the resident items of the dense kernel.
   __shared__ int s_scan[34];
   __shared__ int s_list[kPosThreads * kPosPerThread];
+  __shared__ int s_base;
+  // Programmatic dependent launch: a dense kernel that follows in the stream as a programmatic dependent may start now; it
+  // executes griddepcontrol.wait before it touches anything written here.  Otherwise a no-op.
+  griddep_launch_dependents();
   const bool want_grad = grads.bbox[0] != nullptr;
+  const bool finish = fin.plist != nullptr;
   const int P = grid.off[grid.num_levels];
   const int64_t n = (int64_t)B * P;
   const int64_t blk0 = (int64_t)blockIdx.x * kPosThreads * kPosPerThread;
-  const int64_t t0 = blk0 + (int64_t)threadIdx.x * kPosPerThread;
   unsigned flags = 0u;
 #pragma unroll
-  for (int k = 0; k < kPosPerThread; ++k) {
-    if (t0 + k < n && pidx[t0 + k] >= 0) flags |= 1u << k;   // pos_inds incl. ignored points (radet_head.py:245-247)
+  for (int g = 0; g < kPosGroups; ++g) {
+    const int64_t t0 = blk0 + (int64_t)g * (kPosThreads * 4) + threadIdx.x * 4;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      if (t0 + k < n && pidx[t0 + k] >= 0) flags |= 1u << (4 * g + k);   // pos_inds incl. ignored points (radet_head.py:245-247)
+    }
+  }
+  if (finish && want_grad) {
+    // zero the regression / IoU gradient cells of this thread's points (plane sizes are multiples of 4 in this order, so the 4
+    // points of a group lie in one plane and the stores are aligned); the positives are written by the dense kernel
+#pragma unroll
+    for (int g = 0; g < kPosGroups; ++g) {
+      const int64_t t0 = blk0 + (int64_t)g * (kPosThreads * 4) + threadIdx.x * 4;
+      if (t0 < n) {
+        const int b = (int)(t0 / P), p = (int)(t0 - (int64_t)b * P);
+        const int l = level_of(grid, p);
+        const int q = p - grid.off[l];
+        const int hw = grid.h[l] * grid.w[l];
+        float* gb = grads.bbox[l] + (int64_t)b * 4 * hw + q;
+        const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+        stg_stream4(gb, z);
+        stg_stream4(gb + hw, z);
+        stg_stream4(gb + 2 * hw, z);
+        stg_stream4(gb + 3 * hw, z);
+        stg_stream4(grads.iou[l] + (int64_t)b * hw + q, z);
+      }
+    }
   }
   int total;
   int pos = block_exclusive_scan(__popc(flags), s_scan, &total);
+  PDBG(1);
+  if (finish && want_grad && threadIdx.x == 0 && total > 0) s_base = (int)atomicAdd(&ws->pad[0], (unsigned)total);   // list slots of this CTA
   while (flags) {
     const int k = __ffs((int)flags) - 1;
     flags &= flags - 1u;
-    s_list[pos++] = threadIdx.x * kPosPerThread + k;
+    s_list[pos++] = (k >> 2) * (kPosThreads * 4) + threadIdx.x * 4 + (k & 3);
   }
   __syncthreads();
   float acc[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
@@ -115,6 +162,8 @@ loss_pos_kernel(GridDev grid, int B, MapsDev maps, const int* __restrict__ gt_of
     const int64_t idx = pidx[t];
     const int b = (int)(t / P), p = (int)(t - (int64_t)b * P);
     const int g0 = gt_offsets[b], G = gt_offsets[b + 1] - g0;
+    int listed = -1;
+    float pv[5] = {0.f, 0.f, 0.f, 0.f, 0.f};
     if (G > 0) {
       const float w = pw[t];
       const int l = level_of(grid, p);
@@ -137,16 +186,29 @@ loss_pos_kernel(GridDev grid, int B, MapsDev maps, const int* __restrict__ gt_of
       acc[3] += w * bce_logits(xi, bt.iou);
       acc[4] += (T + Bt) + (L + R);
       acc[5] += xi;
-      if (want_grad) {
+      pv[0] = -wq * bt.d[0];                                // d(1 - giou) = -d giou
+      pv[1] = -wq * bt.d[1];
+      pv[2] = -wq * bt.d[2];
+      pv[3] = -wq * bt.d[3];
+      pv[4] = w * (sigmoidf_(xi) - bt.iou);
+      listed = (int)t;                                      // n < 2^31 in the dense-first order (radet_loss_fwd_bwd)
+      if (want_grad && !finish) {
         float* gb = grads.bbox[l] + (int64_t)b * 4 * hw + q;
-        gb[0] = -wq * bt.d[0];                              // d(1 - giou) = -d giou
-        gb[hw] = -wq * bt.d[1];
-        gb[2 * hw] = -wq * bt.d[2];
-        gb[3 * hw] = -wq * bt.d[3];
-        grads.iou[l][(int64_t)b * hw + q] = w * (sigmoidf_(xi) - bt.iou);
+        gb[0] = pv[0];
+        gb[hw] = pv[1];
+        gb[2 * hw] = pv[2];
+        gb[3 * hw] = pv[3];
+        grads.iou[l][(int64_t)b * hw + q] = pv[4];
       }
     }
+    if (want_grad && finish) {
+      const int64_t o = (int64_t)s_base + i;
+      fin.plist[o] = listed;
+#pragma unroll
+      for (int k = 0; k < 5; ++k) fin.pvals[o * 5 + k] = pv[k];
+    }
   }
+  PDBG(2);
   __shared__ double s_part[kPosThreads / 32][6];
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   const bool warp_any = __any_sync(kFull, threadIdx.x < total);   // most warps hold no positive: skip their shuffles
@@ -166,13 +228,14 @@ loss_pos_kernel(GridDev grid, int B, MapsDev maps, const int* __restrict__ gt_of
   __syncthreads();
   if (threadIdx.x == 0) s_last = (atomicAdd(&ws->counter_pos, 1u) == gridDim.x - 1);
   __syncthreads();
+  PDBG(3);
   if (!s_last) return;
   __threadfence();
   // last block: fixed-order reduction over block partials (deterministic)
   double tot[6] = {0, 0, 0, 0, 0, 0};
   for (int i = threadIdx.x; i < (int)gridDim.x; i += kPosThreads) {
 #pragma unroll
-    for (int k = 0; k < 6; ++k) tot[k] += partials[(int64_t)i * 6 + k];
+    for (int k = 0; k < 6; ++k) tot[k] += __ldcg(partials + (int64_t)i * 6 + k);
   }
 #pragma unroll
   for (int k = 0; k < 6; ++k) {
@@ -180,19 +243,19 @@ loss_pos_kernel(GridDev grid, int B, MapsDev maps, const int* __restrict__ gt_of
     if (lane == 0) s_part[wid][k] = v;
   }
   __syncthreads();
-  if (threadIdx.x == 0) {
-    double S[6];
-    for (int k = 0; k < 6; ++k) {
-      S[k] = 0.0;
-      for (int w = 0; w < kPosThreads / 32; ++w) S[k] += s_part[w][k];
-      ws->norm[k] = S[k];
-    }
+  __shared__ double s_fin[6];
+  if (threadIdx.x < 6) {
+    double v = 0.0;
+    for (int w = 0; w < kPosThreads / 32; ++w) v += s_part[w][threadIdx.x];
+    s_fin[threadIdx.x] = v;
+    ws->norm[threadIdx.x] = v;
     // norm[0], norm[1] are the NORMALISERS (a caller running the opt-in FCOS-style reduce_mean all-reduces them
     // between the two passes); norm[6], norm[7] keep the rank-local values (radet_head.py:254 is rank-local)
-    ws->norm[6] = S[0];
-    ws->norm[7] = S[1];
-    ws->counter_pos = 0u;  // re-arm for the next call on this workspace
+    if (threadIdx.x < 2) ws->norm[6 + threadIdx.x] = v;
   }
+  if (threadIdx.x == 0) ws->counter_pos = 0u;  // re-arm for the next call on this workspace
+  PDBG(4);
+#undef PDBG
 }
 
 // ------------------------------------------------------------------------------------------------ dense pass
@@ -569,6 +632,290 @@ loss_dense_tma_kernel(GridDev grid, TileTable tt, int nch /* class chunks per ti
   }
 }
 
+// ---- warp-item variant of the dense pass (default where the TMA kernel applies) ---------------------------------------
+// One CTA = ONE warp = one item: 256 consecutive points of one (image, level) x one chunk of classes.  A lane holds 8
+// points (two float4 halves of the 256), so a stage of the ring (2 planes x 1 KB, six stages = 12 KB) feeds 16
+// independent focal chains per lane, and every per-plane overhead (mbarrier wait, bulk-copy issue, pointer bumps) is
+// paid once per 256 points instead of once per 128.  What makes it cheaper than loss_dense_tma_kernel per element:
+//   * planes in which no lane of the warp holds its target class (all but ~8 % of them) take a path without the
+//     target / non-target selects, in packed fp32x2 arithmetic (FMUL2 / FFMA2 / FADD2): ~13 instructions per element
+//     instead of ~21;
+//   * single-warp CTAs need no block barrier anywhere and balance over the SMs at a granularity of 256 points.
+constexpr int kWPts = 256;
+constexpr int kWStages = 6;
+constexpr int kWPlanes = 2;
+struct WTable {
+  int gpl[RADET_MAX_LEVELS];        // 256-point groups per (image, level)
+  int goff[RADET_MAX_LEVELS + 1];   // group offset of each level inside one image
+};
+
+// non-target elements only (z = x, coef = 1 - alpha), two at a time; wn = (1 - alpha) w, wnk = wn * k_cls
+__device__ __forceinline__ float2 focal_fast2(float2 x, float2 wn, float2 wnk, float2& lsum) {
+  const float2 t = __fmul2_rn(make_float2(fabsf(x.x), fabsf(x.y)), make_float2(-1.4426950408889634f, -1.4426950408889634f));
+  const float2 e = make_float2(ex2_approx(t.x), ex2_approx(t.y));                       // exp(-|x|)
+  const float2 d = __fadd2_rn(e, make_float2(1.f, 1.f));
+  const float2 inv = make_float2(rcp_approx(d.x), rcp_approx(d.y));                     // 1 / (1 + e)
+  const float2 lg = make_float2(lg2_approx(inv.x), lg2_approx(inv.y));
+  const float2 sp = __ffma2_rn(lg, make_float2(-0.6931471805599453f, -0.6931471805599453f),
+                               make_float2(fmaxf(x.x, 0.f), fmaxf(x.y, 0.f)));          // softplus(x)
+  const float2 ei = __fmul2_rn(e, inv);
+  const float2 s = make_float2(x.x >= 0.f ? inv.x : ei.x, x.y >= 0.f ? inv.y : ei.y);  // sigmoid(x)
+  const float2 u = __fmul2_rn(s, s);
+  lsum = __ffma2_rn(__fmul2_rn(wn, u), sp, lsum);
+  const float2 h = __ffma2_rn(__ffma2_rn(s, make_float2(-2.f, -2.f), make_float2(2.f, 2.f)), sp, s);
+  return __fmul2_rn(__fmul2_rn(wnk, u), h);
+}
+
+template <bool kGamma2, bool kHint>
+__global__ void __launch_bounds__(32)
+loss_dense_w_kernel(GridDev grid, WTable tab, int nch, int cc, int B, int C, MapsDev maps, GradsDev grads,
+                    const int* __restrict__ gt_offsets, const int64_t* __restrict__ gt_labels, const int64_t* __restrict__ pidx,
+                    const float* __restrict__ pw, radet_loss_cfg_t cfg, const float* __restrict__ grad_scale,
+                    LossWs* __restrict__ ws, double* __restrict__ partials, float* __restrict__ losses,
+                    const double* __restrict__ num_pos_hint, PosList plist, unsigned long long* dbg) {
+#define WDBG(k) do { if (dbg && threadIdx.x == 0) { unsigned long long t__; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t__)); dbg[(size_t)blockIdx.x * 8 + (k)] = t__; } } while (0)
+  WDBG(0);
+  __shared__ __align__(128) float s_ring[kWStages][kWPlanes][kWPts];
+  __shared__ __align__(8) uint64_t s_full[kWStages];
+  const int lane = threadIdx.x;
+  if (lane == 0) {
+#pragma unroll
+    for (int k = 0; k < kWStages; ++k) mbar_init(&s_full[k], 1);
+    fence_barrier_init();
+  }
+  // The ring starts out zeroed: lanes beyond a short group read whatever their slot held, and with a zero weight that
+  // contributes exactly 0 as long as it is finite.
+  for (int i = lane; i < kWStages * kWPlanes * kWPts / 4; i += 32) reinterpret_cast<float4*>(&s_ring[0][0][0])[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+  __syncwarp();
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  const uint32_t ring_s = smem_u32(&s_ring[0][0][0]), full_s = smem_u32(&s_full[0]);
+
+  const int P = grid.off[grid.num_levels];
+  const int gpi = tab.goff[grid.num_levels];
+  const unsigned it = blockIdx.x;
+  const int gg = (int)(it / (unsigned)nch), ch = (int)(it - (unsigned)gg * (unsigned)nch);
+  const int c0 = ch * cc, cn = min(cc, C - c0);                        // planes c0 .. c0 + cn - 1 (cn <= 32)
+  const int b = gg / gpi, r = gg - b * gpi;
+  int l = 0;
+#pragma unroll
+  for (int k = 1; k < RADET_MAX_LEVELS; ++k) l += (k < grid.num_levels && r >= tab.goff[k]) ? 1 : 0;
+  const int hw = grid.h[l] * grid.w[l];
+  const int q_warp = (r - tab.goff[l]) * kWPts;
+  const int npts = min(kWPts, hw - q_warp);                            // multiple of 4, > 0
+  const uint32_t bytes = (uint32_t)npts * 4u;
+  const int nst = (cn + kWPlanes - 1) / kWPlanes;
+  const float* nsrc = maps.cls[l] + ((int64_t)b * C + c0) * hw + q_warp;   // lane 0: first plane of the next stage to request
+  int issued = 0;
+  auto issue_next = [&](unsigned sl_) {
+    const int np = cn - issued * kWPlanes;
+    const uint32_t bar = full_s + sl_ * 8u;
+    const uint32_t sdst = ring_s + sl_ * (kWPlanes * kWPts * 4u);
+    mbar_expect_tx_s(bar, bytes * (uint32_t)min(np, kWPlanes));
+#pragma unroll
+    for (int p_ = 0; p_ < kWPlanes; ++p_)
+      if (p_ < np) tma_bulk_g2s_s(sdst + p_ * (kWPts * 4u), nsrc + (int64_t)p_ * hw, bytes, bar);
+    nsrc += (int64_t)kWPlanes * hw;
+    ++issued;
+  };
+  // Normalisers.  loss_pos_kernel precedes this kernel in the stream; launched as its programmatic dependent this kernel may
+  // start while it is still running, and nothing it writes (ws->norm, the positives' gradient values) is read before
+  // griddep_wait().  The class planes need num_pos only (the gradient scale k_cls):
+  //   * kHint ("overlapped" order): num_pos is the fixed-order sum of the assignment's per-image weight sums (num_pos_hint),
+  //     the wait sits BEHIND the class planes, loss_pos_kernel has zero-filled the regression / IoU planes and listed the
+  //     positives' un-normalised gradients -- the items share the list and write the normalised values;
+  //   * otherwise the wait sits behind the per-lane set-up (index / weight loads, labels, the ring's first bulk copies),
+  //     and the items of class chunk 0 zero-fill the regression / IoU planes, rescaling the cells loss_pos_kernel parked.
+  const float gs_cls = grad_scale ? grad_scale[0] : 1.f, gs_box = grad_scale ? grad_scale[1] : 1.f,
+              gs_iou = grad_scale ? grad_scale[2] : 1.f;
+  const bool want_grad = grads.cls[0] != nullptr;
+  const float gamma = cfg.gamma, alpha = cfg.alpha;
+  // per-lane setup: 8 points = half 0 at 4*lane, half 1 at 128 + 4*lane
+  const int g0 = gt_offsets[b], G = gt_offsets[b + 1] - g0;
+  const int64_t pb = (int64_t)b * P + grid.off[l] + q_warp;
+  const bool act[2] = {4 * lane < npts, 128 + 4 * lane < npts};
+  int lab[8];
+  float w8[8], wn[8], wnk[8];
+  unsigned lmask = 0u, posmask = 0u;
+  // The index / weight loads go out BEFORE the ring's first bulk copies: all warps of the grid start together, and 12 KB of
+  // prefetch per warp in front of these 3 KB would delay every warp's set-up by the time the prefetch takes (measured:
+  // 5.4 us from CTA start to the first plane with the copies first).
+  longlong2 ia[2], ib[2];
+  float4 wv2[2];
+#pragma unroll
+  for (int h_ = 0; h_ < 2; ++h_) {
+    ia[h_] = ib[h_] = make_longlong2(-1, -1);
+    wv2[h_] = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (act[h_]) {
+      const int64_t o = pb + 128 * h_ + 4 * lane;
+      ia[h_] = *reinterpret_cast<const longlong2*>(pidx + o);
+      ib[h_] = *reinterpret_cast<const longlong2*>(pidx + o + 2);
+      wv2[h_] = *reinterpret_cast<const float4*>(pw + o);
+    }
+  }
+  if (lane == 0) {
+    const int n0 = min(kWStages, nst);
+    for (int s_ = 0; s_ < n0; ++s_) issue_next((unsigned)s_);
+  }
+#pragma unroll
+  for (int h_ = 0; h_ < 2; ++h_) {
+    const int64_t v[4] = {ia[h_].x, ia[h_].y, ib[h_].x, ib[h_].y};
+    const float w4[4] = {wv2[h_].x, wv2[h_].y, wv2[h_].z, wv2[h_].w};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int k = 4 * h_ + i;
+      const int ix = v[i] < 0 ? -1 : (int)(v[i] > (int64_t)G ? (int64_t)G : v[i]);
+      if (ix >= 0) posmask |= 1u << k;
+      lab[k] = (int)label_of(ix, G, gt_labels + g0, C) - c0;                                  // relative to the chunk
+      if (lab[k] >= 0 && lab[k] < cn) lmask |= 1u << lab[k];
+      w8[k] = w4[i];
+      wn[k] = (1.f - alpha) * w4[i];
+    }
+  }
+  if (!kHint) griddep_wait();           // a no-op unless this kernel was launched as a programmatic dependent
+  const double num_pos = kHint ? warp_sum_array(num_pos_hint, (unsigned)B, lane) : ws->norm[0];
+  const float k_cls = gs_cls * cfg.w_cls / (float)(num_pos + (double)cfg.avg_extra);
+#pragma unroll
+  for (int k = 0; k < 8; ++k) wnk[k] = wn[k] * k_cls;
+  float* dst0 = want_grad ? grads.cls[l] + ((int64_t)b * C + c0) * hw + q_warp + 4 * lane : nullptr;   // next plane to store
+  WDBG(1);
+  float2 ls2 = make_float2(0.f, 0.f);
+  float lsum = 0.f;
+  unsigned slot = 0, par = 0;
+  for (int s_ = 0; s_ < nst; ++s_) {
+    mbar_wait_s(full_s + slot * 8u, par);
+    if (s_ == 0) WDBG(2);
+    if (s_ == 7) WDBG(3);
+    const float* rp = &s_ring[slot][0][0] + 4 * lane;
+#pragma unroll
+    for (int p_ = 0; p_ < kWPlanes; ++p_) {
+      const int c = s_ * kWPlanes + p_;
+      if (c < cn) {                                                                            // warp-uniform
+        const float4 x0 = *reinterpret_cast<const float4*>(rp + p_ * kWPts);
+        const float4 x1 = *reinterpret_cast<const float4*>(rp + p_ * kWPts + 128);
+        float4 g0v, g1v;
+        if (kGamma2 && !__any_sync(kFull, (lmask >> c) & 1u)) {
+          // no lane holds its target class in this plane: packed non-target path
+          float2 t;
+          t = focal_fast2(make_float2(x0.x, x0.y), make_float2(wn[0], wn[1]), make_float2(wnk[0], wnk[1]), ls2); g0v.x = t.x; g0v.y = t.y;
+          t = focal_fast2(make_float2(x0.z, x0.w), make_float2(wn[2], wn[3]), make_float2(wnk[2], wnk[3]), ls2); g0v.z = t.x; g0v.w = t.y;
+          t = focal_fast2(make_float2(x1.x, x1.y), make_float2(wn[4], wn[5]), make_float2(wnk[4], wnk[5]), ls2); g1v.x = t.x; g1v.y = t.y;
+          t = focal_fast2(make_float2(x1.z, x1.w), make_float2(wn[6], wn[7]), make_float2(wnk[6], wnk[7]), ls2); g1v.z = t.x; g1v.w = t.y;
+        } else {
+          g0v.x = focal_acc<kGamma2>(x0.x, lab[0] == c, alpha * w8[0], wn[0], k_cls, gamma, lsum);
+          g0v.y = focal_acc<kGamma2>(x0.y, lab[1] == c, alpha * w8[1], wn[1], k_cls, gamma, lsum);
+          g0v.z = focal_acc<kGamma2>(x0.z, lab[2] == c, alpha * w8[2], wn[2], k_cls, gamma, lsum);
+          g0v.w = focal_acc<kGamma2>(x0.w, lab[3] == c, alpha * w8[3], wn[3], k_cls, gamma, lsum);
+          g1v.x = focal_acc<kGamma2>(x1.x, lab[4] == c, alpha * w8[4], wn[4], k_cls, gamma, lsum);
+          g1v.y = focal_acc<kGamma2>(x1.y, lab[5] == c, alpha * w8[5], wn[5], k_cls, gamma, lsum);
+          g1v.z = focal_acc<kGamma2>(x1.z, lab[6] == c, alpha * w8[6], wn[6], k_cls, gamma, lsum);
+          g1v.w = focal_acc<kGamma2>(x1.w, lab[7] == c, alpha * w8[7], wn[7], k_cls, gamma, lsum);
+        }
+        if (dst0) {
+          if (act[0]) stg_stream4(dst0, g0v);
+          if (act[1]) stg_stream4(dst0 + 128, g1v);
+          dst0 += hw;
+        }
+      }
+    }
+    // Refill the slot only AFTER its values have been consumed (the stores above depend on them): neither a barrier nor
+    // an mbarrier arrive orders the bulk copy's write behind a shared-memory read that is still in flight.
+    __syncwarp();
+    if (lane == 0 && issued < nst) issue_next(slot);
+    if (++slot == kWStages) {
+      slot = 0;
+      par ^= 1u;
+    }
+  }
+  WDBG(4);
+  if (kHint) griddep_wait();
+  WDBG(7);
+  const double sum_wq = ws->norm[1];
+  const bool has_pos = ws->norm[6] > 0.0;                                                     // radet_head.py:261
+  if (kHint) {
+    // the positives' regression / IoU gradients: this item's share of loss_pos_kernel's list (all loads before the stores)
+    if (want_grad) {
+      const float k_box = has_pos ? gs_box * cfg.w_bbox / (float)sum_wq : gs_box;
+      const float k_iou = has_pos ? gs_iou * cfg.w_iou / (float)num_pos : gs_iou;
+      const int npos = (int)__ldcg(&ws->pad[0]);
+      for (int i = (int)it * 32 + lane; i < npos; i += (int)gridDim.x * 32) {
+        const int t = __ldcg(plist.plist + i);
+        float v[5];
+#pragma unroll
+        for (int k = 0; k < 5; ++k) v[k] = __ldcg(plist.pvals + (int64_t)i * 5 + k);
+        if (t < 0) continue;
+        const int tb = t / P, tp = t - tb * P;
+        const int tl = level_of(grid, tp);
+        const int tq = tp - grid.off[tl];
+        const int thw = grid.h[tl] * grid.w[tl];
+        float* gb = grads.bbox[tl] + (int64_t)tb * 4 * thw + tq;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) gb[(int64_t)k * thw] = has_pos ? k_box * v[k] : gs_box;   // radet_head.py:280 when num_pos == 0
+        grads.iou[tl][(int64_t)tb * thw + tq] = has_pos ? k_iou * v[4] : gs_iou;               // :281
+      }
+    }
+  }
+  // regression / IoU gradient planes: zero except at the positives parked by loss_pos_kernel (rescaled in place).  All the
+  // parked values are loaded before the first store (the loads of one plane must not queue behind the stores of another).
+  if (!kHint && want_grad && ch == 0) {
+    const float k_box = has_pos ? gs_box * cfg.w_bbox / (float)sum_wq : gs_box;
+    const float k_iou = has_pos ? gs_iou * cfg.w_iou / (float)num_pos : gs_iou;
+    float gv[2][5][4];
+#pragma unroll
+    for (int h_ = 0; h_ < 2; ++h_) {
+      const int q0 = q_warp + 128 * h_ + 4 * lane;
+      const unsigned pm = (act[h_] && G > 0) ? (posmask >> (4 * h_)) & 15u : 0u;
+#pragma unroll
+      for (int kk = 0; kk < 5; ++kk) {
+        const float* o = kk < 4 ? grads.bbox[l] + ((int64_t)b * 4 + kk) * hw + q0 : grads.iou[l] + (int64_t)b * hw + q0;
+        const float kn = kk < 4 ? k_box : k_iou, gs = kk < 4 ? gs_box : gs_iou;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          gv[h_][kk][i] = 0.f;
+          if ((pm >> i) & 1u) gv[h_][kk][i] = has_pos ? kn * __ldcg(o + i) : gs;   // radet_head.py:280-281 when num_pos == 0
+        }
+      }
+    }
+#pragma unroll
+    for (int h_ = 0; h_ < 2; ++h_) {
+      if (!act[h_]) continue;
+      const int q0 = q_warp + 128 * h_ + 4 * lane;
+#pragma unroll
+      for (int kk = 0; kk < 5; ++kk) {
+        float* o = kk < 4 ? grads.bbox[l] + ((int64_t)b * 4 + kk) * hw + q0 : grads.iou[l] + (int64_t)b * hw + q0;
+        stg_stream4(o, make_float4(gv[h_][kk][0], gv[h_][kk][1], gv[h_][kk][2], gv[h_][kk][3]));
+      }
+    }
+  }
+  WDBG(5);
+  // loss_cls = w_cls * sum / (num_pos + num_imgs): one partial sum per item, the last CTA adds them in a fixed order
+  const double v = warp_sum((double)lsum + ((double)ls2.x + (double)ls2.y));
+  const unsigned nblocks = gridDim.x;
+  unsigned last = 0;
+  if (lane == 0) {
+    partials[it] = v;
+    __threadfence();
+    last = (atomicAdd(&ws->counter_dense, 1u) == nblocks - 1) ? 1u : 0u;
+  }
+  last = __shfl_sync(kFull, last, 0);
+  WDBG(6);
+  if (!last) return;
+  __threadfence();
+  const double tot = warp_sum(strided_sum(partials, nblocks, (unsigned)lane, 32u));
+  if (lane == 0) {
+    losses[0] = (float)((double)cfg.w_cls * tot / (num_pos + (double)cfg.avg_extra));           // radet_head.py:256-259
+    losses[1] = has_pos ? (float)((double)cfg.w_bbox * ws->norm[2] / sum_wq) : (float)ws->norm[4];   // :269-274 / :280
+    losses[2] = has_pos ? (float)((double)cfg.w_iou * ws->norm[3] / num_pos) : (float)ws->norm[5];   // :275-278 / :281
+    losses[3] = (float)num_pos;
+    ws->counter_dense = 0u;
+    if (kHint) {
+      ws->pad[0] = 0u;                  // every item has read the list length (their counter increments came after)
+      // weight sums that do not belong to these weights (a caller's mistake) must not pass silently
+      const double own = ws->norm[6];
+      if (!(fabs(num_pos - own) <= 1e-5 * fmax(1.0, fabs(own)))) losses[0] = losses[1] = losses[2] = __int_as_float(0x7fc00000);
+    }
+  }
+}
+
 struct ScaleTable {
   float* ptr[3 * RADET_MAX_LEVELS];
   int64_t n[3 * RADET_MAX_LEVELS];
@@ -784,12 +1131,50 @@ static bool tile_plan(const GridDev& g, int B, int C, const void* pidx, const vo
   return true;
 }
 
-// workspace: LossWs | loss_pos partials | dense partials (two-launch path) | fused-kernel partials
+// Items of the warp-item dense kernel; false when it does not apply (a plane size that is not a multiple of 4, unaligned
+// index / weight arrays).
+static bool w_plan(const GridDev& g, int B, int C, const void* pidx, const void* pw, WTable* tab, int* nch, int* cc, int64_t* items) {
+  if ((reinterpret_cast<uintptr_t>(pidx) | reinterpret_cast<uintptr_t>(pw)) & 15) return false;   // 128-bit index / weight loads
+  int t = 0;
+  for (int l = 0; l < g.num_levels; ++l) {
+    const int hw = g.h[l] * g.w[l];
+    if (hw & 3) return false;
+    tab->gpl[l] = (hw + kWPts - 1) / kWPts;
+    tab->goff[l] = t;
+    t += tab->gpl[l];
+  }
+  for (int l = g.num_levels; l <= RADET_MAX_LEVELS; ++l) tab->goff[l] = t;
+  for (int l = g.num_levels; l < RADET_MAX_LEVELS; ++l) tab->gpl[l] = 0;
+  const int64_t groups = (int64_t)B * t;
+  // class chunks: at most 32 classes per item (one bit per class in the lanes' target masks); more chunks only when the
+  // groups alone would leave most SMs without an item
+  int64_t n = (C + 31) / 32;
+  if (groups * n < kSMs) {
+    n = (kSMs + groups - 1) / groups;
+    if (n > (C + 3) / 4) n = (C + 3) / 4;             // at least four planes per chunk
+  }
+  if (n < 1) n = 1;
+  *cc = (int)((C + n - 1) / n);
+  if (*cc > 32) *cc = 32;
+  *nch = (C + *cc - 1) / *cc;
+  *items = groups * *nch;
+  return *items < (1ll << 31);
+}
+static int64_t w_items_bound(const GridDev& g, int B, int C) {      // partial-sum slots the workspace reserves
+  int64_t t = 0;
+  for (int l = 0; l < g.num_levels; ++l) t += (g.h[l] * g.w[l] + kWPts - 1) / kWPts;
+  const int64_t n = ((C + 31) / 32) > ((C + 3) / 4) ? (C + 31) / 32 : (C + 3) / 4;
+  return (int64_t)B * t * n;
+}
+
+// workspace: LossWs | loss_pos partials | dense partials (two-launch path) | fused-kernel partials | positives list
 static void loss_ws_layout(const GridDev& g, int batch, int num_classes, int dblk, size_t* off_pos, size_t* off_dense, size_t* off_fused,
-                           size_t* total) {
+                           size_t* off_list, size_t* total) {
   const int64_t n = (int64_t)batch * g.off[g.num_levels];
   const int64_t pos_blocks = (n + kPosThreads * kPosPerThread - 1) / (kPosThreads * kPosPerThread);
-  const int64_t dense_blocks = dblk > (int)(kSMs * 8) ? dblk : (int)(kSMs * 8);   // either two-launch kernel's partial-sum slots
+  int64_t dense_blocks = dblk > (int)(kSMs * 8) ? dblk : (int)(kSMs * 8);          // any two-launch dense kernel's partial-sum slots
+  const int64_t wb = w_items_bound(g, batch, num_classes);
+  if (wb > dense_blocks) dense_blocks = wb;
   size_t o = align_up(sizeof(LossWs), 256);
   *off_pos = o;
   o += align_up((size_t)pos_blocks * 6 * 8, 256);
@@ -797,6 +1182,8 @@ static void loss_ws_layout(const GridDev& g, int batch, int num_classes, int dbl
   o += align_up((size_t)dense_blocks * 8, 256);
   *off_fused = o;
   o += fused_part_bytes(g, batch, num_classes);
+  *off_list = o;                                   // overlapped order: flat index + five gradient values of every positive
+  o += align_up((size_t)n * 4, 256) + align_up((size_t)n * 20, 256);
   *total = o;
 }
 
@@ -806,8 +1193,8 @@ extern "C" size_t radet_loss_workspace_bytes(const radet_grid_t* grid, int32_t b
   DenseTable tab;
   int cc, nj, dblk;
   if (dense_plan(g, batch, num_classes, &tab, &cc, &nj, &dblk) != RADET_OK) return 0;
-  size_t a, b, c, total;
-  loss_ws_layout(g, batch, num_classes, dblk, &a, &b, &c, &total);
+  size_t a, b, c, d, total;
+  loss_ws_layout(g, batch, num_classes, dblk, &a, &b, &c, &d, &total);
   return total;
 }
 
@@ -856,8 +1243,8 @@ extern "C" int radet_loss_fwd_bwd(const radet_grid_t* grid, int32_t batch, int32
   if (use_tma && tma_blocks > dblk) dblk = tma_blocks;       // partial-sum slots (workspace_bytes sizes for the max)
   unsigned char* wsb = static_cast<unsigned char*>(workspace);
   LossWs* ws = reinterpret_cast<LossWs*>(wsb);
-  size_t off_pos, off_dense, off_fused, total_ws;
-  loss_ws_layout(g, batch, num_classes, dblk, &off_pos, &off_dense, &off_fused, &total_ws);
+  size_t off_pos, off_dense, off_fused, off_list, total_ws;
+  loss_ws_layout(g, batch, num_classes, dblk, &off_pos, &off_dense, &off_fused, &off_list, &total_ws);
   const int64_t n = (int64_t)batch * g.off[g.num_levels];
   const int64_t pos_blocks = (n + kPosThreads * kPosPerThread - 1) / (kPosThreads * kPosPerThread);
   double* pos_part = reinterpret_cast<double*>(wsb + off_pos);
@@ -866,7 +1253,7 @@ extern "C" int radet_loss_fwd_bwd(const radet_grid_t* grid, int32_t batch, int32
   const bool hybrid = impl && impl[0] == 'h';   // "hybrid": loss_pos_kernel, then the ticketed streaming kernel for the dense pass
   if (hybrid && phases == RADET_LOSS_PHASE_ALL) {
     loss_pos_kernel<<<(unsigned)pos_blocks, kPosThreads, 0, st>>>(g, batch, md, gt_offsets, gt_bboxes, points_to_gt_index,
-                                                                  points_weight, *cfg, ws, pos_part, gd);
+                                                                  points_weight, *cfg, ws, pos_part, gd, PosList{}, static_cast<unsigned long long*>(g_debug_buf));
     RADET_LAUNCH_CHECK();
     rc = launch_loss_fused(g, batch, num_classes, md, gd, gt_offsets, gt_bboxes, gt_labels, points_to_gt_index, points_weight, *cfg,
                            grad_scale, ws, wsb + off_fused, false, true, losses, nullptr, st);
@@ -881,12 +1268,62 @@ extern "C" int radet_loss_fwd_bwd(const radet_grid_t* grid, int32_t batch, int32
                            grad_scale, ws, wsb + off_fused, with_p1, with_items, losses, cfg->weight_sums, st);
     if (rc != RADET_E_UNSUPPORTED) return rc;
   }
+  // ---- "overlapped" order (the default whenever the caller hands over the assignment's per-image weight sums): the class
+  // planes need no result of loss_pos_kernel then.  loss_pos_kernel is launched first and the dense kernel as its
+  // programmatic dependent: the items stream their class planes NEXT to it and wait for its completion only before the
+  // sparse regression / IoU gradients and the final sums.  loss_pos_kernel zero-fills those planes and lists the positives.
+  WTable wtab;
+  int wnch = 1, wcc = 1;
+  int64_t witems = 0;
+  static const bool pdl_on = !(getenv("RADET_LOSS_PDL") && getenv("RADET_LOSS_PDL")[0] == '0');
+  const bool w_ok = !(impl && (impl[0] == 'r' || impl[0] == 't' || impl[0] == 'f')) &&
+                    w_plan(g, batch, num_classes, points_to_gt_index, points_weight, &wtab, &wnch, &wcc, &witems);
+  // Kernels that are meant to share an SM must agree on its shared-memory carve-out: an SM does not change the split while
+  // CTAs are resident, so items of the dense kernel (12 KB each) could not join loss_pos CTAs running under a small carve-out.
+  static const bool carve_set = [] {
+    cudaFuncSetAttribute(loss_pos_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    cudaFuncSetAttribute(loss_dense_w_kernel<true, true>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    cudaFuncSetAttribute(loss_dense_w_kernel<false, true>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    cudaFuncSetAttribute(loss_dense_w_kernel<true, false>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    cudaFuncSetAttribute(loss_dense_w_kernel<false, false>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    return true;
+  }();
+  (void)carve_set;
+  if (w_ok && pdl_on && phases == RADET_LOSS_PHASE_ALL && cfg->weight_sums && n < (1ll << 31)) {
+    PosList pl{reinterpret_cast<int*>(wsb + off_list), reinterpret_cast<float*>(wsb + off_list + align_up((size_t)n * 4, 256))};
+    loss_pos_kernel<<<(unsigned)pos_blocks, kPosThreads, 0, st>>>(g, batch, md, gt_offsets, gt_bboxes, points_to_gt_index,
+                                                                  points_weight, *cfg, ws, pos_part, gd, pl,
+                                                                  static_cast<unsigned long long*>(g_debug_buf));
+    RADET_LAUNCH_CHECK();
+    auto kern = cfg->gamma == 2.0f ? loss_dense_w_kernel<true, true> : loss_dense_w_kernel<false, true>;
+    cudaError_t le = launch_after_trigger(kern, dim3((unsigned)witems), dim3(32), 0, st, true, g, wtab, wnch, wcc, batch, num_classes,
+                                          md, gd, gt_offsets, gt_labels, points_to_gt_index, points_weight, *cfg, grad_scale, ws, dense_part,
+                                          losses, cfg->weight_sums, pl, static_cast<unsigned long long*>(g_debug_buf));
+    if (le != cudaSuccess) return (int)le;
+    RADET_LAUNCH_CHECK();
+    return RADET_OK;
+  }
   if (phases & RADET_LOSS_PHASE_NORMALIZERS) {
     loss_pos_kernel<<<(unsigned)pos_blocks, kPosThreads, 0, st>>>(g, batch, md, gt_offsets, gt_bboxes, points_to_gt_index,
-                                                                  points_weight, *cfg, ws, pos_part, gd);
+                                                                  points_weight, *cfg, ws, pos_part, gd, PosList{}, static_cast<unsigned long long*>(g_debug_buf));
     RADET_LAUNCH_CHECK();
   }
   if (!(phases & RADET_LOSS_PHASE_DENSE)) return RADET_OK;
+  if (!(impl && (impl[0] == 'r' || impl[0] == 't'))) {          // default: the warp-item kernel ("tma" / "reg": the older two)
+    // classic order: loss_pos_kernel ran above.  Small grids launch as its programmatic dependent (prologue next to it);
+    // large ones do not -- items that trickle in while loss_pos CTAs still hold registers are placed unevenly over the SMs,
+    // and the imbalance costs more than the overlap gains (cfg5: 40.4 -> 42.5 us; cfg2: 27.8 -> 25.1 us).
+    if (w_ok) {
+      const bool prog = (phases == RADET_LOSS_PHASE_ALL) && pdl_on && witems <= 4 * (int64_t)kSMs;
+      auto kern = cfg->gamma == 2.0f ? loss_dense_w_kernel<true, false> : loss_dense_w_kernel<false, false>;
+      cudaError_t le = launch_after_trigger(kern, dim3((unsigned)witems), dim3(32), 0, st, prog, g, wtab, wnch, wcc, batch, num_classes,
+                                            md, gd, gt_offsets, gt_labels, points_to_gt_index, points_weight, *cfg, grad_scale, ws, dense_part,
+                                            losses, (const double*)nullptr, PosList{}, static_cast<unsigned long long*>(g_debug_buf));
+      if (le != cudaSuccess) return (int)le;
+      RADET_LAUNCH_CHECK();
+      return RADET_OK;
+    }
+  }
   if (use_tma && !(impl && impl[0] == 'r')) {
     if (cfg->gamma == 2.0f)
       loss_dense_tma_kernel<true><<<(unsigned)tma_blocks, kTmaThreads, 0, st>>>(g, tt, nch, tcc, batch, num_classes, md, gd, gt_offsets, gt_labels,

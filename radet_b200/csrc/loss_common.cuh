@@ -110,8 +110,8 @@ __device__ __forceinline__ float bce_logits(float x, float z) {  // torch: max(x
 __device__ __forceinline__ float sigmoidf_(float x) { return 1.0f / (1.0f + expf(-x)); }
 
 // workspace layout (doubles): [0..7] final sums / normalisers, then block partials
-constexpr int kPosThreads = 256;
-constexpr int kPosPerThread = 4;
+constexpr int kPosThreads = 128;
+constexpr int kPosPerThread = 8;
 constexpr int kNormSlots = 8;   // S0 num_pos, S1 sum wq, S2 sum wq(1-giou), S3 sum w*bce, S4 sum pred, S5 sum iou logit
 struct LossWs {
   double norm[kNormSlots];
@@ -205,6 +205,29 @@ __device__ __forceinline__ float focal_acc(float x, bool is_t, float wt, float w
   lsum = fmaf(fabsf(A), sp, lsum);
   const float h = fmaf(kGamma2 ? fmaf(-2.f, s, 2.f) : gamma * (1.f - s), sp, s);
   return (A * h) * k_cls;
+}
+
+// Fixed-order partial sum of p[first], p[first + stride], ...: up to 16 loads are issued before the first addition
+// (one L2 round trip for the usual few hundred to few thousand partial sums); the combination order is fixed, so the
+// value depends only on (n, first, stride).
+__device__ __forceinline__ double strided_sum(const double* p, unsigned n, unsigned first, unsigned stride) {
+  double tot = 0.0;
+  for (unsigned i = first; i < n; i += 16 * stride) {
+    double a[16];
+#pragma unroll
+    for (int k = 0; k < 16; ++k) a[k] = (i + k * stride < n) ? __ldcg(p + i + k * stride) : 0.0;
+#pragma unroll
+    for (int w_ = 1; w_ < 16; w_ <<= 1) {
+#pragma unroll
+      for (int k = 0; k < 16; k += 2 * w_) a[k] += a[k + w_];
+    }
+    tot += a[0];
+  }
+  return tot;
+}
+// ... by one warp (lane-strided, then an xor tree): the same result whichever warp evaluates it
+__device__ __forceinline__ double warp_sum_array(const double* p, unsigned n, int lane) {
+  return warp_sum(strided_sum(p, n, (unsigned)lane, 32u));
 }
 
 }  // namespace radet

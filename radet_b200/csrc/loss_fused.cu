@@ -85,29 +85,6 @@ __device__ __forceinline__ void wait_flag(const unsigned* flag) {
 __device__ __forceinline__ void st_relaxed_u32(unsigned* p, unsigned v) {   // after a __threadfence(): fence + relaxed store = release
   asm volatile("st.relaxed.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
-// Fixed-order partial sum of p[first], p[first + stride], ...: up to 16 loads are issued before the first addition
-// (one L2 round trip for the usual few hundred to few thousand partial sums); the combination order is fixed, so the
-// value depends only on (n, first, stride).
-__device__ __forceinline__ double strided_sum(const double* p, unsigned n, unsigned first, unsigned stride) {
-  double tot = 0.0;
-  for (unsigned i = first; i < n; i += 16 * stride) {
-    double a[16];
-#pragma unroll
-    for (int k = 0; k < 16; ++k) a[k] = (i + k * stride < n) ? __ldcg(p + i + k * stride) : 0.0;
-#pragma unroll
-    for (int w_ = 1; w_ < 16; w_ <<= 1) {
-#pragma unroll
-      for (int k = 0; k < 16; k += 2 * w_) a[k] += a[k + w_];
-    }
-    tot += a[0];
-  }
-  return tot;
-}
-// ... by one warp (lane-strided, then an xor tree): the same result whichever warp evaluates it
-__device__ __forceinline__ double warp_sum_array(const double* p, unsigned n, int lane) {
-  return warp_sum(strided_sum(p, n, (unsigned)lane, 32u));
-}
-
 template <bool kGamma2, int CG, int D>
 __global__ void __launch_bounds__(kFThreads, kFOcc)
 loss_fused_kernel(GridDev grid, FusedPlan plan, int B, int C, MapsDev maps, GradsDev grads, const int* __restrict__ gt_offsets,

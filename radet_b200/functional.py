@@ -228,8 +228,8 @@ def loss_fwd_bwd(geom: Geometry, num_classes: int, cls, bbox, iou, gt_counts, gt
 
     sync_group: opt-in FCOS/ATSS-style reduce_mean of the two normalisers over that process group (NOT the
     reference behaviour of RADetHead, which keeps them rank-local).
-    weight_sums: optional float64 [B] written by assign(weight_sums=...) for these idx / w: the dense pass then starts
-    without waiting for its own reduction over them."""
+    weight_sums: optional float64 [B] written by assign(weight_sums=...) for these idx / w: the dense pass then streams its
+    class planes NEXT to the sparse positive pass instead of behind it (radet_loss_fwd_bwd, "overlapped" order)."""
     B = cls[0].shape[0]
     level_shapes = tuple(tuple(t.shape[-2:]) for t in cls)
     _check_maps(cls, bbox, iou, level_shapes, B, num_classes)
@@ -298,11 +298,11 @@ class HeadLossFunction(torch.autograd.Function):
     """Autograd node of the fused loss: gradients are produced by the forward kernel and only rescaled in backward."""
 
     @staticmethod
-    def forward(ctx, geom, num_classes, cfg, gt_counts, gt_bboxes, gt_labels, idx, w, sync_group, nlev, *maps):
+    def forward(ctx, geom, num_classes, cfg, gt_counts, gt_bboxes, gt_labels, idx, w, sync_group, weight_sums, nlev, *maps):
         cls, bbox, iou = list(maps[:nlev]), list(maps[nlev:2 * nlev]), list(maps[2 * nlev:])
         need = any(t.requires_grad for t in maps)
         losses, grads = loss_fwd_bwd(geom, num_classes, cls, bbox, iou, gt_counts, gt_bboxes, gt_labels, idx, w, cfg,
-                                     want_grads=need, sync_group=sync_group)
+                                     want_grads=need, sync_group=sync_group, weight_sums=weight_sums)
         ctx.geom, ctx.num_classes, ctx.grads, ctx.nlev = geom, num_classes, grads, nlev
         ctx.applied = None            # upstream factors already folded into ctx.grads (after the first backward)
         return losses[0], losses[1], losses[2], losses[3]
@@ -311,23 +311,23 @@ class HeadLossFunction(torch.autograd.Function):
     def backward(ctx, g_cls, g_bbox, g_iou, _g_np):
         grads = ctx.grads
         if grads is None:
-            return (None,) * (10 + 3 * ctx.nlev)
+            return (None,) * (11 + 3 * ctx.nlev)
         z = lambda g, ref: torch.zeros((), dtype=torch.float32, device=ref.device) if g is None else g.reshape(()).float()
         ref = grads[0][0]
         up = torch.stack([z(g_cls, ref), z(g_bbox, ref), z(g_iou, ref)])
         if ctx.applied is None:       # first backward: rescale the forward's buffers in place (no extra memory, no copy)
             scale_grads(ctx.geom, ctx.num_classes, grads, up)   # exits early on the device when upstream == (1,1,1)
             ctx.applied = up
-            return (None,) * 10 + tuple(grads[0]) + tuple(grads[1]) + tuple(grads[2])
+            return (None,) * 11 + tuple(grads[0]) + tuple(grads[1]) + tuple(grads[2])
         # re-entrant use (retain_graph=True, autograd.grad twice, checkpointing): the buffers already carry the first call's
         # factors and were handed out; return fresh tensors scaled by the ratio instead of compounding in place
         ratio = up / ctx.applied
         out = [[t * ratio[k] for t in grads[k]] for k in range(3)]
-        return (None,) * 10 + tuple(out[0]) + tuple(out[1]) + tuple(out[2])
+        return (None,) * 11 + tuple(out[0]) + tuple(out[1]) + tuple(out[2])
 
 
-def head_loss(geom, num_classes, cfg, cls, bbox, iou, gt_counts, gt_bboxes, gt_labels, idx, w, sync_group=None):
-    out = HeadLossFunction.apply(geom, num_classes, cfg, gt_counts, gt_bboxes, gt_labels, idx, w, sync_group, len(cls),
+def head_loss(geom, num_classes, cfg, cls, bbox, iou, gt_counts, gt_bboxes, gt_labels, idx, w, sync_group=None, weight_sums=None):
+    out = HeadLossFunction.apply(geom, num_classes, cfg, gt_counts, gt_bboxes, gt_labels, idx, w, sync_group, weight_sums, len(cls),
                                  *cls, *bbox, *iou)
     return dict(loss_cls=out[0], loss_bbox=out[1], loss_iou=out[2]), out[3]
 

@@ -72,6 +72,7 @@ class GraphedHotPath:
         self._graph = None
         self._stream = torch.cuda.Stream(device=self.dev)
         self._side = [torch.cuda.Stream(device=self.dev) for _ in range(2)]
+        self._wsum = torch.zeros((self.B,), dtype=torch.float64, device=self.dev)   # assignment -> loss: per-image weight sums
         with torch.cuda.device(self.dev):
             self._done = torch.cuda.Event()
         self.grads = None
@@ -139,9 +140,9 @@ class GraphedHotPath:
                                     positive_num=self.assigner.positive_num, balance_sample=self.assigner.balance_sample,
                                     adapt_positive_num=self.assigner.adapt_positive_num,
                                     multiply_samplepro_for_weight=self.assigner.multiply_sample_pro_for_weight,
-                                    gt_offsets=off)
+                                    gt_offsets=off, weight_sums=self._wsum)
         losses, grads = F.loss_fwd_bwd(self.geom, self.C, cls, bbox, iou, None, d["gt_bboxes"], d["gt_labels"], idx, w,
-                                       self.head.loss_cfg, gt_offsets=off)
+                                       self.head.loss_cfg, gt_offsets=off, weight_sums=self._wsum)
         if self.with_inference:
             main.wait_stream(s_det)
         return dict(losses=losses, grads=grads, dets=dets, labels=labels, num=num, idx=idx, w=w, consumed=consumed)

@@ -167,7 +167,11 @@ class RADetHead(nn.Module):
         dev = self.atss_cls.weight.device
         sd = torch.as_tensor([int(torch.as_tensor(s).reshape(-1)[0]) for s in seeds], dtype=torch.int64).to(dev, non_blocking=True)
         with torch.cuda.device(dev):
-            idx, w, consumed = self.assigner().assign_batch(shapes, gt_bboxes, mask_grids, seeds=sd)
+            wsum = torch.empty((len(shapes),), dtype=torch.float64, device=dev)
+            idx, w, consumed = self.assigner().assign_batch(shapes, gt_bboxes, mask_grids, seeds=sd, weight_sums=wsum)
+        # The per-image weight sums travel with the index tensor through the reference's loss() signature: with them the dense
+        # loss kernel does not wait for num_pos (functional.loss_fwd_bwd, weight_sums).
+        idx._radet_weight_sums = wsum
         return idx, w
 
     def forward_train(self, x, img_metas, gt_bboxes, gt_labels=None, points_to_gt_index=None, points_weight=None,
@@ -227,8 +231,9 @@ class RADetHead(nn.Module):
         group = None
         if self.sync_num_pos and torch.distributed.is_available() and torch.distributed.is_initialized():
             group = torch.distributed.group.WORLD
+        wsum = getattr(points_to_gt_index, "_radet_weight_sums", None) if idx is points_to_gt_index else None
         losses, _ = F.head_loss(self.geom, self.num_classes, self.loss_cfg, list(cls_scores), list(bbox_preds), list(iou_preds),
-                                counts, boxes, labels, idx, w, sync_group=group)
+                                counts, boxes, labels, idx, w, sync_group=group, weight_sums=wsum)
         return losses
 
     # ------------------------------------------------------------------ get_targets (radet_head.py:290-369)

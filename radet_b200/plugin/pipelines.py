@@ -106,11 +106,13 @@ class LabelAssignment:
         check_binary_grid(grid)
         return grid, gh, gw
 
-    def assign_batch(self, img_shapes, gt_bboxes_list, mask_grids, *, seeds=None, mt_states=None, uniforms=None):
+    def assign_batch(self, img_shapes, gt_bboxes_list, mask_grids, *, seeds=None, mt_states=None, uniforms=None, weight_sums=None):
         """Batched device entry point.  All images must share (H, W).
         gt_bboxes_list: list of np/torch [G_i,4]; mask_grids: list of uint8 [G_i, ceil(H/step), ceil(W/step)]
         (the stride-`step` sample grid, see `_mask_grid`).  Exactly one RNG source: seeds (np.random.seed per image),
         mt_states [B,625] (full legacy states, advanced in place) or uniforms [B,n].
+        weight_sums: optional CUDA float64 [B], written: per-image sum of the weights of the assigned points -- handed to the
+        loss (functional.loss_fwd_bwd(weight_sums=...)) it spares the dense pass the wait for num_pos.
         Returns device tensors points_to_gt_index [B,P] int64, points_weight [B,P] f32, consumed [B] int32."""
         dev = self._dev()
         H, W = int(img_shapes[0][0]), int(img_shapes[0][1])
@@ -131,7 +133,7 @@ class LabelAssignment:
         return F.assign(self.geom, shapes, counts, boxes, bits, (gh, gw), seeds=seeds, mt_states=mt_states, uniforms=uniforms,
                         positive_num=self.positive_num, balance_sample=self.balance_sample,
                         adapt_positive_num=self.adapt_positive_num,
-                        multiply_samplepro_for_weight=self.multiply_sample_pro_for_weight)
+                        multiply_samplepro_for_weight=self.multiply_sample_pro_for_weight, weight_sums=weight_sums)
 
     # ------------------------------------------------------------------ reference contract
     def __call__(self, results):

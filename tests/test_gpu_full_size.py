@@ -88,6 +88,15 @@ def test_full_batch_loss_vs_oracle(key):
     for mine, want in ((grads[0], o["grad_cls"]), (grads[1], o["grad_bbox"]), (grads[2], o["grad_iou"])):
         for a, r in zip(mine, want):
             np.testing.assert_allclose(a.cpu().numpy(), r, rtol=1e-4, atol=1e-6 * max(1e-30, float(np.abs(r).max())))
+    # dense-first order (per-image weight sums of the assignment handed over): the same bar against the oracle
+    l1, g1 = F.loss_fwd_bwd(GEOM, wl.C, cls, bbox, iou, counts, boxes, labels, idx, w, F.LossConfig(), weight_sums=_CACHE[key + "/wsum"])
+    l1 = l1.cpu().numpy()
+    for i, k in enumerate(("loss_cls", "loss_bbox", "loss_iou")):
+        assert abs(l1[i] - o[k]) <= 1e-5 * abs(o[k]), (key, k, l1[i], o[k])
+    assert l1[3] == o["num_pos"]
+    for mine, want in ((g1[0], o["grad_cls"]), (g1[1], o["grad_bbox"]), (g1[2], o["grad_iou"])):
+        for a, r in zip(mine, want):
+            np.testing.assert_allclose(a.cpu().numpy(), r, rtol=1e-4, atol=1e-6 * max(1e-30, float(np.abs(r).max())))
     # the experimental single-launch kernel agrees, with and without the assignment's per-image weight sums handed over
     from tests.test_gpu_parity import _fused_loss
     for kw in (dict(), dict(weight_sums=_CACHE[key + "/wsum"])):

@@ -1070,3 +1070,91 @@ def test_grid_priors_on_the_device():
         flags = ag.valid_flags(sizes, (H - 40, W - 90, 3), device=DEV)
         ref = ag.valid_flags(sizes, (H - 40, W - 90, 3), device="cpu")
         assert all(torch.equal(f.cpu(), r) for f, r in zip(flags, ref))
+
+
+def _weight_sums(idx_l, w_l, batch):
+    """What radet_assign(weight_sums=...) hands over: per image, the float64 sum of the weights of the points with index >= 0
+    (0 for an image without ground truth)."""
+    v = [float(w[i >= 0].astype(np.float64).sum()) if im.gt_bboxes.shape[0] > 0 else 0.0 for i, w, im in zip(idx_l, w_l, batch)]
+    return torch.tensor(v, dtype=torch.float64, device=DEV)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("key", ["small", "cfg1", "cfg3b2"])
+@pytest.mark.parametrize("hyper", [dict(), dict(gamma=1.5, alpha=0.4, w_cls=0.7, w_bbox=1.3, w_iou=0.9, eps=1e-5)])
+def test_loss_dense_first_order_vs_oracle(key, hyper):
+    """With the assignment's per-image weight sums the dense kernel runs FIRST and loss_pos_kernel follows as its programmatic
+    dependent (zero-fill / rescale of the regression planes, the three losses): same numbers as the oracle, upstream
+    gradient scales applied, forward-only calls and repeated calls on one workspace."""
+    wl, batch, idx_l, w_l, ho = _head_inputs(key)
+    cls, bbox, iou = _to_dev(ho)
+    counts, boxes, labels = _gt_dev(batch)
+    idx = torch.from_numpy(np.stack(idx_l)).to(DEV)
+    w = torch.from_numpy(np.stack(w_l)).to(DEV)
+    wsum = _weight_sums(idx_l, w_l, batch)
+    cfg = F.LossConfig(**hyper)
+    o = orc.head_loss(ho.cls, ho.bbox, ho.iou, [b.gt_bboxes for b in batch], [b.gt_labels for b in batch], idx_l, w_l, wl.C, wl.H, wl.W, **hyper)
+    for rep in range(2):
+        losses, grads = F.loss_fwd_bwd(GEOM, wl.C, cls, bbox, iou, counts, boxes, labels, idx, w, cfg, weight_sums=wsum)
+        losses = losses.cpu().numpy()
+        for i, k in enumerate(("loss_cls", "loss_bbox", "loss_iou")):
+            assert abs(losses[i] - o[k]) <= 1e-5 * abs(o[k]), (k, losses[i], o[k], rep)
+        assert losses[3] == o["num_pos"]
+        _check_grads(grads[0], o["grad_cls"], 1e-4, 1e-6)
+        _check_grads(grads[1], o["grad_bbox"], 1e-4, 1e-6)
+        _check_grads(grads[2], o["grad_iou"], 1e-4, 1e-6)
+    l2, g2 = F.loss_fwd_bwd(GEOM, wl.C, cls, bbox, iou, counts, boxes, labels, idx, w, cfg, weight_sums=wsum, want_grads=False)
+    assert g2 is None and np.array_equal(l2.cpu().numpy(), losses)
+    # the classic order (loss_pos_kernel first) gives the same losses to rounding and the same gradients
+    l3, g3 = F.loss_fwd_bwd(GEOM, wl.C, cls, bbox, iou, counts, boxes, labels, idx, w, cfg)
+    np.testing.assert_allclose(l3.cpu().numpy(), losses, rtol=2e-6)
+    for ga, gb in zip(grads, g3):
+        for a, b in zip(ga, gb):
+            np.testing.assert_allclose(a.cpu().numpy(), b.cpu().numpy(), rtol=2e-6, atol=1e-12)
+    # upstream gradients of the three losses
+    gs = torch.tensor([0.5, 2.0, 3.0], device=DEV)
+    _, g4 = F.loss_fwd_bwd(GEOM, wl.C, cls, bbox, iou, counts, boxes, labels, idx, w, cfg, weight_sums=wsum, grad_scale=gs)
+    for grp, base, k in zip(g4, grads, (0.5, 2.0, 3.0)):
+        for a, b in zip(grp, base):
+            np.testing.assert_allclose(a.cpu().numpy(), k * b.cpu().numpy(), rtol=2e-6, atol=1e-12)
+
+
+@pytest.mark.gpu
+def test_loss_dense_first_order_no_positive_branch_and_empty_image():
+    """num_pos == 0 (radet_head.py:279-281) and an image without ground truth, in the dense-first order."""
+    wl, batch, idx_l, w_l, ho = _head_inputs("small")
+    cls, bbox, iou = _to_dev(ho)
+    counts, boxes, labels = _gt_dev(batch)
+    idx0 = [np.where(i > 0, 0, i) for i in idx_l]          # positives -> ignored (still members of pos_inds)
+    w0 = [np.where(i >= 0, 0.0, w).astype(np.float32) for i, w in zip(idx0, w_l)]
+    losses, grads = F.loss_fwd_bwd(GEOM, wl.C, cls, bbox, iou, counts, boxes, labels, torch.from_numpy(np.stack(idx0)).to(DEV),
+                                   torch.from_numpy(np.stack(w0)).to(DEV), F.LossConfig(), weight_sums=_weight_sums(idx0, w0, batch))
+    o = orc.head_loss(ho.cls, ho.bbox, ho.iou, [b.gt_bboxes for b in batch], [b.gt_labels for b in batch], idx0, w0, wl.C, wl.H, wl.W)
+    losses = losses.cpu().numpy()
+    assert o["num_pos"] == 0 and losses[3] == 0
+    for i, k in enumerate(("loss_cls", "loss_bbox", "loss_iou")):
+        assert abs(losses[i] - o[k]) <= 1e-5 * abs(o[k]) + 1e-6, k
+    _check_grads(grads[1], o["grad_bbox"], 1e-5, 1e-7)
+    _check_grads(grads[2], o["grad_iou"], 1e-5, 1e-7)
+    _check_grads(grads[0], o["grad_cls"], 1e-4, 1e-6)
+    # last image without ground truth: its points keep index -1 / the oracle's weights, nothing of it is a positive
+    nb = len(batch)
+    gt_b = [b.gt_bboxes for b in batch[:-1]] + [np.zeros((0, 4), np.float32)]
+    gt_l = [b.gt_labels for b in batch[:-1]] + [np.zeros((0,), np.int64)]
+    idx1 = idx_l[:-1] + [np.full_like(idx_l[-1], -1)]
+    w1 = w_l[:-1] + [np.ones_like(w_l[-1])]
+    counts1 = [g.shape[0] for g in gt_b]
+    boxes1 = torch.from_numpy(np.concatenate(gt_b)).to(DEV)
+    labels1 = torch.from_numpy(np.concatenate(gt_l)).to(DEV)
+    ws1 = torch.tensor([float(w[i >= 0].astype(np.float64).sum()) if c > 0 else 0.0 for i, w, c in zip(idx1, w1, counts1)],
+                       dtype=torch.float64, device=DEV)
+    losses, grads = F.loss_fwd_bwd(GEOM, wl.C, cls, bbox, iou, counts1, boxes1, labels1, torch.from_numpy(np.stack(idx1)).to(DEV),
+                                   torch.from_numpy(np.stack(w1)).to(DEV), F.LossConfig(), weight_sums=ws1)
+    o = orc.head_loss(ho.cls, ho.bbox, ho.iou, gt_b, gt_l, idx1, w1, wl.C, wl.H, wl.W)
+    losses = losses.cpu().numpy()
+    for i, k in enumerate(("loss_cls", "loss_bbox", "loss_iou")):
+        assert abs(losses[i] - o[k]) <= 1e-5 * abs(o[k]), k
+    _check_grads(grads[0], o["grad_cls"], 1e-4, 1e-6)
+    _check_grads(grads[1], o["grad_bbox"], 1e-4, 1e-6)
+    _check_grads(grads[2], o["grad_iou"], 1e-4, 1e-6)
+    assert nb >= 2
