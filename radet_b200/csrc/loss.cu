@@ -641,7 +641,6 @@ loss_dense_tma_kernel(GridDev grid, TileTable tt, int nch /* class chunks per ti
 //     target / non-target selects, in packed fp32x2 arithmetic (FMUL2 / FFMA2 / FADD2): ~13 instructions per element
 //     instead of ~21;
 //   * single-warp CTAs need no block barrier anywhere and balance over the SMs at a granularity of 256 points.
-constexpr int kWPts = 256;
 constexpr int kWStages = 6;
 constexpr int kWPlanes = 2;
 struct WTable {
@@ -666,7 +665,7 @@ __device__ __forceinline__ float2 focal_fast2(float2 x, float2 wn, float2 wnk, f
   return __fmul2_rn(__fmul2_rn(wnk, u), h);
 }
 
-template <bool kGamma2, bool kHint>
+template <bool kGamma2, bool kHint, int kH /* float4 groups per lane and plane: an item is 128 * kH points */>
 __global__ void __launch_bounds__(32)
 loss_dense_w_kernel(GridDev grid, WTable tab, int nch, int cc, int B, int C, MapsDev maps, GradsDev grads,
                     const int* __restrict__ gt_offsets, const int64_t* __restrict__ gt_labels, const int64_t* __restrict__ pidx,
@@ -675,6 +674,7 @@ loss_dense_w_kernel(GridDev grid, WTable tab, int nch, int cc, int B, int C, Map
                     const double* __restrict__ num_pos_hint, PosList plist, unsigned long long* dbg) {
 #define WDBG(k) do { if (dbg && threadIdx.x == 0) { unsigned long long t__; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t__)); dbg[(size_t)blockIdx.x * 8 + (k)] = t__; } } while (0)
   WDBG(0);
+  constexpr int kWPts = 128 * kH;
   __shared__ __align__(128) float s_ring[kWStages][kWPlanes][kWPts];
   __shared__ __align__(8) uint64_t s_full[kWStages];
   const int lane = threadIdx.x;
@@ -732,17 +732,19 @@ loss_dense_w_kernel(GridDev grid, WTable tab, int nch, int cc, int B, int C, Map
   // per-lane setup: 8 points = half 0 at 4*lane, half 1 at 128 + 4*lane
   const int g0 = gt_offsets[b], G = gt_offsets[b + 1] - g0;
   const int64_t pb = (int64_t)b * P + grid.off[l] + q_warp;
-  const bool act[2] = {4 * lane < npts, 128 + 4 * lane < npts};
-  int lab[8];
-  float w8[8], wn[8], wnk[8];
+  bool act[kH];
+#pragma unroll
+  for (int h_ = 0; h_ < kH; ++h_) act[h_] = 128 * h_ + 4 * lane < npts;
+  int lab[4 * kH];
+  float w8[4 * kH], wn[4 * kH], wnk[4 * kH];
   unsigned lmask = 0u, posmask = 0u;
   // The index / weight loads go out BEFORE the ring's first bulk copies: all warps of the grid start together, and 12 KB of
   // prefetch per warp in front of these 3 KB would delay every warp's set-up by the time the prefetch takes (measured:
   // 5.4 us from CTA start to the first plane with the copies first).
-  longlong2 ia[2], ib[2];
-  float4 wv2[2];
+  longlong2 ia[kH], ib[kH];
+  float4 wv2[kH];
 #pragma unroll
-  for (int h_ = 0; h_ < 2; ++h_) {
+  for (int h_ = 0; h_ < kH; ++h_) {
     ia[h_] = ib[h_] = make_longlong2(-1, -1);
     wv2[h_] = make_float4(0.f, 0.f, 0.f, 0.f);
     if (act[h_]) {
@@ -752,12 +754,15 @@ loss_dense_w_kernel(GridDev grid, WTable tab, int nch, int cc, int B, int C, Map
       wv2[h_] = *reinterpret_cast<const float4*>(pw + o);
     }
   }
+  // the image's labels, one per lane (G <= 32): the index -> label step below is then a shuffle instead of a second
+  // dependent round trip behind the index loads
+  const int lab_lane = (G > 0 && G <= 32 && lane < G) ? (int)gt_labels[g0 + lane] : C;
   if (lane == 0) {
     const int n0 = min(kWStages, nst);
     for (int s_ = 0; s_ < n0; ++s_) issue_next((unsigned)s_);
   }
 #pragma unroll
-  for (int h_ = 0; h_ < 2; ++h_) {
+  for (int h_ = 0; h_ < kH; ++h_) {
     const int64_t v[4] = {ia[h_].x, ia[h_].y, ib[h_].x, ib[h_].y};
     const float w4[4] = {wv2[h_].x, wv2[h_].y, wv2[h_].z, wv2[h_].w};
 #pragma unroll
@@ -765,7 +770,17 @@ loss_dense_w_kernel(GridDev grid, WTable tab, int nch, int cc, int B, int C, Map
       const int k = 4 * h_ + i;
       const int ix = v[i] < 0 ? -1 : (int)(v[i] > (int64_t)G ? (int64_t)G : v[i]);
       if (ix >= 0) posmask |= 1u << k;
-      lab[k] = (int)label_of(ix, G, gt_labels + g0, C) - c0;                                  // relative to the chunk
+      int lb;
+      if (G <= 32) {                                                                            // warp-uniform
+        int kq = ix - 1;                                                                        // label_of(): python indexing of gt_labels
+        if (kq < 0) kq += G;
+        if (kq >= G) kq = G - 1;
+        lb = __shfl_sync(kFull, lab_lane, kq & 31);
+        if (G <= 0 || ix < 0) lb = C;
+      } else {
+        lb = (int)label_of(ix, G, gt_labels + g0, C);
+      }
+      lab[k] = lb - c0;                                                                         // relative to the chunk
       if (lab[k] >= 0 && lab[k] < cn) lmask |= 1u << lab[k];
       w8[k] = w4[i];
       wn[k] = (1.f - alpha) * w4[i];
@@ -775,7 +790,7 @@ loss_dense_w_kernel(GridDev grid, WTable tab, int nch, int cc, int B, int C, Map
   const double num_pos = kHint ? warp_sum_array(num_pos_hint, (unsigned)B, lane) : ws->norm[0];
   const float k_cls = gs_cls * cfg.w_cls / (float)(num_pos + (double)cfg.avg_extra);
 #pragma unroll
-  for (int k = 0; k < 8; ++k) wnk[k] = wn[k] * k_cls;
+  for (int k = 0; k < 4 * kH; ++k) wnk[k] = wn[k] * k_cls;
   float* dst0 = want_grad ? grads.cls[l] + ((int64_t)b * C + c0) * hw + q_warp + 4 * lane : nullptr;   // next plane to store
   WDBG(1);
   float2 ls2 = make_float2(0.f, 0.f);
@@ -790,29 +805,34 @@ loss_dense_w_kernel(GridDev grid, WTable tab, int nch, int cc, int B, int C, Map
     for (int p_ = 0; p_ < kWPlanes; ++p_) {
       const int c = s_ * kWPlanes + p_;
       if (c < cn) {                                                                            // warp-uniform
-        const float4 x0 = *reinterpret_cast<const float4*>(rp + p_ * kWPts);
-        const float4 x1 = *reinterpret_cast<const float4*>(rp + p_ * kWPts + 128);
-        float4 g0v, g1v;
+        float4 xv[kH], gv_[kH];
+#pragma unroll
+        for (int h_ = 0; h_ < kH; ++h_) xv[h_] = *reinterpret_cast<const float4*>(rp + p_ * kWPts + 128 * h_);
         if (kGamma2 && !__any_sync(kFull, (lmask >> c) & 1u)) {
           // no lane holds its target class in this plane: packed non-target path
-          float2 t;
-          t = focal_fast2(make_float2(x0.x, x0.y), make_float2(wn[0], wn[1]), make_float2(wnk[0], wnk[1]), ls2); g0v.x = t.x; g0v.y = t.y;
-          t = focal_fast2(make_float2(x0.z, x0.w), make_float2(wn[2], wn[3]), make_float2(wnk[2], wnk[3]), ls2); g0v.z = t.x; g0v.w = t.y;
-          t = focal_fast2(make_float2(x1.x, x1.y), make_float2(wn[4], wn[5]), make_float2(wnk[4], wnk[5]), ls2); g1v.x = t.x; g1v.y = t.y;
-          t = focal_fast2(make_float2(x1.z, x1.w), make_float2(wn[6], wn[7]), make_float2(wnk[6], wnk[7]), ls2); g1v.z = t.x; g1v.w = t.y;
+#pragma unroll
+          for (int h_ = 0; h_ < kH; ++h_) {
+            const int k = 4 * h_;
+            float2 t;
+            t = focal_fast2(make_float2(xv[h_].x, xv[h_].y), make_float2(wn[k], wn[k + 1]), make_float2(wnk[k], wnk[k + 1]), ls2);
+            gv_[h_].x = t.x; gv_[h_].y = t.y;
+            t = focal_fast2(make_float2(xv[h_].z, xv[h_].w), make_float2(wn[k + 2], wn[k + 3]), make_float2(wnk[k + 2], wnk[k + 3]), ls2);
+            gv_[h_].z = t.x; gv_[h_].w = t.y;
+          }
         } else {
-          g0v.x = focal_acc<kGamma2>(x0.x, lab[0] == c, alpha * w8[0], wn[0], k_cls, gamma, lsum);
-          g0v.y = focal_acc<kGamma2>(x0.y, lab[1] == c, alpha * w8[1], wn[1], k_cls, gamma, lsum);
-          g0v.z = focal_acc<kGamma2>(x0.z, lab[2] == c, alpha * w8[2], wn[2], k_cls, gamma, lsum);
-          g0v.w = focal_acc<kGamma2>(x0.w, lab[3] == c, alpha * w8[3], wn[3], k_cls, gamma, lsum);
-          g1v.x = focal_acc<kGamma2>(x1.x, lab[4] == c, alpha * w8[4], wn[4], k_cls, gamma, lsum);
-          g1v.y = focal_acc<kGamma2>(x1.y, lab[5] == c, alpha * w8[5], wn[5], k_cls, gamma, lsum);
-          g1v.z = focal_acc<kGamma2>(x1.z, lab[6] == c, alpha * w8[6], wn[6], k_cls, gamma, lsum);
-          g1v.w = focal_acc<kGamma2>(x1.w, lab[7] == c, alpha * w8[7], wn[7], k_cls, gamma, lsum);
+#pragma unroll
+          for (int h_ = 0; h_ < kH; ++h_) {
+            const int k = 4 * h_;
+            gv_[h_].x = focal_acc<kGamma2>(xv[h_].x, lab[k] == c, alpha * w8[k], wn[k], k_cls, gamma, lsum);
+            gv_[h_].y = focal_acc<kGamma2>(xv[h_].y, lab[k + 1] == c, alpha * w8[k + 1], wn[k + 1], k_cls, gamma, lsum);
+            gv_[h_].z = focal_acc<kGamma2>(xv[h_].z, lab[k + 2] == c, alpha * w8[k + 2], wn[k + 2], k_cls, gamma, lsum);
+            gv_[h_].w = focal_acc<kGamma2>(xv[h_].w, lab[k + 3] == c, alpha * w8[k + 3], wn[k + 3], k_cls, gamma, lsum);
+          }
         }
         if (dst0) {
-          if (act[0]) stg_stream4(dst0, g0v);
-          if (act[1]) stg_stream4(dst0 + 128, g1v);
+#pragma unroll
+          for (int h_ = 0; h_ < kH; ++h_)
+            if (act[h_]) stg_stream4(dst0 + 128 * h_, gv_[h_]);
           dst0 += hw;
         }
       }
@@ -832,25 +852,31 @@ loss_dense_w_kernel(GridDev grid, WTable tab, int nch, int cc, int B, int C, Map
   const double sum_wq = ws->norm[1];
   const bool has_pos = ws->norm[6] > 0.0;                                                     // radet_head.py:261
   if (kHint) {
-    // the positives' regression / IoU gradients: this item's share of loss_pos_kernel's list (all loads before the stores)
+    // the positives' regression / IoU gradients: this item's share of loss_pos_kernel's list.  The first entry is loaded
+    // speculatively, together with the list length and the normalisers (one round trip instead of two); whatever the
+    // slot holds is ignored when it lies beyond the length.
     if (want_grad) {
-      const float k_box = has_pos ? gs_box * cfg.w_bbox / (float)sum_wq : gs_box;
-      const float k_iou = has_pos ? gs_iou * cfg.w_iou / (float)num_pos : gs_iou;
       const int npos = (int)__ldcg(&ws->pad[0]);
-      for (int i = (int)it * 32 + lane; i < npos; i += (int)gridDim.x * 32) {
-        const int t = __ldcg(plist.plist + i);
+      for (int i = (int)it * 32 + lane; ; i += (int)gridDim.x * 32) {
+        const int il = min(i, B * P - 1);                   // the scratch has B * P slots (>= the list length)
+        const int t = __ldcg(plist.plist + il);
         float v[5];
 #pragma unroll
-        for (int k = 0; k < 5; ++k) v[k] = __ldcg(plist.pvals + (int64_t)i * 5 + k);
-        if (t < 0) continue;
-        const int tb = t / P, tp = t - tb * P;
-        const int tl = level_of(grid, tp);
-        const int tq = tp - grid.off[tl];
-        const int thw = grid.h[tl] * grid.w[tl];
-        float* gb = grads.bbox[tl] + (int64_t)tb * 4 * thw + tq;
+        for (int k = 0; k < 5; ++k) v[k] = __ldcg(plist.pvals + (int64_t)il * 5 + k);
+        if (i >= npos) break;
+        if (t >= 0) {
+          const float k_box = has_pos ? gs_box * cfg.w_bbox / (float)sum_wq : gs_box;
+          const float k_iou = has_pos ? gs_iou * cfg.w_iou / (float)num_pos : gs_iou;
+          const int tb = t / P, tp = t - tb * P;
+          const int tl = level_of(grid, tp);
+          const int tq = tp - grid.off[tl];
+          const int thw = grid.h[tl] * grid.w[tl];
+          float* gb = grads.bbox[tl] + (int64_t)tb * 4 * thw + tq;
 #pragma unroll
-        for (int k = 0; k < 4; ++k) gb[(int64_t)k * thw] = has_pos ? k_box * v[k] : gs_box;   // radet_head.py:280 when num_pos == 0
-        grads.iou[tl][(int64_t)tb * thw + tq] = has_pos ? k_iou * v[4] : gs_iou;               // :281
+          for (int k = 0; k < 4; ++k) gb[(int64_t)k * thw] = has_pos ? k_box * v[k] : gs_box;   // radet_head.py:280 when num_pos == 0
+          grads.iou[tl][(int64_t)tb * thw + tq] = has_pos ? k_iou * v[4] : gs_iou;               // :281
+        }
+        if (i + (int)gridDim.x * 32 >= npos) break;       // (keeps the next speculative slot inside the scratch)
       }
     }
   }
@@ -859,9 +885,9 @@ loss_dense_w_kernel(GridDev grid, WTable tab, int nch, int cc, int B, int C, Map
   if (!kHint && want_grad && ch == 0) {
     const float k_box = has_pos ? gs_box * cfg.w_bbox / (float)sum_wq : gs_box;
     const float k_iou = has_pos ? gs_iou * cfg.w_iou / (float)num_pos : gs_iou;
-    float gv[2][5][4];
+    float gv[kH][5][4];
 #pragma unroll
-    for (int h_ = 0; h_ < 2; ++h_) {
+    for (int h_ = 0; h_ < kH; ++h_) {
       const int q0 = q_warp + 128 * h_ + 4 * lane;
       const unsigned pm = (act[h_] && G > 0) ? (posmask >> (4 * h_)) & 15u : 0u;
 #pragma unroll
@@ -876,7 +902,7 @@ loss_dense_w_kernel(GridDev grid, WTable tab, int nch, int cc, int B, int C, Map
       }
     }
 #pragma unroll
-    for (int h_ = 0; h_ < 2; ++h_) {
+    for (int h_ = 0; h_ < kH; ++h_) {
       if (!act[h_]) continue;
       const int q0 = q_warp + 128 * h_ + 4 * lane;
 #pragma unroll
@@ -900,7 +926,30 @@ loss_dense_w_kernel(GridDev grid, WTable tab, int nch, int cc, int B, int C, Map
   WDBG(6);
   if (!last) return;
   __threadfence();
-  const double tot = warp_sum(strided_sum(partials, nblocks, (unsigned)lane, 32u));
+  // The partial sums come in through the (now idle) ring: one bulk copy per 1536 of them instead of a chain of L2 round trips
+  // (1632 items at the cfg5 shape were four dependent rounds of loads for one warp).  Fixed order: lane-strided inside a round,
+  // xor tree over the lanes, rounds in sequence.
+  asm volatile("fence.proxy.async;" ::: "memory");      // written through the generic proxy, read by the async proxy
+  double tot = 0.0;
+  constexpr unsigned kRound = kWStages * kWPlanes * kWPts / 2;
+  for (unsigned base = 0; base < nblocks; base += kRound) {
+    const unsigned cnt = min(kRound, nblocks - base);
+    const uint32_t nb = (cnt * 8u + 15u) & ~15u;        // the workspace pads the slots to 256 bytes
+    const uint32_t bar = full_s + slot * 8u;
+    if (lane == 0) {
+      mbar_expect_tx_s(bar, nb);
+      tma_bulk_g2s_s(ring_s, partials + base, nb, bar);
+    }
+    mbar_wait_s(bar, par);
+    const double* sp = reinterpret_cast<const double*>(&s_ring[0][0][0]);
+    double a = 0.0;
+    for (unsigned i = (unsigned)lane; i < cnt; i += 32u) a += sp[i];
+    tot += warp_sum(a);                                 // every lane's reads are consumed before the next round's copy is issued
+    if (++slot == kWStages) {
+      slot = 0;
+      par ^= 1u;
+    }
+  }
   if (lane == 0) {
     losses[0] = (float)((double)cfg.w_cls * tot / (num_pos + (double)cfg.avg_extra));           // radet_head.py:256-259
     losses[1] = has_pos ? (float)((double)cfg.w_bbox * ws->norm[2] / sum_wq) : (float)ws->norm[4];   // :269-274 / :280
@@ -1133,13 +1182,13 @@ static bool tile_plan(const GridDev& g, int B, int C, const void* pidx, const vo
 
 // Items of the warp-item dense kernel; false when it does not apply (a plane size that is not a multiple of 4, unaligned
 // index / weight arrays).
-static bool w_plan(const GridDev& g, int B, int C, const void* pidx, const void* pw, WTable* tab, int* nch, int* cc, int64_t* items) {
+static bool w_plan(const GridDev& g, int B, int C, const void* pidx, const void* pw, int pts, WTable* tab, int* nch, int* cc, int64_t* items) {
   if ((reinterpret_cast<uintptr_t>(pidx) | reinterpret_cast<uintptr_t>(pw)) & 15) return false;   // 128-bit index / weight loads
   int t = 0;
   for (int l = 0; l < g.num_levels; ++l) {
     const int hw = g.h[l] * g.w[l];
     if (hw & 3) return false;
-    tab->gpl[l] = (hw + kWPts - 1) / kWPts;
+    tab->gpl[l] = (hw + pts - 1) / pts;
     tab->goff[l] = t;
     t += tab->gpl[l];
   }
@@ -1153,6 +1202,10 @@ static bool w_plan(const GridDev& g, int B, int C, const void* pidx, const void*
     n = (kSMs + groups - 1) / groups;
     if (n > (C + 3) / 4) n = (C + 3) / 4;             // at least four planes per chunk
   }
+  if (const char* e = getenv("RADET_DENSE_CHUNKS")) { // development override
+    const long v = atol(e);
+    if (v >= n && v <= (C + 3) / 4) n = v;
+  }
   if (n < 1) n = 1;
   *cc = (int)((C + n - 1) / n);
   if (*cc > 32) *cc = 32;
@@ -1162,7 +1215,7 @@ static bool w_plan(const GridDev& g, int B, int C, const void* pidx, const void*
 }
 static int64_t w_items_bound(const GridDev& g, int B, int C) {      // partial-sum slots the workspace reserves
   int64_t t = 0;
-  for (int l = 0; l < g.num_levels; ++l) t += (g.h[l] * g.w[l] + kWPts - 1) / kWPts;
+  for (int l = 0; l < g.num_levels; ++l) t += (g.h[l] * g.w[l] + 127) / 128;
   const int64_t n = ((C + 31) / 32) > ((C + 3) / 4) ? (C + 31) / 32 : (C + 3) / 4;
   return (int64_t)B * t * n;
 }
@@ -1276,16 +1329,25 @@ extern "C" int radet_loss_fwd_bwd(const radet_grid_t* grid, int32_t batch, int32
   int wnch = 1, wcc = 1;
   int64_t witems = 0;
   static const bool pdl_on = !(getenv("RADET_LOSS_PDL") && getenv("RADET_LOSS_PDL")[0] == '0');
+  // Item size: 256 points (8 per lane) halves every per-plane overhead; 128 points doubles the warps per SM sub-partition
+  // (the streaming loop is latency-bound per warp).  RADET_DENSE_PTS = 128 | 256 overrides the choice.
+  int wpts = 256;
+  {
+    int64_t g256 = 0;
+    for (int l = 0; l < g.num_levels; ++l) g256 += (g.h[l] * g.w[l] + 255) / 256;
+    if (g256 * batch <= 8 * (int64_t)kSMs) wpts = 128;     // cfg2 / cfg3: 224 items of 256 points; cfg5: 1632
+  }
+  if (const char* e = getenv("RADET_DENSE_PTS")) wpts = atoi(e) == 128 ? 128 : 256;
   const bool w_ok = !(impl && (impl[0] == 'r' || impl[0] == 't' || impl[0] == 'f')) &&
-                    w_plan(g, batch, num_classes, points_to_gt_index, points_weight, &wtab, &wnch, &wcc, &witems);
+                    w_plan(g, batch, num_classes, points_to_gt_index, points_weight, wpts, &wtab, &wnch, &wcc, &witems);
   // Kernels that are meant to share an SM must agree on its shared-memory carve-out: an SM does not change the split while
   // CTAs are resident, so items of the dense kernel (12 KB each) could not join loss_pos CTAs running under a small carve-out.
   static const bool carve_set = [] {
     cudaFuncSetAttribute(loss_pos_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-    cudaFuncSetAttribute(loss_dense_w_kernel<true, true>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-    cudaFuncSetAttribute(loss_dense_w_kernel<false, true>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-    cudaFuncSetAttribute(loss_dense_w_kernel<true, false>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-    cudaFuncSetAttribute(loss_dense_w_kernel<false, false>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    for (auto k : {loss_dense_w_kernel<true, true, 2>, loss_dense_w_kernel<false, true, 2>, loss_dense_w_kernel<true, false, 2>,
+                   loss_dense_w_kernel<false, false, 2>, loss_dense_w_kernel<true, true, 1>, loss_dense_w_kernel<false, true, 1>,
+                   loss_dense_w_kernel<true, false, 1>, loss_dense_w_kernel<false, false, 1>})
+      cudaFuncSetAttribute(k, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
     return true;
   }();
   (void)carve_set;
@@ -1295,7 +1357,8 @@ extern "C" int radet_loss_fwd_bwd(const radet_grid_t* grid, int32_t batch, int32
                                                                   points_weight, *cfg, ws, pos_part, gd, pl,
                                                                   static_cast<unsigned long long*>(g_debug_buf));
     RADET_LAUNCH_CHECK();
-    auto kern = cfg->gamma == 2.0f ? loss_dense_w_kernel<true, true> : loss_dense_w_kernel<false, true>;
+    auto kern = cfg->gamma == 2.0f ? (wpts == 128 ? loss_dense_w_kernel<true, true, 1> : loss_dense_w_kernel<true, true, 2>)
+                                   : (wpts == 128 ? loss_dense_w_kernel<false, true, 1> : loss_dense_w_kernel<false, true, 2>);
     cudaError_t le = launch_after_trigger(kern, dim3((unsigned)witems), dim3(32), 0, st, true, g, wtab, wnch, wcc, batch, num_classes,
                                           md, gd, gt_offsets, gt_labels, points_to_gt_index, points_weight, *cfg, grad_scale, ws, dense_part,
                                           losses, cfg->weight_sums, pl, static_cast<unsigned long long*>(g_debug_buf));
@@ -1315,7 +1378,8 @@ extern "C" int radet_loss_fwd_bwd(const radet_grid_t* grid, int32_t batch, int32
     // and the imbalance costs more than the overlap gains (cfg5: 40.4 -> 42.5 us; cfg2: 27.8 -> 25.1 us).
     if (w_ok) {
       const bool prog = (phases == RADET_LOSS_PHASE_ALL) && pdl_on && witems <= 4 * (int64_t)kSMs;
-      auto kern = cfg->gamma == 2.0f ? loss_dense_w_kernel<true, false> : loss_dense_w_kernel<false, false>;
+      auto kern = cfg->gamma == 2.0f ? (wpts == 128 ? loss_dense_w_kernel<true, false, 1> : loss_dense_w_kernel<true, false, 2>)
+                                     : (wpts == 128 ? loss_dense_w_kernel<false, false, 1> : loss_dense_w_kernel<false, false, 2>);
       cudaError_t le = launch_after_trigger(kern, dim3((unsigned)witems), dim3(32), 0, st, prog, g, wtab, wnch, wcc, batch, num_classes,
                                             md, gd, gt_offsets, gt_labels, points_to_gt_index, points_weight, *cfg, grad_scale, ws, dense_part,
                                             losses, (const double*)nullptr, PosList{}, static_cast<unsigned long long*>(g_debug_buf));

@@ -1,0 +1,19 @@
+cd $GRAFT_REPO_ROOT; mkdir -p gpurun_out
+timeout 900 python -m pytest tests/test_gpu_parity.py tests/test_gpu_full_size.py -m gpu -x -q -k "loss or graphed or whole_path or full_size or full_batch_loss" > gpurun_out/r2_tests_w.txt 2>&1; tail -3 gpurun_out/r2_tests_v.txt
+for w in cfg5 cfg2 cfg3; do
+  LOSS_HINT=1 timeout 120 python scripts/loss_bench.py $w 200
+done 2>&1 | grep "^{" > gpurun_out/r2_loss_bench19.txt
+python - <<'PY'
+import json
+for l in open("gpurun_out/r2_loss_bench19.txt"):
+    d=json.loads(l); print(d["workload"], d["env"], round(d["us"],2), round(d["frac_of_6553.9"],3))
+PY
+for pts in 0; do
+RADET_DENSE_PTS=$pts python bench.py --no-side-configs --no-e2e --no-cpu-baseline > gpurun_out/r2_bench_n_$pts.json 2>gpurun_out/r2_bench_m.err
+done
+python - <<'PY'
+import json
+for ch in (0,):
+    d=json.loads(open(f"gpurun_out/r2_bench_n_{ch}.json").read().strip().splitlines()[-1])
+    print(ch, round(d["value"]), d["ms_per_step"], d["run"]["ms_per_step_one_in_flight"], {k:round(v,2) for k,v in d["stage_us"].items()}, round(d["roofline"]["frac"],4))
+PY
