@@ -295,6 +295,33 @@ int radet_get_candidates(const radet_grid_t* grid, int32_t batch, int32_t num_cl
 int radet_bbox2result(const float* dets, const int64_t* labels, const int32_t* num, int32_t batch, int32_t max_rows,
                       int32_t num_classes, int32_t xywh, float* out, int32_t* class_offsets, void* stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * Head-tower epilogues: what sits between the head's cuDNN convolutions and the path above.
+ *
+ * radet_gn_relu_forward / _backward replace GroupNorm(groups) + ReLU of every tower layer, ConvModule(conv3x3,
+ * norm_cfg=GN(32), act=ReLU) (models/dense_heads/atss_head.py:52-87, forward_single :133-138): statistics, normalise +
+ * affine and the ReLU in one launch each way (torch: F.group_norm + F.relu and their autograd backwards).
+ *   x, y, dy, dx   f32 [n, c, hw]  NCHW planes, contiguous
+ *   gamma, beta    f32 [c]         GroupNorm.weight / .bias (NULL = 1 / 0)
+ *   mean, rstd     f32 [n, groups] written by forward (biased variance, eps inside the root), read by backward
+ *   dgamma_nc, dbeta_nc  f32 [n, c]  optional: per-image sums; GroupNorm.weight.grad / .bias.grad are their sums over n
+ * backward recomputes the ReLU mask from x (y is not read); c / groups <= 64.
+ *
+ * radet_scale_relu_forward / _backward replace relu(Scale(x)) on the regression branch (atss_head.py:141-143 mmcv Scale,
+ * radet_head.py:27-30 F.relu): y = max(scale[0] * x, 0); dx = dy * scale * [scale x > 0]; dscale_partials f64
+ * [radet_scale_relu_partials(n)] = fixed-order partial sums of dy * x * [scale x > 0] (Scale.scale.grad is their sum).
+ *
+ * The sigmoid / score-threshold epilogue of the classification branch needs no entry: radet_get_bboxes consumes raw logits. */
+int radet_gn_relu_forward(const float* x, const float* gamma, const float* beta, int32_t n, int32_t c, int32_t hw, int32_t groups,
+                          float eps, float* y, float* mean, float* rstd, void* stream);
+int radet_gn_relu_backward(const float* dy, const float* x, const float* gamma, const float* beta, const float* mean,
+                           const float* rstd, int32_t n, int32_t c, int32_t hw, int32_t groups, float* dx, float* dgamma_nc,
+                           float* dbeta_nc, void* stream);
+int32_t radet_scale_relu_partials(int64_t n);
+int radet_scale_relu_forward(const float* x, const float* scale, int64_t n, float* y, void* stream);
+int radet_scale_relu_backward(const float* dy, const float* x, const float* scale, int64_t n, float* dx, double* dscale_partials,
+                              void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -75,6 +75,13 @@ _SIGS = {
     "radet_candidates_capacity": (c_int64, [POINTER(Grid), c_int32, c_int32]),
     "radet_get_candidates": (c_int32, [POINTER(Grid), c_int32, c_int32, POINTER(Maps), c_void_p, c_void_p, POINTER(DetectCfg),
                                        c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
+    "radet_gn_relu_forward": (c_int32, [c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_int32, c_int32, c_float, c_void_p, c_void_p,
+                                        c_void_p, c_void_p]),
+    "radet_gn_relu_backward": (c_int32, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_int32, c_int32,
+                                         c_void_p, c_void_p, c_void_p, c_void_p]),
+    "radet_scale_relu_partials": (c_int32, [c_int64]),
+    "radet_scale_relu_forward": (c_int32, [c_void_p, c_void_p, c_int64, c_void_p, c_void_p]),
+    "radet_scale_relu_backward": (c_int32, [c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_void_p]),
     "radet_get_bboxes": (c_int32, [POINTER(Grid), c_int32, c_int32, POINTER(Maps), c_void_p, c_void_p, POINTER(DetectCfg),
                                    c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
 }

@@ -12,7 +12,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB_DIR = os.path.join(HERE, "lib")
 LIB = os.path.join(LIB_DIR, "libradet_b200.so")
-SOURCES = ["capi.cu", "assign.cu", "loss.cu", "loss_fused.cu", "detect.cu", "nms_list.cu"]
+SOURCES = ["capi.cu", "assign.cu", "loss.cu", "loss_fused.cu", "detect.cu", "nms_list.cu", "tower.cu"]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-Xcompiler", "-fPIC",
          "--expt-relaxed-constexpr"]

@@ -575,3 +575,86 @@ def bbox2result_batch(dets: torch.Tensor, labels: torch.Tensor, num: torch.Tenso
     check(_lib.load().radet_bbox2result(_ptr(dets), _ptr(labels), _ptr(num), B, mx, num_classes, int(bool(xywh)), _ptr(out), _ptr(off),
                                         _stream()), "radet_bbox2result")
     return out, off
+
+
+# ------------------------------------------------------------------------------------------------ head-tower epilogues (f4)
+class _GnRelu(torch.autograd.Function):
+    """GroupNorm + ReLU of a tower layer (atss_head.py:52-87) in one launch each way (csrc/tower.cu)."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, groups, eps):
+        _require_cuda(x, "x")
+        if x.dtype != torch.float32 or x.dim() < 2:
+            raise RadetError("gn_relu: float32 [N, C, ...] expected")
+        x = x.contiguous()
+        N, C = int(x.shape[0]), int(x.shape[1])
+        hw = x.numel() // max(1, N * C)
+        if C % groups:
+            raise RadetError(f"gn_relu: {C} channels do not split into {groups} groups")
+        w = None if weight is None else weight.detach().contiguous().float()
+        b = None if bias is None else bias.detach().contiguous().float()
+        y = torch.empty_like(x)
+        mean = torch.empty((N, groups), dtype=torch.float32, device=x.device)
+        rstd = torch.empty_like(mean)
+        with torch.cuda.device(x.device):
+            check(_lib.load().radet_gn_relu_forward(_ptr(x), _ptr(w), _ptr(b), N, C, hw, groups, float(eps), _ptr(y), _ptr(mean), _ptr(rstd),
+                                                    _stream()), "radet_gn_relu_forward")
+        ctx.save_for_backward(x, w, b, mean, rstd)
+        ctx.groups, ctx.has = groups, (weight is not None, bias is not None)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, w, b, mean, rstd = ctx.saved_tensors
+        N, C = int(x.shape[0]), int(x.shape[1])
+        hw = x.numel() // max(1, N * C)
+        dy = dy.contiguous().float()
+        dx = torch.empty_like(x)
+        need_w, need_b = ctx.has[0] and ctx.needs_input_grad[1], ctx.has[1] and ctx.needs_input_grad[2]
+        dg = torch.empty((N, C), dtype=torch.float32, device=x.device) if need_w else None
+        db = torch.empty((N, C), dtype=torch.float32, device=x.device) if need_b else None
+        with torch.cuda.device(x.device):
+            check(_lib.load().radet_gn_relu_backward(_ptr(dy), _ptr(x), _ptr(w), _ptr(b), _ptr(mean), _ptr(rstd), N, C, hw, ctx.groups,
+                                                     _ptr(dx), _ptr(dg), _ptr(db), _stream()), "radet_gn_relu_backward")
+        return dx, (dg.sum(0) if need_w else None), (db.sum(0) if need_b else None), None, None
+
+
+def gn_relu(x: torch.Tensor, weight: Optional[torch.Tensor], bias: Optional[torch.Tensor], num_groups: int, eps: float = 1e-5):
+    """relu(group_norm(x, num_groups, weight, bias, eps)) fused (forward and backward one launch each)."""
+    return _GnRelu.apply(x, weight, bias, int(num_groups), float(eps))
+
+
+class _ScaleRelu(torch.autograd.Function):
+    """relu(scale * x): mmcv Scale + F.relu of the regression branch (atss_head.py:141-143, radet_head.py:27-30)."""
+
+    @staticmethod
+    def forward(ctx, x, scale):
+        _require_cuda(x, "x")
+        if x.dtype != torch.float32:
+            raise RadetError("scale_relu: float32 expected")
+        x = x.contiguous()
+        s = scale.detach().reshape(1).contiguous().float()
+        y = torch.empty_like(x)
+        with torch.cuda.device(x.device):
+            check(_lib.load().radet_scale_relu_forward(_ptr(x), _ptr(s), x.numel(), _ptr(y), _stream()), "radet_scale_relu_forward")
+        ctx.save_for_backward(x, s)
+        ctx.scale_shape = scale.shape
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, s = ctx.saved_tensors
+        dy = dy.contiguous().float()
+        dx = torch.empty_like(x)
+        lib = _lib.load()
+        part = torch.empty((max(1, lib.radet_scale_relu_partials(x.numel())),), dtype=torch.float64, device=x.device)
+        with torch.cuda.device(x.device):
+            check(lib.radet_scale_relu_backward(_ptr(dy), _ptr(x), _ptr(s), x.numel(), _ptr(dx), _ptr(part), _stream()),
+                  "radet_scale_relu_backward")
+        ds = part.sum().float().reshape(ctx.scale_shape) if x.numel() else torch.zeros(ctx.scale_shape, device=x.device)
+        return dx, ds
+
+
+def scale_relu(x: torch.Tensor, scale: torch.Tensor):
+    """relu(scale * x) fused, scale a one-element parameter (mmcv Scale)."""
+    return _ScaleRelu.apply(x, scale)

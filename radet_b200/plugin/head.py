@@ -43,6 +43,9 @@ class ConvModule(nn.Module):
     def forward(self, x):
         x = self.conv(x)
         if self.gn is not None:
+            if x.is_cuda and x.dtype == torch.float32 and x.shape[1] // self.gn.num_groups <= 64:
+                # GroupNorm + ReLU in one launch each way (csrc/tower.cu); the convolution stays cuDNN
+                return F.gn_relu(x, self.gn.weight, self.gn.bias, self.gn.num_groups, self.gn.eps)
             x = self.gn(x)
         return TF.relu(x, inplace=True)
 
@@ -145,7 +148,11 @@ class RADetHead(nn.Module):
         for reg_conv in self.reg_convs:
             reg_feat = reg_conv(reg_feat)
         cls_score = self.atss_cls(cls_feat)
-        bbox_pred = TF.relu(scale(self.atss_reg(reg_feat)).float())
+        reg = self.atss_reg(reg_feat)
+        if reg.is_cuda and reg.dtype == torch.float32:      # Scale + ReLU epilogue in one launch (csrc/tower.cu)
+            bbox_pred = F.scale_relu(reg, scale.scale)
+        else:
+            bbox_pred = TF.relu(scale(reg).float())
         iou_pred = self.atss_centerness(reg_feat)
         return cls_score, bbox_pred, iou_pred
 
