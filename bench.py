@@ -711,14 +711,12 @@ def main():
     peak_gbs = float(peaks.get("hbm_gbs", 6650.0))
     peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650 GB/s"
     traffic = None   # dram bytes per launch of the same kernel from the committed `ncu --set full` capture, if it matches this shape
-    for tj in ("r2_traffic.json", "r1_traffic.json"):
-        tj = os.path.join(ROOT, "profiles", tj)
-        if os.path.exists(tj) and wl.name.startswith("cfg2") and B == 8:
-            traffic = json.load(open(tj)).get("loss_dense_kernel@cfg2_B8")
-            break
+    tj = os.path.join(ROOT, "profiles", "r2b_traffic.json")
+    if os.path.exists(tj) and wl.name.startswith("cfg2") and B == 8:
+        traffic = json.load(open(tj)).get("loss_dense_w_kernel@cfg2_B8")
     loss_bytes = B * Ppts * (8 * wl.C + 52)
     ach = loss_bytes / (stage_us["loss_dense_kernel"] * 1e-6) / 1e9
-    roofline = {"bound": "hbm", "kernel": "loss_dense_kernel", "achieved": ach, "peak": peak_gbs, "unit": "GB/s", "frac": ach / peak_gbs,
+    roofline = {"bound": "hbm", "kernel": "loss_dense_w_kernel", "achieved": ach, "peak": peak_gbs, "unit": "GB/s", "frac": ach / peak_gbs,
                 "traffic": traffic, "peak_source": peak_src, "algorithmic_bytes_per_launch": loss_bytes,
                 "us_per_launch": stage_us["loss_dense_kernel"],
                 "note": f"(8C+52) B/point x {B * Ppts} points; at this batch the launch moves {loss_bytes / 1e6:.1f} MB "
@@ -926,7 +924,7 @@ def run_e2e(args, wl, B, host_sets, dev, P, F, world):
 
     # ---------------- graphed path
     gmax = max(int(im.gt_bboxes.shape[0]) for batch, _ in host_sets for im in batch)
-    NP = 3   # instances in flight: the H2D copy of batch i+1/i+2 overlaps the kernels and the D2H of batch i
+    NP = int(os.environ.get("RADET_E2E_INFLIGHT", "3"))   # instances in flight: the H2D copy of batch i+1/i+2 overlaps the kernels and the D2H of batch i
     pipes = [P.GraphedHotPath(head, la, B, (wl.H, wl.W), max_gt_per_image=max(32, gmax), device=dev).capture() for _ in range(NP)]
     arenas = []
     for batch, ho in host_sets:

@@ -37,6 +37,13 @@ for wl, fused in ((syn.Workload("s1", 480, 640, 30, 2, 40, 40, 3), False), (syn.
     losses, grads = F.loss_fwd_bwd(geom, wl.C, cls, bbox, iou, counts, boxes, labels, idx, w, F.LossConfig(), weight_sums=wsum if fused else None)
     losses, grads = F.loss_fwd_bwd(geom, wl.C, cls, bbox, iou, counts, boxes, labels, idx, w, F.LossConfig(gamma=1.5))
     os.environ.pop("RADET_LOSS_IMPL", None)
+    # the overlapped order (dense kernel as the programmatic dependent of loss_pos), general gamma, 256- and 128-point items
+    for pts in ("256", "128"):
+        os.environ["RADET_DENSE_PTS"] = pts
+        F.loss_fwd_bwd(geom, wl.C, cls, bbox, iou, counts, boxes, labels, idx, w, F.LossConfig(gamma=1.5), weight_sums=wsum)
+        F.loss_fwd_bwd(geom, wl.C, cls, bbox, iou, counts, boxes, labels, idx, w, F.LossConfig(), weight_sums=wsum)
+        F.loss_fwd_bwd(geom, wl.C, cls, bbox, iou, counts, boxes, labels, idx, w, F.LossConfig())
+    os.environ.pop("RADET_DENSE_PTS", None)
     F.scale_grads(geom, wl.C, grads, torch.tensor([2.0, 0.5, 1.0], device=dev))
     F.get_targets(geom, shapes, wl.C, counts, boxes, labels, idx, w)
     shp = torch.tensor([[wl.H, wl.W]] * len(batch), dtype=torch.int32, device=dev)
@@ -64,5 +71,13 @@ x = torch.randn(64, 7, device=dev, requires_grad=True)
 F.sigmoid_focal_loss_elementwise(x, torch.randint(0, 8, (64,), device=dev), 2.0, 0.25).sum().backward()
 F.giou_loss_elementwise(pri.clone().requires_grad_(), pri + 2, 1e-6).sum().backward()
 F.bce_with_logits_elementwise(torch.randn(50, device=dev, requires_grad=True), torch.rand(50, device=dev)).sum().backward()
+# head-tower epilogues (csrc/tower.cu): aligned and odd plane sizes, with and without affine parameters
+for shape, groups in (((2, 64, 12, 20), 32), ((2, 24, 7, 5), 4)):
+    xt = torch.randn(shape, device=dev, requires_grad=True)
+    wt = torch.randn(shape[1], device=dev, requires_grad=True)
+    bt = torch.randn(shape[1], device=dev, requires_grad=True)
+    F.gn_relu(xt, wt, bt, groups).sum().backward()
+    F.gn_relu(xt.detach().requires_grad_(), None, None, groups).sum().backward()
+    F.scale_relu(xt, torch.tensor(1.3, device=dev, requires_grad=True)).sum().backward()
 torch.cuda.synchronize()
 print("sanitize driver done")
