@@ -409,6 +409,7 @@ __host__ __device__ inline size_t resolve_smem_bytes(int maxG, int K, bool list_
   s += (size_t)maxG * K;                    // sel_cnt
   s += (size_t)maxG * 4;                    // n_sel
   s += (size_t)maxG * RADET_MAX_LEVELS * 4; // remaining candidates per (GT, level)
+  s += (size_t)maxG * 4;                    // running member count per GT (member positions, phase 3b)
   s = (s + 15) & ~size_t(15);
   if (list_in_smem) s += (size_t)kListCap * 4 + (size_t)kListCap * 2;
   return s;
@@ -442,6 +443,7 @@ assign_resolve_kernel(GridDev grid, const int* __restrict__ gt_offsets, const fl
   int* s_selpos = reinterpret_cast<int*>(cur); cur += (size_t)maxG * Kcap * 4;
   int* s_nsel = reinterpret_cast<int*>(cur); cur += (size_t)maxG * 4;
   int* s_lcnt = reinterpret_cast<int*>(cur); cur += (size_t)maxG * RADET_MAX_LEVELS * 4;   // remaining candidates per (GT, level)
+  int* s_run = reinterpret_cast<int*>(cur); cur += (size_t)maxG * 4;
   unsigned char* s_selcnt = cur; cur += (size_t)maxG * Kcap;
   cur = smem_raw + (((size_t)(cur - smem_raw) + 15) & ~size_t(15));
   uint32_t* list;
@@ -482,6 +484,7 @@ assign_resolve_kernel(GridDev grid, const int* __restrict__ gt_offsets, const fl
   MtStream ms{MtWarp{s_key, 624}, s_xbuf, 0, 0, false};
   MtWarp& mt = ms.mt;
   int M = 0;
+  const bool pack_pos = P < 65536;          // member positions ride in the upper half of the list entries (phase 3b)
   if (wid == 0) RESOLVE_DBG(0);
   if (wid == 0) {
     // ---- warp 0 (specialised): bring up the MT19937 state while the worker warps resolve the claiming.
@@ -777,17 +780,69 @@ assign_resolve_kernel(GridDev grid, const int* __restrict__ gt_offsets, const fl
       for (int i = lane; i < 624; i += 32) st[i] = s_key[i];
       if (lane == 0) st[624] = (uint32_t)ms.word_pos();
     }
+  } else if (wid == 1 && pack_pos) {
+    // 3b. (in the shadow of the sampling) the position of every member inside its GT's member list, in ascending point
+    //     order -- what choice() returns indices into (label_assignment.py:117-126).  One warp walks the list 32 entries at a
+    //     time with a running count per GT; the position rides in the upper half of the list entry (P < 65536).
+    for (int r = lane; r < G; r += 32) s_run[r] = 0;
+    __syncwarp();
+    for (int base = 0; base < M; base += 32) {
+      const int e = base + lane;
+      const int r = e < M ? (int)own[e] : 0xffff;
+      const unsigned peers = __match_any_sync(kFull, r);
+      if (r != 0xffff) {
+        const int before = s_run[r];
+        const int mpos = before + __popc(peers & ((1u << lane) - 1u));
+        list[e] = (list[e] & 0xffffu) | ((uint32_t)mpos << 16);
+        __syncwarp(peers);
+        if (lane == __ffs((int)peers) - 1) s_run[r] = before + __popc(peers);
+      }
+      __syncwarp();
+    }
   }
   __syncthreads();
-  // 5. one warp per GT: walk its members in ascending point order, selected -> positive, others -> ignore
+  // 5. selected -> positive, other members -> ignore (label_assignment.py:193-196)
+  if (pack_pos) {
+    // one thread per member: its position inside the GT's list was prepared in 3b
+    for (int e = tid; e < M; e += kResolveThreads) {
+      const int r = (int)own[e];
+      if (r == 0xffff) continue;
+      const uint32_t v = list[e];
+      const int p = (int)(v & 0xffffu), mpos = (int)(v >> 16);
+      const int nsel = s_nsel[r];
+      const int* selpos = s_selpos + r * Kcap;
+      const unsigned char* selcnt = s_selcnt + r * Kcap;
+      int cnt = nsel < 0 ? 1 : 0;
+      for (int j = 0; j < nsel; ++j)
+        if (selpos[j] == mpos) cnt = selcnt[j];
+      // multiply_sample_pro_for_weight (:127-128): binary masks give pro = 1 for a visible point, clip(min=1e-8) otherwise
+      // (a GT sampling from its fallback set has only such points)
+      const float pro = (mult && ((S->F[r >> 5] >> (r & 31)) & 1u)) ? 1e-8f : 1.0f;
+      idx[p] = cnt > 0 ? s_rank2gt[r] + 1 : 0;
+      wt[p] = __fmul_rn((float)cnt, pro);
+    }
+    if (weight_sums) {
+      // sum of the weights written for each GT, from the selection counts (the same terms as the member walk below adds;
+      // sums of <= 32 equal-scale float values are exact in fp64, so the order does not matter)
+      for (int r = tid; r < G; r += kResolveThreads) {
+        double wsum = 0.0;
+        if (s_nr[r] != 0) {
+          const float pro = (mult && ((S->F[r >> 5] >> (r & 31)) & 1u)) ? 1e-8f : 1.0f;
+          const int nsel = s_nsel[r];
+          if (nsel < 0) wsum = (double)s_nr[r] * (double)__fmul_rn(1.0f, pro);
+          for (int j = 0; j < nsel; ++j) wsum += (double)__fmul_rn((float)s_selcnt[r * Kcap + j], pro);
+        }
+        reinterpret_cast<double*>(s_xbuf)[r] = wsum;       // the sampling is over: its pre-tempered stream buffer is free
+      }
+    }
+  } else {
+  // (P >= 65536) one warp per GT: walk its members in ascending point order
   for (int r = wid; r < G; r += kResolveThreads / 32) {
     if (s_nr[r] == 0) continue;
     const int gt1 = s_rank2gt[r] + 1;
     const int nsel = s_nsel[r];
     const int* selpos = s_selpos + r * Kcap;
     const unsigned char* selcnt = s_selcnt + r * Kcap;
-    // multiply_sample_pro_for_weight (:127-128): binary masks give pro = 1 for a visible point, clip(min=1e-8) otherwise
-    // (a GT sampling from its fallback set has only such points)
     const float pro = (mult && ((S->F[r >> 5] >> (r & 31)) & 1u)) ? 1e-8f : 1.0f;
     int running = 0;
     double wsum = 0.0;                                    // sum of the weights written for this GT (weight_sums)
@@ -813,6 +868,7 @@ assign_resolve_kernel(GridDev grid, const int* __restrict__ gt_offsets, const fl
       wsum = warp_sum(wsum);
       if (lane == 0) reinterpret_cast<double*>(s_xbuf)[r] = wsum;
     }
+  }
   }
   if (weight_sums) {
     __syncthreads();
