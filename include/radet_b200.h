@@ -183,8 +183,11 @@ typedef struct {
   float avg_extra;                    /* num_imgs */
   /* Optional (NULL = compute it): per-image sum of points_weight over the points with points_to_gt_index >= 0 in images
    * that have ground truth, double[batch] on the device -- what radet_assign(weight_sums=...) writes next to the
-   * assignment.  num_pos (radet_head.py:254) is the sum of these; with it the dense pass does not have to wait for
-   * its own reduction over the index / weight arrays.  Must match the arrays passed; ignored unless phases == 3. */
+   * assignment.  num_pos (radet_head.py:254) is the sum of these; with it the dense pass does not have to wait for the
+   * reduction over the index / weight arrays: the dense kernel is launched as a programmatic dependent of the sparse one and
+   * streams its class planes next to it.  Must belong to the arrays passed: the kernel compares the sum with its own
+   * reduction at the end and writes NaN into the three losses when they disagree (relative 1e-5).  Ignored unless
+   * phases == 3 and every level's h*w is a multiple of 4. */
   const double* weight_sums;
 } radet_loss_cfg_t;
 /* phases: RADET_LOSS_PHASE_NORMALIZERS computes num_pos / sum(wq) into workspace doubles [0] and [1];

@@ -1122,7 +1122,7 @@ def test_loss_dense_first_order_vs_oracle(key, hyper):
 @pytest.mark.gpu
 def test_loss_dense_first_order_no_positive_branch_and_empty_image():
     """num_pos == 0 (radet_head.py:279-281) and an image without ground truth, in the dense-first order."""
-    wl, batch, idx_l, w_l, ho = _head_inputs("small")
+    wl, batch, idx_l, w_l, ho = _head_inputs("cfg1")   # 640x480: every level h*w % 4 == 0, so the overlapped order runs
     cls, bbox, iou = _to_dev(ho)
     counts, boxes, labels = _gt_dev(batch)
     idx0 = [np.where(i > 0, 0, i) for i in idx_l]          # positives -> ignored (still members of pos_inds)
@@ -1158,3 +1158,21 @@ def test_loss_dense_first_order_no_positive_branch_and_empty_image():
     _check_grads(grads[1], o["grad_bbox"], 1e-4, 1e-6)
     _check_grads(grads[2], o["grad_iou"], 1e-4, 1e-6)
     assert nb >= 2
+
+
+@pytest.mark.gpu
+def test_loss_weight_sums_that_do_not_belong_to_the_weights_are_reported():
+    """radet_loss_cfg_t.weight_sums must be the sums of the weights passed: a mismatch must not pass silently (NaN losses)."""
+    wl, batch, idx_l, w_l, ho = _head_inputs("cfg1")   # 640x480: the overlapped order applies (h*w % 4 == 0 on every level)
+    cls, bbox, iou = _to_dev(ho)
+    counts, boxes, labels = _gt_dev(batch)
+    idx = torch.from_numpy(np.stack(idx_l)).to(DEV)
+    w = torch.from_numpy(np.stack(w_l)).to(DEV)
+    good = _weight_sums(idx_l, w_l, batch)
+    l_ok, _ = F.loss_fwd_bwd(GEOM, wl.C, cls, bbox, iou, counts, boxes, labels, idx, w, F.LossConfig(), weight_sums=good)
+    assert torch.isfinite(l_ok).all()
+    l_bad, _ = F.loss_fwd_bwd(GEOM, wl.C, cls, bbox, iou, counts, boxes, labels, idx, w, F.LossConfig(), weight_sums=good * 1.01)
+    assert torch.isnan(l_bad[:3]).all()
+    # and the workspace is usable afterwards
+    l_again, _ = F.loss_fwd_bwd(GEOM, wl.C, cls, bbox, iou, counts, boxes, labels, idx, w, F.LossConfig(), weight_sums=good)
+    assert torch.equal(l_again, l_ok)
