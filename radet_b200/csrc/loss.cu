@@ -5,14 +5,17 @@
 // The reference flattens NCHW -> (point, channel) with permute+reshape+cat, materialises labels / bbox targets /
 // anchors and runs ~80 eager kernels forward plus autograd backward.  Here:
 //
-//   loss_pos_kernel    one pass over (image, point): the sparse positive terms (IoU target, GIoU, BCE) and the
-//                      normalisers num_pos = sum w, sum wq.  Deterministic two-level reduction (block partials in
-//                      fixed order, last block finalises).  ~12 B/point of traffic.
-//   loss_dense_kernel  the HBM-bound pass: reads every logit once IN PLACE (NCHW planes, 128-bit streaming loads,
-//                      4 consecutive points per thread), computes sigmoid-focal loss and its gradient with the final
-//                      normaliser already applied, writes the gradient once (128-bit stores); the threads of class
-//                      chunk 0 also emit the bbox / iou gradients of their 4 points.  Labels and TBLR targets are
-//                      rebuilt on the fly from points_to_gt_index (no label / target / anchor tensors).
+//   loss_pos_kernel      one pass over (image, point): the sparse positive terms (IoU target, GIoU, BCE), their gradients, and
+//                        the normalisers num_pos = sum w, sum wq.  Deterministic two-level reduction (block partials in
+//                        fixed order, last block finalises).  ~12 B/point of traffic.
+//   loss_dense_w_kernel  the HBM-bound pass (default): one warp per item of 128 / 256 points streams the class planes IN PLACE
+//                        (NCHW) through a TMA-fed shared-memory ring, computes sigmoid-focal loss and its gradient with the
+//                        final normaliser already applied and writes the gradient once (128-bit streaming stores).  Labels
+//                        and TBLR targets are rebuilt on the fly from points_to_gt_index (no label / target / anchor
+//                        tensors).  Launched as the programmatic dependent of loss_pos_kernel: with the assignment's
+//                        per-image weight sums it runs NEXT to it ("overlapped" order, radet_loss_fwd_bwd).
+//   loss_dense_tma_kernel / loss_dense_kernel   the round-2 / round-1 predecessors (4-warp TMA tiles; register-pipelined
+//                        loads): the latter serves plane sizes that are not multiples of 4, the former RADET_LOSS_IMPL=tma.
 //
 // Algorithmic traffic: (8C + 52) B/point  (C logits read + C grads written + 16 B bbox + 4 B iou read, 20 B grads
 // written, 8 B index + 4 B weight read).
