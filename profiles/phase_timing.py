@@ -37,6 +37,16 @@ for k, n in enumerate(names):
 print("  total   %10.0f %10.0f" % ((d[:, 6] - d[:, 0]).mean(), (d[:, 6] - d[:, 0]).max()))
 print("  span of all CTAs (first start .. last end): %d cycles" % (d[:, 6].max() - d[:, 0].min()))
 
+L = len(shapes)
+print("detect_bin per (image 0, level): cycles load | select | slots | emit")
+for l in range(L):
+    r = d[0 * L + l, 10:15]
+    print("  level %d: %s" % (l, " ".join("%6d" % v for v in np.diff(r))))
+print("detect_rank per image: cycles load | select")
+for b_ in range(min(B, 4)):
+    r = d[64 + b_, 10:13]
+    print("  image %d: %s" % (b_, " ".join("%6d" % v for v in np.diff(r))))
+
 # ---- assign_resolve_kernel phases
 dbg2 = torch.zeros((B, 16), dtype=torch.int64, device=dev)
 seeds = torch.tensor([im.seed for im in batch], dtype=torch.int32, device=dev)

@@ -387,6 +387,23 @@ __device__ __forceinline__ int cdf_search(double x, int m) {
   return t;
 }
 
+// Out-of-line copies for the sampling fast path: warp 0 runs it alone, one dependent instruction after the other, so
+// what it costs is the number of instructions fetched -- the rare branches must not sit in the loop body.
+__device__ __noinline__ int cdf_search_slow(unsigned long long X, int m) { return cdf_search((double)X / 9007199254740992.0, m); }
+struct StreamRefill {
+  unsigned long long X;
+  int xi, nx;
+};
+// the draw that crosses the end of the current 624-word block: regenerate, re-buffer, take the rest from the new block
+__device__ __noinline__ StreamRefill stream_draw_slow(uint32_t* key, unsigned long long* xbuf, int xi, int nx, int count, int lane) {
+  MtStream ms{MtWarp{key, 624 - 2 * nx}, xbuf, nx, xi, true};
+  StreamRefill r;
+  r.X = ms.draw53(count, lane);
+  r.xi = ms.xi;
+  r.nx = ms.nx;
+  return r;
+}
+
 struct ResolveSmem {
   // fixed part; dynamic arrays follow (see resolve_smem_bytes)
   uint32_t F[8], A[8];
@@ -416,7 +433,7 @@ __host__ __device__ inline size_t resolve_smem_bytes(int maxG, int K, bool list_
 }
 
 template <int W32>
-__global__ void __launch_bounds__(kResolveThreads)
+__global__ void __maxnreg__(96)
 assign_resolve_kernel(GridDev grid, const int* __restrict__ gt_offsets, const float* __restrict__ gt_bboxes,
                       const uint32_t* __restrict__ pair_bits, int maxG, int Kcap /* smem stride, <= 32 */, int Kbase /* positive_num */,
                       int flags /* RADET_ASSIGN_* */,
@@ -682,7 +699,120 @@ assign_resolve_kernel(GridDev grid, const int* __restrict__ gt_offsets, const fl
       return X;
     };
     auto search = [&](unsigned long long X, int m) -> int { return (X >> 63) ? cdf_search(ux, m) : cdf_search53(X, m); };
-    for (int r = 0; r < G && !overflow; ++r) {
+    const bool tight = !ub && !adapt && ms.fast;
+    if (tight) {
+      // The usual configuration (MT19937 stream buffered in s_xbuf, fixed positive_num).  Warp 0 runs this alone, one
+      // dependent instruction after the other, and on this machine every warp-wide primitive is 30-40 cycles of latency
+      // (SHFL 38, VOTE 33, POPC 29, FLO/BREV 29 each, LDS 40; MATCH.ANY ~95 + 6 per distinct value: scripts/ubench/warp_lat.cu),
+      // so the loop is written to keep them off the critical path: the uniforms of the NEXT draw are fetched as soon as the
+      // stream position is known (the next draw starts there whether it is this GT's next round or the next GT's first),
+      // the next GT's first search runs in the shadow of this GT's MATCH, a round without collisions ends on a mask
+      // compare instead of a population count, the lowest-peer test needs no FLO, and the (f, g) bookkeeping of the
+      // later rounds reads its operands as shared-memory broadcasts instead of a chain of shuffles.
+      const int K = Kbase;
+      const unsigned lt = (1u << lane) - 1u, fullK = K >= 32 ? 0xffffffffu : (1u << K) - 1u;
+      int* s_g = S->found;
+      int xi = ms.xi, nx = ms.nx;
+      auto search_t = [&](unsigned long long X, int m) -> int {
+        const unsigned long long hi = __umul64hi(X << 11, (unsigned long long)m);   // floor(X*m / 2^53), see cdf_search53
+        const unsigned long long lo = (X << 11) * (unsigned long long)m;
+        const unsigned long long R = (0ull - lo) >> 11;
+        int t = (int)hi;
+        if (lo != 0ull && R <= (unsigned long long)m) t = cdf_search_slow(X, m);
+        return t;
+      };
+      unsigned long long Xc = s_xbuf[min(xi + lane, 311)];     // uniforms at the current stream position
+      // consumes `count` uniforms: returns them (lane i < count holds the i-th) and prefetches the following ones
+      auto draw_t = [&](int count, bool* refilled) -> unsigned long long {
+        unsigned long long X = Xc;
+        *refilled = false;
+        if (xi + count > nx) {                                  // crosses the end of the 624-word block
+          const StreamRefill rf = stream_draw_slow(s_key, s_xbuf, xi, nx, count, lane);
+          X = rf.X;
+          xi = rf.xi;
+          nx = rf.nx;
+          *refilled = true;
+        } else {
+          xi += count;
+        }
+        used += count;
+        Xc = s_xbuf[min(xi + lane, 311)];
+        return X;
+      };
+      int n_next = s_nr[0];
+      int t_spec = search_t(Xc, n_next);                        // first search of the next GT that draws
+#pragma unroll 1
+      for (int r = 0; r < G; ++r) {
+        const int n = n_next;
+        n_next = r + 1 < G ? s_nr[r + 1] : 0;
+        if (n == 0 || (n < K && !balance)) {                    // label_assignment.py:182-183 no RNG use; :116 chosen = arange(n)
+          if (n != 0 && lane == 0) s_nsel[r] = -1;
+          t_spec = search_t(Xc, n_next);
+          continue;
+        }
+        int* selpos = s_selpos + r * Kcap;
+        unsigned char* selcnt = s_selcnt + r * Kcap;
+        bool refilled;
+        const unsigned long long x = draw_t(K, &refilled);
+        const int t = refilled ? search_t(x, n) : t_spec;
+        const int pos = lane < K ? t : -1;
+        const unsigned peers = __match_any_sync(kFull, pos);    // idle lanes all hold -1
+        t_spec = search_t(Xc, n_next);                          // in the shadow of the MATCH
+        const bool first = lane < K && (peers & lt) == 0u;
+        const unsigned fm = __ballot_sync(kFull, first);
+        if (n < K) {                                            // :112 choice(n, K, p, replace=True); np.unique(return_counts), :125
+          if (first) {
+            const int slot = __popc(fm & lt);
+            selpos[slot] = pos;
+            selcnt[slot] = (unsigned char)__popc(peers);
+          }
+          if (lane == 0) s_nsel[r] = __popc(fm);
+          continue;
+        }
+        // :119 choice(n, K, p, replace=False); see the general loop below for the (f, g) bookkeeping
+        if (fm == fullK) {                                      // no collision: done after one round
+          if (lane < K) {
+            selpos[lane] = pos;
+            selcnt[lane] = 1;
+          }
+          if (lane == 0) s_nsel[r] = K;
+          continue;
+        }
+        if (first) selpos[__popc(fm & lt)] = pos;
+        int n_uniq = __popc(fm);
+#pragma unroll 1
+        while (true) {
+          __syncwarp();
+          const int f = lane < n_uniq ? selpos[lane] : 0x7fffffff;
+          int rk = 0;
+#pragma unroll 4
+          for (int j = 0; j < n_uniq; ++j) rk += selpos[j] < f ? 1 : 0;
+          s_g[lane] = lane < n_uniq ? f - rk : 0x7fffffff;
+          __syncwarp();
+          const int d = K - n_uniq, m = n - n_uniq;
+          const unsigned long long x2 = draw_t(d, &refilled);
+          const int t2 = search_t(x2, m);                       // idle lanes: result unused
+          int c = 0;
+#pragma unroll 4
+          for (int j = 0; j < n_uniq; ++j) c += s_g[j] <= t2 ? 1 : 0;
+          const int pos2 = lane < d ? t2 + c : -1;
+          const unsigned peers2 = __match_any_sync(kFull, pos2);
+          const bool first2 = lane < d && (peers2 & lt) == 0u;
+          const unsigned fm2 = __ballot_sync(kFull, first2);
+          if (first2) selpos[n_uniq + __popc(fm2 & lt)] = pos2;
+          n_uniq += __popc(fm2);
+          if (n_uniq >= K) break;
+        }
+        if (lane < K) selcnt[lane] = 1;
+        if (lane == 0) s_nsel[r] = K;
+        t_spec = search_t(Xc, n_next);
+      }
+      ms.xi = xi;
+      ms.nx = nx;
+      ms.mt.pos = 624 - 2 * nx;
+      __syncwarp();
+    }
+    for (int r = 0; r < G && !overflow && !tight; ++r) {
       const int n = s_nr[r];
       if (n == 0) continue;                                         // label_assignment.py:182-183: no RNG use
       int K = Kbase;

@@ -163,54 +163,146 @@ detect_select_kernel(GridDev grid, SelPlan plan, int C, MapsDev maps, float thr,
 
 // ------------------------------------------------------------------------------------------------ 2. top-k + binning
 constexpr int kBinThreads = 512;
+constexpr int kBinNK = 12;   // keys a thread keeps in registers: levels with <= 6144 candidates read them from memory once
 
-// k-th largest of `n` unique 64-bit keys (k >= 1): returns the smallest key to keep.  Block-wide, 8-bit radix passes
-// from the top; stops as soon as the selected bucket is needed entirely.
-__device__ u64 radix_select_kth(const u64* __restrict__ src, int n, int k, int* s_hist, int* s_misc) {
-  u64 prefix = 0ull, pmask = 0ull;
-  const int tid = threadIdx.x, nt = blockDim.x, lane = tid & 31;
-  for (int shift = 56; shift >= 0; shift -= 8) {
-    for (int i = tid; i < 256; i += nt) s_hist[i] = 0;
-    __syncthreads();
-    for (int i = tid; i < n; i += nt) {
-      const u64 key = src[i];
-      if ((key & pmask) == prefix) atomicAdd(&s_hist[(int)((key >> shift) & 0xffull)], 1);
-    }
-    __syncthreads();
-    if (tid < 32) {  // suffix sums over 256 bins: lane holds bins [8*lane, 8*lane+8)
-      int h[8], s = 0;
+// A CTA's view of `n` 64-bit keys: thread t keeps keys t, t + T, ..., t + (NK-1) T in registers (one batch of
+// independent loads); keys beyond NK * T are re-read from global memory, eight loads in flight per thread.  Every sweep
+// below used to be a chain of dependent load -> shared-memory-atomic iterations (~10 round trips to L2 per sweep on the
+// finest level); from registers a sweep costs a few hundred cycles.
+template <int NK>
+struct KeyCache {
+  u64 r[NK];
+  const u64* src;
+  int n;
+  __device__ __forceinline__ void load(const u64* s, int n_) {
+    src = s;
+    n = n_;
 #pragma unroll
-      for (int q = 0; q < 8; ++q) {
-        h[q] = s_hist[8 * lane + q];
-        s += h[q];
-      }
-      int suf = s;  // inclusive suffix over lanes >= lane
+    for (int j = 0; j < NK; ++j) {
+      const int i = (int)threadIdx.x + j * (int)blockDim.x;
+      r[j] = i < n ? src[i] : 0ull;
+    }
+  }
+  // f(key, valid) for every key slot of this thread; all threads of the CTA make the same number of calls, so f may
+  // use full-warp collectives.
+  template <typename F>
+  __device__ __forceinline__ void each(F&& f) const {
+    const int T = (int)blockDim.x;
 #pragma unroll
-      for (int o = 1; o < 32; o <<= 1) {
-        const int t = __shfl_down_sync(kFull, suf, o);
-        if (lane + o < 32) suf += t;
+    for (int j = 0; j < NK; ++j) f(r[j], (int)threadIdx.x + j * T < n);
+    for (int base = NK * T; base < n; base += 8 * T) {
+      u64 t[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        const int i = base + u * T + (int)threadIdx.x;
+        t[u] = i < n ? src[i] : 0ull;
       }
-      const int above = suf - s;  // elements in bins of higher lanes
-      if (above < k && k <= suf) {
-        int acc = above, bin = 7;
-        for (; bin > 0; --bin) {
-          if (acc + h[bin] >= k) break;
-          acc += h[bin];
-        }
-        s_misc[0] = 8 * lane + bin;
-        s_misc[1] = k - acc;      // rank inside the bucket
-        s_misc[2] = h[bin];       // bucket population
+#pragma unroll
+      for (int u = 0; u < 8; ++u) f(t[u], base + u * T + (int)threadIdx.x < n);
+    }
+  }
+};
+
+// Common leading bits of the view's keys: (AND of all keys, OR of all keys), block-wide.  s_red: 128 unsigned.  One barrier.
+template <int NK>
+__device__ __forceinline__ void key_and_or(const KeyCache<NK>& kc, unsigned* s_red, u64* and_out, u64* or_out) {
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5, nw = (int)blockDim.x >> 5;
+  u64 a = ~0ull, o = 0ull;
+  kc.each([&](u64 key, bool v) {
+    if (v) {
+      a &= key;
+      o |= key;
+    }
+  });
+  const unsigned alo = __reduce_and_sync(kFull, (unsigned)a), ahi = __reduce_and_sync(kFull, (unsigned)(a >> 32));
+  const unsigned olo = __reduce_or_sync(kFull, (unsigned)o), ohi = __reduce_or_sync(kFull, (unsigned)(o >> 32));
+  if (lane == 0) {
+    s_red[wid] = alo;
+    s_red[32 + wid] = ahi;
+    s_red[64 + wid] = olo;
+    s_red[96 + wid] = ohi;
+  }
+  __syncthreads();
+  const unsigned xa = lane < nw ? s_red[lane] : 0xffffffffu, xb = lane < nw ? s_red[32 + lane] : 0xffffffffu;
+  const unsigned xc = lane < nw ? s_red[64 + lane] : 0u, xd = lane < nw ? s_red[96 + lane] : 0u;
+  *and_out = ((u64)__reduce_and_sync(kFull, xb) << 32) | (u64)__reduce_and_sync(kFull, xa);
+  *or_out = ((u64)__reduce_or_sync(kFull, xd) << 32) | (u64)__reduce_or_sync(kFull, xc);
+}
+
+// k-th largest of the view's unique 64-bit keys (1 <= k <= n): returns the smallest key to keep.  8-bit radix passes over
+// a shared-memory histogram that start right below the bits all keys have in common (scores above a threshold share their
+// top byte) and stop as soon as the selected bucket is needed entirely.  One block barrier per pass: the histograms rotate
+// through three buffers and every warp does the 256-bin suffix scan itself.  The increments compile to ATOMS.POPC.INC
+// (lanes of a warp that hit the same bin are added in one operation).  s_hist: 3 * 256 ints, s_red: 128 unsigned.
+// (Measured and dropped: 4-bit passes counted in packed register fields + REDUX instead of shared-memory atomics --
+// 20 k cycles instead of 7.4 k on the finest level of the bench workload; MATCH.ANY-aggregated increments -- slower too.)
+template <int NK>
+__device__ u64 radix_select_kth(const KeyCache<NK>& kc, int k, int* s_hist, unsigned* s_red) {
+  const int tid = threadIdx.x, lane = tid & 31;
+  u64 a, o;
+  for (int i = tid; i < 256; i += (int)blockDim.x) s_hist[i] = 0;
+  key_and_or(kc, s_red, &a, &o);
+  const u64 diff = a ^ o;
+  if (diff == 0ull) return a;
+  const int top = 63 - __clzll((long long)diff);
+  u64 pmask = top == 63 ? 0ull : ~((2ull << top) - 1ull);
+  u64 prefix = a & pmask;
+  int shift = max(top - 7, 0);
+  for (int pass = 0;; ++pass) {
+    int* h = s_hist + (pass % 3) * 256;
+    int* hz = s_hist + ((pass + 1) % 3) * 256;
+    for (int i = tid; i < 256; i += (int)blockDim.x) hz[i] = 0;
+    kc.each([&](u64 key, bool v) {
+      if (v && (key & pmask) == prefix) atomicAdd(&h[(int)((key >> shift) & 0xffull)], 1);
+    });
+    __syncthreads();
+    int hq[8], s = 0;                                     // lane holds bins [8 lane, 8 lane + 8)
+    {
+      const int4 h0 = *reinterpret_cast<const int4*>(h + 8 * lane), h1 = *reinterpret_cast<const int4*>(h + 8 * lane + 4);
+      hq[0] = h0.x; hq[1] = h0.y; hq[2] = h0.z; hq[3] = h0.w;
+      hq[4] = h1.x; hq[5] = h1.y; hq[6] = h1.z; hq[7] = h1.w;
+    }
+#pragma unroll
+    for (int q = 0; q < 8; ++q) s += hq[q];
+    int suf = s;                                          // inclusive suffix over lanes >= lane
+#pragma unroll
+    for (int of = 1; of < 32; of <<= 1) {
+      const int t = __shfl_down_sync(kFull, suf, of);
+      if (lane + of < 32) suf += t;
+    }
+    const int above = suf - s;                            // keys in the bins of higher lanes
+    const bool hit = above < k && k <= suf;               // exactly one lane
+    int bin = 7, acc = above;
+#pragma unroll
+    for (int q = 7; q > 0; --q) {
+      if (bin == q && acc + hq[q] < k) {
+        acc += hq[q];
+        bin = q - 1;
       }
     }
-    __syncthreads();
-    prefix |= (u64)s_misc[0] << shift;
+    int pop = hq[0];
+#pragma unroll
+    for (int q = 1; q < 8; ++q) pop = bin == q ? hq[q] : pop;
+    const int src_lane = __ffs((int)__ballot_sync(kFull, hit)) - 1;
+    const int digit = __shfl_sync(kFull, 8 * lane + bin, src_lane);
+    const int krem = __shfl_sync(kFull, k - acc, src_lane);   // rank inside the bucket
+    pop = __shfl_sync(kFull, pop, src_lane);                  // bucket population
+    prefix |= (u64)digit << shift;
     pmask |= 0xffull << shift;
-    k = s_misc[1];
-    const bool whole = (s_misc[2] == k);
-    __syncthreads();
-    if (whole) break;  // every key of this bucket is kept: threshold = prefix with zero low bits
+    k = krem;
+    if (pop == k || shift == 0) break;
+    shift = max(shift - 8, 0);
   }
   return prefix;
+}
+
+struct SelectSmem {
+  int hist[3 * 256];
+  unsigned red[128];
+};
+template <int NK>
+__device__ __forceinline__ u64 select_kth(const KeyCache<NK>& kc, int k, SelectSmem* S) {
+  return radix_select_kth(kc, k, S->hist, S->red);
 }
 
 struct BinParams {
@@ -222,63 +314,124 @@ struct BinParams {
   int* counts;        // [B][8] candidates per (image, level); re-armed here
   u64* bins;          // [B][C][class_cap]
   int* class_counts;  // [B][C]; re-armed by detect_rank_kernel
+  long long* dbg;
 };
 
-__global__ void __launch_bounds__(kBinThreads)
+__global__ void __maxnreg__(80)
 detect_bin_kernel(BinParams p) {
-  __shared__ int s_hist[256], s_misc[4];
+  __shared__ __align__(16) SelectSmem s_sel;
   const int l = blockIdx.x, b = blockIdx.y, tid = threadIdx.x;
   const GridDev& g = p.grid;
+#define BIN_DBG(k) do { if (p.dbg && tid == 0) p.dbg[(int64_t)(b * g.num_levels + l) * 16 + 10 + (k)] = clock64(); } while (0)
+  BIN_DBG(0);
   const u64* src = p.cand + (int64_t)b * p.coff[g.num_levels] + p.coff[l];
   const int nl = p.counts[b * RADET_MAX_LEVELS + l];
   __syncthreads();
   if (tid == 0) p.counts[b * RADET_MAX_LEVELS + l] = 0;  // re-arm for the next call
   if (nl == 0) return;
+  KeyCache<kBinNK> kc;
+  kc.load(src, nl);
   u64 kth = 0ull;
-  if (p.nms_pre > 0 && nl > p.nms_pre) kth = radix_select_kth(src, nl, p.nms_pre, s_hist, s_misc);  // radet_head.py:112-122
+  BIN_DBG(1);
+  if (p.nms_pre > 0 && nl > p.nms_pre) kth = select_kth(kc, p.nms_pre, &s_sel);  // radet_head.py:112-122
+  BIN_DBG(2);
   const int hw = g.h[l] * g.w[l];
-  // Class binning.  A global atomic with a return value per candidate is a ~1 us round trip on every thread's serial
-  // path (10 candidates per thread on the finest level); instead the CTA counts its candidates per class in shared
-  // memory, reserves one range per class with ONE global atomic each, and hands out the slots from shared memory.
-  // (The order inside a bin is irrelevant: class_nms_kernel sorts by key.)
+  const float* ioumap = p.maps.iou[l] + (int64_t)b * hw;
+  const unsigned C = (unsigned)p.C;
+  const bool need_ctr = p.cs_mode != 1;
+  const bool rest = nl > kBinNK * kBinThreads;             // keys beyond the register-resident ones
+  // Class binning.  A kept candidate takes its slot inside the CTA's share of its class from a shared-memory counter (one
+  // ATOMS per kept candidate, the result stays in a register); the CTA then reserves one range per class with ONE global
+  // atomic each.  (The order inside a bin is irrelevant: class_nms_kernel sorts by key.)
   constexpr int kBinClasses = 1024;
-  __shared__ int s_ccnt[kBinClasses], s_cbase[kBinClasses];
+  __shared__ int s_ccnt[kBinClasses], s_cbase[kBinClasses], s_creg[kBinClasses];
   const bool local = p.C <= kBinClasses;
+  int lslot[kBinNK];
+  float ctrx[kBinNK];
+  // the centerness gathers of the register-resident keys go first: they are in flight during the slot hand-out
+#pragma unroll
+  for (int j = 0; j < kBinNK; ++j) {
+    const bool keep = tid + j * kBinThreads < nl && kc.r[j] >= kth;
+    const unsigned flat = 0xffffffffu - (unsigned)(kc.r[j] & 0xffffffffull);
+    ctrx[j] = (keep && need_ctr) ? ioumap[flat / C] : 0.f;
+    lslot[j] = 0;
+  }
   if (local) {
     for (int c = tid; c < p.C; c += kBinThreads) s_ccnt[c] = 0;
     __syncthreads();
-    for (int i = tid; i < nl; i += kBinThreads) {
-      const u64 key = src[i];
-      if (key < kth) continue;
-      const unsigned flat = 0xffffffffu - (unsigned)(key & 0xffffffffull);
-      atomicAdd(&s_ccnt[flat % (unsigned)p.C], 1);
+#pragma unroll
+    for (int j = 0; j < kBinNK; ++j) {
+      const bool keep = tid + j * kBinThreads < nl && kc.r[j] >= kth;
+      const unsigned flat = 0xffffffffu - (unsigned)(kc.r[j] & 0xffffffffull);
+      if (keep) lslot[j] = atomicAdd(&s_ccnt[flat % C], 1);
+    }
+    if (rest) {                                            // block-uniform
+      __syncthreads();
+      for (int c = tid; c < p.C; c += kBinThreads) s_creg[c] = s_ccnt[c];
+      __syncthreads();
+      for (int base = kBinNK * kBinThreads; base < nl; base += 8 * kBinThreads) {
+        u64 t[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+          const int i = base + u * kBinThreads + tid;
+          t[u] = i < nl ? src[i] : 0ull;
+        }
+#pragma unroll
+        for (int u = 0; u < 8; ++u)
+          if (base + u * kBinThreads + tid < nl && t[u] >= kth)
+            atomicAdd(&s_ccnt[(0xffffffffu - (unsigned)(t[u] & 0xffffffffull)) % C], 1);
+      }
     }
     __syncthreads();
     for (int c = tid; c < p.C; c += kBinThreads) {
       const int n = s_ccnt[c];
       s_cbase[c] = n ? atomicAdd(&p.class_counts[b * p.C + c], n) : 0;
-      s_ccnt[c] = 0;
+      s_ccnt[c] = rest ? s_creg[c] : 0;                    // the rest continues behind the register-resident keys
     }
     __syncthreads();
   }
-#pragma unroll 4
-  for (int i = tid; i < nl; i += kBinThreads) {
-    const u64 key = src[i];
-    if (key < kth) continue;
+  BIN_DBG(3);
+  auto emit = [&](u64 key, float cx, int slot) {
     const float S = __uint_as_float((unsigned)(key >> 32));
     const unsigned flat = 0xffffffffu - (unsigned)(key & 0xffffffffull);
-    const int q = (int)(flat / (unsigned)p.C);
-    const int c = (int)(flat - (unsigned)q * (unsigned)p.C);
+    const int c = (int)(flat % C);
     float cs = S;
-    if (p.cs_mode != 1) {
-      const float ctr = sigmoid_rn(p.maps.iou[l][(int64_t)b * hw + q]);        // radet_head.py:109
+    if (need_ctr) {
+      const float ctr = sigmoid_rn(cx);                                         // radet_head.py:109
       cs = p.cs_mode == 0 ? __fmul_rn(S, ctr) : ctr;                            // vote_wrapper.py:14-21
     }
     const unsigned ord = ((unsigned)l << kOrdLevelShift) | flat;
-    const int slot = local ? s_cbase[c] + atomicAdd(&s_ccnt[c], 1) : atomicAdd(&p.class_counts[b * p.C + c], 1);
+    slot = local ? s_cbase[c] + slot : atomicAdd(&p.class_counts[b * p.C + c], 1);
     if (slot < p.class_cap)
       p.bins[((int64_t)b * p.C + c) * p.class_cap + slot] = ((u64)float_order_key(cs) << 32) | (u64)(0xffffffffu - ord);
+  };
+#pragma unroll
+  for (int j = 0; j < kBinNK; ++j)
+    if (tid + j * kBinThreads < nl && kc.r[j] >= kth) emit(kc.r[j], ctrx[j], lslot[j]);
+  if (rest) {
+    for (int base = kBinNK * kBinThreads; base < nl; base += 8 * kBinThreads) {   // eight at a time
+      u64 t[8];
+      float cx[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        const int i = base + u * kBinThreads + tid;
+        t[u] = i < nl ? src[i] : 0ull;
+      }
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        const bool keep = base + u * kBinThreads + tid < nl && t[u] >= kth;
+        const unsigned flat = 0xffffffffu - (unsigned)(t[u] & 0xffffffffull);
+        cx[u] = (keep && need_ctr) ? ioumap[flat / C] : 0.f;
+      }
+#pragma unroll
+      for (int u = 0; u < 8; ++u)
+        if (base + u * kBinThreads + tid < nl && t[u] >= kth) {
+          const unsigned flat = 0xffffffffu - (unsigned)(t[u] & 0xffffffffull);
+          emit(t[u], cx[u], local ? atomicAdd(&s_ccnt[flat % C], 1) : 0);
+        }
+    }
   }
+  BIN_DBG(4);
 }
 
 // ------------------------------------------------------------------------------------------------ 3. per-class NMS + vote
@@ -853,13 +1006,19 @@ struct RankParams {
   float* dets;          // [B][max_num][5]
   int64_t* labels;      // [B][max_num]
   int* num_dets;        // [B]
+  long long* dbg;
 };
+
+constexpr int kRankNK = 8;   // seeds a thread keeps in registers (images with <= 4096 seeds read them once)
 
 __global__ void __launch_bounds__(kRankThreads)
 detect_rank_kernel(RankParams p) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  __shared__ int s_hist[256], s_misc[4], s_tot;
+  __shared__ __align__(16) SelectSmem s_sel;
+  __shared__ int s_tot;
   const int b = blockIdx.x, tid = threadIdx.x;
+#define RANK_DBG(k) do { if (p.dbg && tid == 0) p.dbg[(int64_t)(64 + b) * 16 + 10 + (k)] = clock64(); } while (0)
+  RANK_DBG(0);
   u64* sel = reinterpret_cast<u64*>(smem_raw);          // [pad(max_num)] selected keys
   int* selidx = reinterpret_cast<int*>(sel + kRankMaxOut);  // position of each selected seed in the image's list
   const int S = min(p.img_seed_count[b], p.img_cap);
@@ -873,41 +1032,81 @@ detect_rank_kernel(RankParams p) {
   if (tid == 0) p.num_dets[b] = nkeep;
   if (nkeep == 0) return;
   const u64* all = p.seed_keys + (int64_t)b * p.img_cap;
+  KeyCache<kRankNK> kc;
+  kc.load(all, S);
   u64 kth = 0ull;
-  if (S > nkeep) kth = radix_select_kth(all, S, nkeep, s_hist, s_misc);
-  int npad = 32;
-  while (npad < nkeep) npad <<= 1;
-  for (int i = tid; i < npad; i += kRankThreads) {
-    sel[i] = 0ull;
-    selidx[i] = 0;
+  RANK_DBG(1);
+  if (S > nkeep) kth = select_kth(kc, nkeep, &s_sel);
+  __syncthreads();                                         // s_tot
+  RANK_DBG(2);
+  {
+    int slot_of[kRankNK];
+#pragma unroll
+    for (int j = 0; j < kRankNK; ++j) slot_of[j] = (tid + j * kRankThreads < S && kc.r[j] >= kth) ? atomicAdd(&s_tot, 1) : 0;
+#pragma unroll
+    for (int j = 0; j < kRankNK; ++j)
+      if (tid + j * kRankThreads < S && kc.r[j] >= kth) {
+        sel[slot_of[j]] = kc.r[j];
+        selidx[slot_of[j]] = tid + j * kRankThreads;
+      }
   }
-  __syncthreads();
-  for (int i = tid; i < S; i += kRankThreads) {
-    const u64 key = all[i];
-    if (key >= kth) {
+  for (int base = kRankNK * kRankThreads; base < S; base += kRankThreads) {
+    const int i = base + tid;
+    const u64 key = i < S ? all[i] : 0ull;
+    const bool keep = i < S && key >= kth;
+    if (keep) {
       const int slot = atomicAdd(&s_tot, 1);
       sel[slot] = key;
       selidx[slot] = i;
     }
   }
   __syncthreads();
-  // descending bitonic sort of (key, index) pairs
-  for (int k = 2; k <= npad; k <<= 1) {
-    for (int j = k >> 1; j > 0; j >>= 1) {
-      for (int t = tid; t < (npad >> 1); t += kRankThreads) {
-        const int i = ((t & ~(j - 1)) << 1) | (t & (j - 1));
-        const int ixj = i | j;
-        const bool desc = (i & k) == 0;
-        const u64 a = sel[i], bk = sel[ixj];
-        if ((a < bk) == desc) {
-          sel[i] = bk;
-          sel[ixj] = a;
-          const int ti = selidx[i];
-          selidx[i] = selidx[ixj];
-          selidx[ixj] = ti;
+  if (nkeep <= 256) {
+    // descending order by counting: rank = #{selected keys above mine} (unique keys), broadcast shared-memory reads, no
+    // barriers; two threads share a key and split the sweep
+    const int r = tid >> 1, half = tid & 1;
+    int rank = 0;
+    u64 mine = 0ull;
+    int mi = 0;
+    if (r < nkeep) {
+      mine = sel[r];
+      mi = selidx[r];
+      const int mid = (nkeep + 1) >> 1, j0 = half ? mid : 0, j1 = half ? nkeep : mid;
+      for (int j = j0; j < j1; ++j) rank += sel[j] > mine ? 1 : 0;
+    }
+    rank += __shfl_xor_sync(kFull, rank, 1);
+    __syncthreads();
+    if (r < nkeep && half == 0) {
+      sel[rank] = mine;
+      selidx[rank] = mi;
+    }
+    __syncthreads();
+  } else {
+    int npad = 32;
+    while (npad < nkeep) npad <<= 1;
+    for (int i = nkeep + tid; i < npad; i += kRankThreads) {
+      sel[i] = 0ull;
+      selidx[i] = 0;
+    }
+    __syncthreads();
+    // descending bitonic sort of (key, index) pairs
+    for (int k = 2; k <= npad; k <<= 1) {
+      for (int j = k >> 1; j > 0; j >>= 1) {
+        for (int t = tid; t < (npad >> 1); t += kRankThreads) {
+          const int i = ((t & ~(j - 1)) << 1) | (t & (j - 1));
+          const int ixj = i | j;
+          const bool desc = (i & k) == 0;
+          const u64 a = sel[i], bk = sel[ixj];
+          if ((a < bk) == desc) {
+            sel[i] = bk;
+            sel[ixj] = a;
+            const int ti = selidx[i];
+            selidx[i] = selidx[ixj];
+            selidx[ixj] = ti;
+          }
         }
+        __syncthreads();
       }
-      __syncthreads();
     }
   }
   for (int t = tid; t < nkeep * 5; t += kRankThreads) {
@@ -1135,6 +1334,7 @@ extern "C" int radet_get_bboxes(const radet_grid_t* grid, int32_t batch, int32_t
   bp.C = num_classes;
   bp.nms_pre = cfg->nms_pre;
   bp.cs_mode = cfg->cluster_score_mode;
+  bp.dbg = static_cast<long long*>(g_debug_buf);
   bp.class_cap = cap;
   bp.cand = w.cand;
   bp.counts = w.counts;
@@ -1182,6 +1382,7 @@ extern "C" int radet_get_bboxes(const radet_grid_t* grid, int32_t batch, int32_t
   rp.dets = dets;
   rp.labels = labels;
   rp.num_dets = num_dets;
+  rp.dbg = static_cast<long long*>(g_debug_buf);
   const size_t rank_smem = (size_t)kRankMaxOut * 12;
   cudaFuncSetAttribute(detect_rank_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rank_smem);
   detect_rank_kernel<<<batch, kRankThreads, rank_smem, st>>>(rp);
