@@ -450,6 +450,26 @@ assign_resolve_kernel(GridDev grid, const int* __restrict__ gt_offsets, const fl
   int64_t* idx = out_idx + (int64_t)b * P;
   float* wt = out_w + (int64_t)b * P;
 
+  // The worker warps' first batch of candidate words does not depend on anything this CTA computes: issue the loads now,
+  // they land while the GT offsets / boxes are fetched and ranked (three dependent round trips to L2 otherwise).
+  constexpr int kWW0 = (kResolveThreads - 32) / 32;
+  uint32_t pre_any[8];
+  {
+    const uint32_t* bits0 = pair_bits + (int64_t)b * P * (2 * W32);
+    const int span0 = min(P, kWW0 * 1024);
+    const int chunk0 = (((span0 + kWW0 - 1) / kWW0) + 31) & ~31;
+    const int c00 = (wid - 1) * chunk0;
+    const int nit0 = max(0, min(chunk0, span0 - c00) + 31) >> 5;
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      const int p = c00 + u * 32 + lane;
+      pre_any[u] = 0u;
+      if (wid > 0 && u < nit0 && p < span0) {
+#pragma unroll
+        for (int w = 0; w < W32; ++w) pre_any[u] |= bits0[(int64_t)p * (2 * W32) + w];
+      }
+    }
+  }
   ResolveSmem* S = reinterpret_cast<ResolveSmem*>(smem_raw);
   unsigned char* cur = smem_raw + ((sizeof(ResolveSmem) + 15) & ~size_t(15));
   unsigned long long* s_xbuf = reinterpret_cast<unsigned long long*>(cur); cur += 312 * 8;
@@ -548,7 +568,9 @@ assign_resolve_kernel(GridDev grid, const int* __restrict__ gt_offsets, const fl
         for (int u = 0; u < 8; ++u) {
           const int p = c0 + (it0 + u) * 32 + lane;
           any[u] = 0u;
-          if (it0 + u < nit && p < base + span) {
+          if (base == 0 && it0 == 0) {
+            any[u] = pre_any[u];                                    // loaded at the top of the kernel
+          } else if (it0 + u < nit && p < base + span) {
 #pragma unroll
             for (int w = 0; w < W32; ++w) any[u] |= bits[(int64_t)p * (2 * W32) + w];
           }
@@ -579,10 +601,22 @@ assign_resolve_kernel(GridDev grid, const int* __restrict__ gt_offsets, const fl
       const int before = __reduce_add_sync(kFull, lane < ww ? wtot : 0);
       const int total = __reduce_add_sync(kFull, wtot);
       const int ex = M + before + inc - cnt;
-      for (int it = 0; it < nit; ++it) {
-        const uint32_t bal = __shfl_sync(kFull, myword, it);
-        const int off = __shfl_sync(kFull, ex, it);
-        if ((bal >> lane) & 1u) list[off + __popc(bal & ((1u << lane) - 1u))] = (uint32_t)(c0 + it * 32 + lane);
+      const int wsum = __shfl_sync(kFull, inc, 31);                 // candidates of this warp's chunk
+      if (wsum <= 4 * nit) {
+        // sparse (the usual case: a few percent of the points are candidates): lane `it` walks the set bits of its own word
+        uint32_t wbits = myword;
+        int o = ex;
+        while (wbits) {
+          const int bpos = __ffs((int)wbits) - 1;
+          wbits &= wbits - 1u;
+          list[o++] = (uint32_t)(c0 + lane * 32 + bpos);
+        }
+      } else {
+        for (int it = 0; it < nit; ++it) {
+          const uint32_t bal = __shfl_sync(kFull, myword, it);
+          const int off = __shfl_sync(kFull, ex, it);
+          if ((bal >> lane) & 1u) list[off + __popc(bal & ((1u << lane) - 1u))] = (uint32_t)(c0 + it * 32 + lane);
+        }
       }
       M += total;
     }
@@ -714,11 +748,12 @@ assign_resolve_kernel(GridDev grid, const int* __restrict__ gt_offsets, const fl
       int* s_g = S->found;
       int xi = ms.xi, nx = ms.nx;
       auto search_t = [&](unsigned long long X, int m) -> int {
-        const unsigned long long hi = __umul64hi(X << 11, (unsigned long long)m);   // floor(X*m / 2^53), see cdf_search53
-        const unsigned long long lo = (X << 11) * (unsigned long long)m;
+        const unsigned long long Xs = X << 11, um = (unsigned long long)(unsigned)m;   // m < 2^31: two 32 x 32 products
+        const unsigned long long p0 = (Xs & 0xffffffffull) * um, p1 = (Xs >> 32) * um + (p0 >> 32);
+        const unsigned long long lo = (p1 << 32) | (p0 & 0xffffffffull);            // low 64 bits of Xs * m
         const unsigned long long R = (0ull - lo) >> 11;
-        int t = (int)hi;
-        if (lo != 0ull && R <= (unsigned long long)m) t = cdf_search_slow(X, m);
+        int t = (int)(p1 >> 32);                                                    // floor(X*m / 2^53), see cdf_search53
+        if (lo != 0ull && R <= um) t = cdf_search_slow(X, m);
         return t;
       };
       unsigned long long Xc = s_xbuf[min(xi + lane, 311)];     // uniforms at the current stream position
