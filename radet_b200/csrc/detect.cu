@@ -317,7 +317,7 @@ struct BinParams {
   long long* dbg;
 };
 
-__global__ void __maxnreg__(80)
+__global__ void __launch_bounds__(kBinThreads, 2)
 detect_bin_kernel(BinParams p) {
   __shared__ __align__(16) SelectSmem s_sel;
   const int l = blockIdx.x, b = blockIdx.y, tid = threadIdx.x;
@@ -339,97 +339,80 @@ detect_bin_kernel(BinParams p) {
   const float* ioumap = p.maps.iou[l] + (int64_t)b * hw;
   const unsigned C = (unsigned)p.C;
   const bool need_ctr = p.cs_mode != 1;
-  const bool rest = nl > kBinNK * kBinThreads;             // keys beyond the register-resident ones
-  // Class binning.  A kept candidate takes its slot inside the CTA's share of its class from a shared-memory counter (one
-  // ATOMS per kept candidate, the result stays in a register); the CTA then reserves one range per class with ONE global
-  // atomic each.  (The order inside a bin is irrelevant: class_nms_kernel sorts by key.)
+  // Class binning.  The CTA counts its kept candidates per class in shared memory (ATOMS.POPC.INC: lanes of a warp that hit
+  // the same class are added in one operation), reserves one range per class with ONE global atomic each, and hands out
+  // the slots from shared memory.  (The order inside a bin is irrelevant: class_nms_kernel sorts by key.)
+  // Register budget: this CTA shares its SM with other steps' kernels (64 registers x 512 threads); the emission below
+  // therefore works in groups of four keys (four centerness gathers and four slot requests in flight) instead of
+  // keeping twelve slots and twelve gathered values live.
   constexpr int kBinClasses = 1024;
-  __shared__ int s_ccnt[kBinClasses], s_cbase[kBinClasses], s_creg[kBinClasses];
+  __shared__ int s_ccnt[kBinClasses], s_cbase[kBinClasses];
   const bool local = p.C <= kBinClasses;
-  int lslot[kBinNK];
-  float ctrx[kBinNK];
-  // the centerness gathers of the register-resident keys go first: they are in flight during the slot hand-out
-#pragma unroll
-  for (int j = 0; j < kBinNK; ++j) {
-    const bool keep = tid + j * kBinThreads < nl && kc.r[j] >= kth;
-    const unsigned flat = 0xffffffffu - (unsigned)(kc.r[j] & 0xffffffffull);
-    ctrx[j] = (keep && need_ctr) ? ioumap[flat / C] : 0.f;
-    lslot[j] = 0;
-  }
   if (local) {
     for (int c = tid; c < p.C; c += kBinThreads) s_ccnt[c] = 0;
     __syncthreads();
-#pragma unroll
-    for (int j = 0; j < kBinNK; ++j) {
-      const bool keep = tid + j * kBinThreads < nl && kc.r[j] >= kth;
-      const unsigned flat = 0xffffffffu - (unsigned)(kc.r[j] & 0xffffffffull);
-      if (keep) lslot[j] = atomicAdd(&s_ccnt[flat % C], 1);
-    }
-    if (rest) {                                            // block-uniform
-      __syncthreads();
-      for (int c = tid; c < p.C; c += kBinThreads) s_creg[c] = s_ccnt[c];
-      __syncthreads();
-      for (int base = kBinNK * kBinThreads; base < nl; base += 8 * kBinThreads) {
-        u64 t[8];
-#pragma unroll
-        for (int u = 0; u < 8; ++u) {
-          const int i = base + u * kBinThreads + tid;
-          t[u] = i < nl ? src[i] : 0ull;
-        }
-#pragma unroll
-        for (int u = 0; u < 8; ++u)
-          if (base + u * kBinThreads + tid < nl && t[u] >= kth)
-            atomicAdd(&s_ccnt[(0xffffffffu - (unsigned)(t[u] & 0xffffffffull)) % C], 1);
-      }
-    }
+    kc.each([&](u64 key, bool v) {
+      if (v && key >= kth) atomicAdd(&s_ccnt[(0xffffffffu - (unsigned)(key & 0xffffffffull)) % C], 1);
+    });
     __syncthreads();
     for (int c = tid; c < p.C; c += kBinThreads) {
       const int n = s_ccnt[c];
       s_cbase[c] = n ? atomicAdd(&p.class_counts[b * p.C + c], n) : 0;
-      s_ccnt[c] = rest ? s_creg[c] : 0;                    // the rest continues behind the register-resident keys
+      s_ccnt[c] = 0;
     }
     __syncthreads();
   }
   BIN_DBG(3);
-  auto emit = [&](u64 key, float cx, int slot) {
-    const float S = __uint_as_float((unsigned)(key >> 32));
-    const unsigned flat = 0xffffffffu - (unsigned)(key & 0xffffffffull);
-    const int c = (int)(flat % C);
-    float cs = S;
-    if (need_ctr) {
-      const float ctr = sigmoid_rn(cx);                                         // radet_head.py:109
-      cs = p.cs_mode == 0 ? __fmul_rn(S, ctr) : ctr;                            // vote_wrapper.py:14-21
+  auto emit4 = [&](const u64 (&key)[4], const bool (&keep)[4]) {
+    float cx[4];
+    int slot[4], cl[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const unsigned flat = 0xffffffffu - (unsigned)(key[u] & 0xffffffffull);
+      const unsigned q = flat / C;
+      cl[u] = (int)(flat - q * C);
+      cx[u] = (keep[u] && need_ctr) ? ioumap[q] : 0.f;
+      slot[u] = 0;
+      if (keep[u]) slot[u] = local ? atomicAdd(&s_ccnt[cl[u]], 1) : atomicAdd(&p.class_counts[b * p.C + cl[u]], 1);
     }
-    const unsigned ord = ((unsigned)l << kOrdLevelShift) | flat;
-    slot = local ? s_cbase[c] + slot : atomicAdd(&p.class_counts[b * p.C + c], 1);
-    if (slot < p.class_cap)
-      p.bins[((int64_t)b * p.C + c) * p.class_cap + slot] = ((u64)float_order_key(cs) << 32) | (u64)(0xffffffffu - ord);
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      if (!keep[u]) continue;
+      const float S = __uint_as_float((unsigned)(key[u] >> 32));
+      const unsigned flat = 0xffffffffu - (unsigned)(key[u] & 0xffffffffull);
+      float cs = S;
+      if (need_ctr) {
+        const float ctr = sigmoid_rn(cx[u]);                                    // radet_head.py:109
+        cs = p.cs_mode == 0 ? __fmul_rn(S, ctr) : ctr;                          // vote_wrapper.py:14-21
+      }
+      const unsigned ord = ((unsigned)l << kOrdLevelShift) | flat;
+      const int sl = local ? s_cbase[cl[u]] + slot[u] : slot[u];
+      if (sl < p.class_cap)
+        p.bins[((int64_t)b * p.C + cl[u]) * p.class_cap + sl] = ((u64)float_order_key(cs) << 32) | (u64)(0xffffffffu - ord);
+    }
   };
 #pragma unroll
-  for (int j = 0; j < kBinNK; ++j)
-    if (tid + j * kBinThreads < nl && kc.r[j] >= kth) emit(kc.r[j], ctrx[j], lslot[j]);
-  if (rest) {
-    for (int base = kBinNK * kBinThreads; base < nl; base += 8 * kBinThreads) {   // eight at a time
-      u64 t[8];
-      float cx[8];
+  for (int j0 = 0; j0 < kBinNK; j0 += 4) {
+    u64 key[4];
+    bool keep[4];
 #pragma unroll
-      for (int u = 0; u < 8; ++u) {
-        const int i = base + u * kBinThreads + tid;
-        t[u] = i < nl ? src[i] : 0ull;
-      }
-#pragma unroll
-      for (int u = 0; u < 8; ++u) {
-        const bool keep = base + u * kBinThreads + tid < nl && t[u] >= kth;
-        const unsigned flat = 0xffffffffu - (unsigned)(t[u] & 0xffffffffull);
-        cx[u] = (keep && need_ctr) ? ioumap[flat / C] : 0.f;
-      }
-#pragma unroll
-      for (int u = 0; u < 8; ++u)
-        if (base + u * kBinThreads + tid < nl && t[u] >= kth) {
-          const unsigned flat = 0xffffffffu - (unsigned)(t[u] & 0xffffffffull);
-          emit(t[u], cx[u], local ? atomicAdd(&s_ccnt[flat % C], 1) : 0);
-        }
+    for (int u = 0; u < 4; ++u) {
+      key[u] = kc.r[j0 + u];
+      keep[u] = tid + (j0 + u) * kBinThreads < nl && key[u] >= kth;
     }
+    emit4(key, keep);
+  }
+  for (int base = kBinNK * kBinThreads; base < nl; base += 4 * kBinThreads) {   // keys beyond the register-resident ones
+    u64 key[4];
+    bool keep[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int i = base + u * kBinThreads + tid;
+      key[u] = i < nl ? src[i] : 0ull;
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) keep[u] = base + u * kBinThreads + tid < nl && key[u] >= kth;
+    emit4(key, keep);
   }
   BIN_DBG(4);
 }
