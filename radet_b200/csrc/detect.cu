@@ -183,13 +183,16 @@ struct KeyCache {
       r[j] = i < n ? src[i] : 0ull;
     }
   }
-  // f(key, valid) for every key slot of this thread; all threads of the CTA make the same number of calls, so f may
-  // use full-warp collectives.
+  // f(key, valid) for the key slots of this thread; all threads of a WARP make the same number of calls, so f may use
+  // full-warp collectives (not block barriers).
   template <typename F>
   __device__ __forceinline__ void each(F&& f) const {
     const int T = (int)blockDim.x;
 #pragma unroll
-    for (int j = 0; j < NK; ++j) f(r[j], (int)threadIdx.x + j * T < n);
+    for (int j = 0; j < NK; ++j) {
+      if (((int)threadIdx.x & ~31) + j * T >= n) break;   // warp-uniform: none of this warp's keys in slot j or beyond
+      f(r[j], (int)threadIdx.x + j * T < n);
+    }
     for (int base = NK * T; base < n; base += 8 * T) {
       u64 t[8];
 #pragma unroll
@@ -339,80 +342,140 @@ detect_bin_kernel(BinParams p) {
   const float* ioumap = p.maps.iou[l] + (int64_t)b * hw;
   const unsigned C = (unsigned)p.C;
   const bool need_ctr = p.cs_mode != 1;
-  // Class binning.  The CTA counts its kept candidates per class in shared memory (ATOMS.POPC.INC: lanes of a warp that hit
-  // the same class are added in one operation), reserves one range per class with ONE global atomic each, and hands out
-  // the slots from shared memory.  (The order inside a bin is irrelevant: class_nms_kernel sorts by key.)
-  // Register budget: this CTA shares its SM with other steps' kernels (64 registers x 512 threads); the emission below
-  // therefore works in groups of four keys (four centerness gathers and four slot requests in flight) instead of
-  // keeping twelve slots and twelve gathered values live.
-  constexpr int kBinClasses = 1024;
+  // flat = point * C + class: division by the (runtime) class count as a multiplication, exact for flat * C < 2^40
+  // (flat < 2^27, C <= 2^13; plain division beyond): q = flat * ceil(2^40 / C) >> 40
+  const u64 cmagic = ((1ull << 40) + C - 1ull) / C;
+  auto split = [&](unsigned flat, unsigned& q, int& cl) {
+    q = C <= 8192u ? (unsigned)(((u64)flat * cmagic) >> 40) : flat / C;
+    cl = (int)(flat - q * C);
+  };
+  // Class binning.  The kept candidates (a fifth of the keys on the finest level) are first compacted into shared memory
+  // -- warp ballots, no atomics -- so that the two sweeps below run over ~2 keys per thread with full lanes instead of 12
+  // mostly idle ones.  The CTA counts them per class in shared memory (ATOMS.POPC.INC: lanes of a warp that hit the same
+  // class are added in one operation), reserves one range per class with ONE global atomic each, and hands out the slots
+  // from shared memory.  (The order inside a bin is irrelevant: class_nms_kernel sorts by key.)
+  constexpr int kBinClasses = 1024, kKeepCap = 2048;
   __shared__ int s_ccnt[kBinClasses], s_cbase[kBinClasses];
+  __shared__ u64 s_keep[kKeepCap];
+  __shared__ int s_wcnt[32], s_cursor;
   const bool local = p.C <= kBinClasses;
-  if (local) {
+  const int lane = tid & 31, wid = tid >> 5;
+  const unsigned lt = (1u << lane) - 1u;
+  const int nkeep = kth != 0ull ? p.nms_pre : nl;            // unique keys: exactly nms_pre survive the selection
+  auto emit = [&](u64 key, float cx, int cl, int sl) {
+    const float S = __uint_as_float((unsigned)(key >> 32));
+    const unsigned flat = 0xffffffffu - (unsigned)(key & 0xffffffffull);
+    float cs = S;
+    if (need_ctr) {
+      const float ctr = sigmoid_rn(cx);                                       // radet_head.py:109
+      cs = p.cs_mode == 0 ? __fmul_rn(S, ctr) : ctr;                          // vote_wrapper.py:14-21
+    }
+    const unsigned ord = ((unsigned)l << kOrdLevelShift) | flat;
+    if (sl < p.class_cap)
+      p.bins[((int64_t)b * p.C + cl) * p.class_cap + sl] = ((u64)float_order_key(cs) << 32) | (u64)(0xffffffffu - ord);
+  };
+  if (local && nkeep <= kKeepCap) {
     for (int c = tid; c < p.C; c += kBinThreads) s_ccnt[c] = 0;
+    int wc = 0;
+#pragma unroll
+    for (int j = 0; j < kBinNK; ++j) {
+      if (wid * 32 + j * kBinThreads >= nl) break;          // warp-uniform: no key of this warp in slot j or beyond
+      wc += __popc(__ballot_sync(kFull, tid + j * kBinThreads < nl && kc.r[j] >= kth));
+    }
+    if (lane == 0) s_wcnt[wid] = wc;
     __syncthreads();
-    kc.each([&](u64 key, bool v) {
-      if (v && key >= kth) atomicAdd(&s_ccnt[(0xffffffffu - (unsigned)(key & 0xffffffffull)) % C], 1);
-    });
+    int wbase = 0, total = 0;
+    {
+      const int v = lane < kBinThreads / 32 ? s_wcnt[lane] : 0;
+      wbase = __reduce_add_sync(kFull, lane < wid ? v : 0);
+      total = __reduce_add_sync(kFull, v);
+    }
+    if (tid == 0) s_cursor = total;
+#pragma unroll
+    for (int j = 0; j < kBinNK; ++j) {
+      if (wid * 32 + j * kBinThreads >= nl) break;
+      const bool keep = tid + j * kBinThreads < nl && kc.r[j] >= kth;
+      const unsigned bal = __ballot_sync(kFull, keep);
+      if (keep) s_keep[wbase + __popc(bal & lt)] = kc.r[j];
+      wbase += __popc(bal);
+    }
+    __syncthreads();
+    for (int base = kBinNK * kBinThreads; base < nl; base += 8 * kBinThreads) {   // keys beyond the register-resident ones
+      u64 t[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        const int i = base + u * kBinThreads + tid;
+        t[u] = i < nl ? src[i] : 0ull;
+      }
+#pragma unroll
+      for (int u = 0; u < 8; ++u)
+        if (base + u * kBinThreads + tid < nl && t[u] >= kth) s_keep[atomicAdd(&s_cursor, 1)] = t[u];
+    }
+    if (nl > kBinNK * kBinThreads) __syncthreads();
+    // per-class counts, one reservation per class, slots
+    for (int i = tid; i < nkeep; i += kBinThreads) {
+      unsigned q;
+      int cl;
+      split(0xffffffffu - (unsigned)(s_keep[i] & 0xffffffffull), q, cl);
+      atomicAdd(&s_ccnt[cl], 1);
+    }
     __syncthreads();
     for (int c = tid; c < p.C; c += kBinThreads) {
       const int n = s_ccnt[c];
       s_cbase[c] = n ? atomicAdd(&p.class_counts[b * p.C + c], n) : 0;
       s_ccnt[c] = 0;
     }
-    __syncthreads();
-  }
-  BIN_DBG(3);
-  auto emit4 = [&](const u64 (&key)[4], const bool (&keep)[4]) {
+    BIN_DBG(3);
+    // the centerness gathers of a thread's (<= 4) keys are in flight while the reservations return
+    static_assert(kKeepCap == 4 * kBinThreads, "one trip of four keys per thread covers the staging area");
+    u64 key[4];
     float cx[4];
-    int slot[4], cl[4];
+    int cl[4];
 #pragma unroll
     for (int u = 0; u < 4; ++u) {
-      const unsigned flat = 0xffffffffu - (unsigned)(key[u] & 0xffffffffull);
-      const unsigned q = flat / C;
-      cl[u] = (int)(flat - q * C);
-      cx[u] = (keep[u] && need_ctr) ? ioumap[q] : 0.f;
-      slot[u] = 0;
-      if (keep[u]) slot[u] = local ? atomicAdd(&s_ccnt[cl[u]], 1) : atomicAdd(&p.class_counts[b * p.C + cl[u]], 1);
+      const int i = tid + u * kBinThreads;
+      key[u] = i < nkeep ? s_keep[i] : 0ull;
+      unsigned q;
+      split(0xffffffffu - (unsigned)(key[u] & 0xffffffffull), q, cl[u]);
+      cx[u] = (i < nkeep && need_ctr) ? ioumap[q] : 0.f;
     }
+    __syncthreads();                                         // s_cbase
 #pragma unroll
-    for (int u = 0; u < 4; ++u) {
-      if (!keep[u]) continue;
-      const float S = __uint_as_float((unsigned)(key[u] >> 32));
-      const unsigned flat = 0xffffffffu - (unsigned)(key[u] & 0xffffffffull);
-      float cs = S;
-      if (need_ctr) {
-        const float ctr = sigmoid_rn(cx[u]);                                    // radet_head.py:109
-        cs = p.cs_mode == 0 ? __fmul_rn(S, ctr) : ctr;                          // vote_wrapper.py:14-21
+    for (int u = 0; u < 4; ++u)
+      if (tid + u * kBinThreads < nkeep) emit(key[u], cx[u], cl[u], s_cbase[cl[u]] + atomicAdd(&s_ccnt[cl[u]], 1));
+  } else {
+    // more kept candidates than the staging area holds (nms_pre > 2048 or no per-level limit), or more than 1024 classes:
+    // every key takes its slot with an atomic of its own
+    if (local) {
+      for (int c = tid; c < p.C; c += kBinThreads) s_ccnt[c] = 0;
+      __syncthreads();
+      kc.each([&](u64 key, bool v) {
+        if (v && key >= kth) {
+          unsigned q;
+          int cl;
+          split(0xffffffffu - (unsigned)(key & 0xffffffffull), q, cl);
+          atomicAdd(&s_ccnt[cl], 1);
+        }
+      });
+      __syncthreads();
+      for (int c = tid; c < p.C; c += kBinThreads) {
+        const int n = s_ccnt[c];
+        s_cbase[c] = n ? atomicAdd(&p.class_counts[b * p.C + c], n) : 0;
+        s_ccnt[c] = 0;
       }
-      const unsigned ord = ((unsigned)l << kOrdLevelShift) | flat;
-      const int sl = local ? s_cbase[cl[u]] + slot[u] : slot[u];
-      if (sl < p.class_cap)
-        p.bins[((int64_t)b * p.C + cl[u]) * p.class_cap + sl] = ((u64)float_order_key(cs) << 32) | (u64)(0xffffffffu - ord);
+      __syncthreads();
     }
-  };
-#pragma unroll
-  for (int j0 = 0; j0 < kBinNK; j0 += 4) {
-    u64 key[4];
-    bool keep[4];
-#pragma unroll
-    for (int u = 0; u < 4; ++u) {
-      key[u] = kc.r[j0 + u];
-      keep[u] = tid + (j0 + u) * kBinThreads < nl && key[u] >= kth;
-    }
-    emit4(key, keep);
-  }
-  for (int base = kBinNK * kBinThreads; base < nl; base += 4 * kBinThreads) {   // keys beyond the register-resident ones
-    u64 key[4];
-    bool keep[4];
-#pragma unroll
-    for (int u = 0; u < 4; ++u) {
-      const int i = base + u * kBinThreads + tid;
-      key[u] = i < nl ? src[i] : 0ull;
-    }
-#pragma unroll
-    for (int u = 0; u < 4; ++u) keep[u] = base + u * kBinThreads + tid < nl && key[u] >= kth;
-    emit4(key, keep);
+    BIN_DBG(3);
+    kc.each([&](u64 key, bool v) {
+      if (v && key >= kth) {
+        unsigned q;
+        int cl;
+        split(0xffffffffu - (unsigned)(key & 0xffffffffull), q, cl);
+        const float cx = need_ctr ? ioumap[q] : 0.f;
+        const int sl = local ? s_cbase[cl] + atomicAdd(&s_ccnt[cl], 1) : atomicAdd(&p.class_counts[b * p.C + cl], 1);
+        emit(key, cx, cl, sl);
+      }
+    });
   }
   BIN_DBG(4);
 }
