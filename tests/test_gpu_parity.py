@@ -776,6 +776,33 @@ def test_get_bboxes_low_threshold_fills_the_select_staging():
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("nms_pre", [300, 3000, -1])
+def test_get_candidates_many_candidates_per_level(nms_pre):
+    """~100 k candidates on the finest level of a 640x480 image (score_thr 1e-4): detect_bin_kernel reads the keys beyond
+    its register-resident 6 144 from memory, and the three ways it hands out class slots all run -- kept keys compacted in
+    shared memory (nms_pre 300), more kept keys than the staging area holds (nms_pre 3 000) and no per-level limit (-1).
+    The rows [box, score*centerness, prior] + class are compared with the oracle as sets, bit for bit."""
+    wl, batch, idx_l, w_l, ho = _head_inputs("cfg1")
+    cls, bbox, iou = _to_dev(ho)
+    thr = 1e-4
+    shp = torch.tensor([[im.H, im.W] for im in batch], dtype=torch.int32, device=DEV)
+    sf = torch.ones((len(batch), 4), device=DEV)
+    cfg = F.DetectConfig(score_thr=thr, nms_pre=nms_pre, nms_type="vote", **{k: v for k, v in NMS_CFG.items() if k != "sima"})
+    rows, cats, num = F.get_candidates(GEOM, wl.C, cls, bbox, iou, shp, sf, cfg, rescale=True)
+    for b, im in enumerate(batch):
+        maps = ([m[b] for m in ho.cls], [m[b] for m in ho.bbox], [m[b] for m in ho.iou])
+        assert int((torch.sigmoid(cls[0][b]) > thr).sum()) > 6144 * 4
+        bx, sc, ctr, ocats, anc = orc.select_candidates(*maps, (im.H, im.W, 3), np.ones(4, np.float32), thr, nms_pre)
+        full = np.concatenate([bx, (sc * ctr)[:, None], anc], 1).astype(np.float32)
+        k = int(num[b])
+        assert k == full.shape[0]
+        r, c = rows[b, :k].cpu().numpy(), cats[b, :k].cpu().numpy()
+        o = np.lexsort((c, r[:, 8], r[:, 7], r[:, 6], r[:, 5], r[:, 4]))
+        oo = np.lexsort((ocats, full[:, 8], full[:, 7], full[:, 6], full[:, 5], full[:, 4]))
+        assert np.array_equal(r[o].view(np.uint32), full[oo].view(np.uint32)) and np.array_equal(c[o], ocats[oo])
+
+
+@pytest.mark.gpu
 def test_whole_path_coco_like_shape():
     """80 classes, 40 GT per image (two 32-bit GT words), a 333x500 image (every level size odd, planes not 16-byte
     tileable -> the register-pipelined dense kernel, the scalar select path): assignment bit-exact, loss / gradients
