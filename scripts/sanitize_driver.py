@@ -54,6 +54,24 @@ for wl, fused in ((syn.Workload("s1", 480, 640, 30, 2, 40, 40, 3), False), (syn.
         dets, dl, num = F.get_bboxes(geom, wl.C, cls, bbox, iou, shp, sf, cfg, rescale=True)
     rows, cats, n = F.get_candidates(geom, wl.C, cls, bbox, iou, shp, sf, cfg, rescale=True)
     F.bbox2result_batch(dets, dl, num, wl.C, xywh=True)
+# detect_bin_kernel beyond its register-resident keys: ~100 k candidates on the finest level (score_thr 1e-4), kept keys
+# compacted in shared memory (nms_pre 300), more than the staging area holds (3 000), no per-level limit (-1); many seeds
+# per image through detect_rank_kernel (max_per_img 1 000 -> bitonic path)
+wl = syn.Workload("s4", 480, 640, 21, 1, 4, 4, 9)
+batch = syn.make_batch(wl)
+shapes = geom.level_shapes(wl.H, wl.W)
+Pn = geom.num_points(shapes)
+ho = syn.make_head_outputs(wl, batch, [np.zeros(Pn, np.int64) for _ in batch])
+T = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)
+cls, bbox, iou = [T(m) for m in ho.cls], [T(m) for m in ho.bbox], [T(m) for m in ho.iou]
+shp = torch.tensor([[wl.H, wl.W]] * len(batch), dtype=torch.int32, device=dev)
+sf = torch.ones((len(batch), 4), device=dev)
+for nms_pre in (300, 3000, -1):
+    cfg = F.DetectConfig(score_thr=1e-4, nms_pre=nms_pre, max_per_img=1000, nms_type="vote", iou_threshold=0.65,
+                         cluster_score=["cls", "iou"], vote_score=["iou", "cls"])
+    F.get_candidates(geom, wl.C, cls, bbox, iou, shp, sf, cfg, rescale=True)
+    if nms_pre == 300:
+        F.get_bboxes(geom, wl.C, cls, bbox, iou, shp, sf, cfg, rescale=True)
 # radet.ops lists (shared-memory and global-memory variants of nms_list_kernel), standalone coder / losses
 rs = np.random.RandomState(0)
 for n in (300, 6000):
