@@ -10,8 +10,12 @@ BASE_KEYS = {"metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_ste
              "dtype", "data", "config"}
 
 
-def test_committed_bench_line_has_the_contract_keys():
-    line = open(os.path.join(ROOT, "profiles", "r1_bench_final.json")).read().strip().splitlines()[-1]
+import pytest
+
+
+@pytest.mark.parametrize("name", ["r1_bench_final.json", "r2b_bench_n1.json", "r2c_bench_n1.json", "r2c_bench_n1_long.json"])
+def test_committed_bench_line_has_the_contract_keys(name):
+    line = open(os.path.join(ROOT, "profiles", name)).read().strip().splitlines()[-1]
     d = json.loads(line)
     assert BASE_KEYS <= set(d)
     assert d["unit"] == "images/s" and d["higher_is_better"] is True and d["scaling"] == "weak" and d["vs_baseline"] is None
@@ -20,7 +24,7 @@ def test_committed_bench_line_has_the_contract_keys():
     assert {"bound", "achieved", "peak", "unit", "frac", "traffic"} <= set(r) and r["bound"] == "hbm" and r["unit"] == "GB/s"
     assert abs(r["frac"] - r["achieved"] / r["peak"]) < 1e-9
     c = d["cpu_baseline"]
-    assert {"value", "unit", "cores", "kind", "sample"} <= set(c) and c["kind"] in ("port", "reference")
+    assert {"value", "unit", "cores", "kind", "sample"} <= set(c) and c["kind"] in ("port", "reference", "reference+port")
     e = d["e2e"]
     assert {"value", "unit", "h2d_bytes_per_step", "d2h_bytes_per_step"} <= set(e) and e["h2d_bytes_per_step"] > 0 and e["d2h_bytes_per_step"] > 0
     assert d["gpu_launches"] == d["launches_per_step"] * d["steps"] > 0
